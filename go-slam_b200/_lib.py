@@ -1,0 +1,107 @@
+"""ctypes binding of libgoslam_b200.so (C-ABI in include/goslam_b200.h).
+
+No CPU fallback lives here or anywhere else in the product path: if the shared library is
+missing it is built with nvcc (go-slam_b200/build.py); if a kernel cannot launch the caller
+gets a RuntimeError.
+"""
+import ctypes
+import os
+import threading
+
+from . import build as _build
+
+_lock = threading.Lock()
+_LIB = None
+
+c_void_p, c_int, c_float, c_size_t, c_int64 = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_int64)
+
+
+class NeusParams(ctypes.Structure):
+    _fields_ = [
+        ("grid", c_void_p), ("sdf_w", c_void_p), ("sdf_b", c_void_p), ("color_B", c_void_p),
+        ("mlp_w", c_void_p), ("bound", c_float * 6), ("rt_bound", c_float * 6),
+        ("inv_s", c_float), ("cos_anneal_ratio", c_float),
+    ]
+
+
+class NeusOut(ctypes.Structure):
+    _fields_ = [
+        ("color", c_void_p), ("depth", c_void_p), ("depth_variance", c_void_p),
+        ("normal", c_void_p), ("weight_sum", c_void_p), ("sdf", c_void_p), ("z_mid", c_void_p),
+        ("gradient_error", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/goslam_b200.h declares
+SIGNATURES = {
+    "goslam_version": (c_int, []),
+    "goslam_sm_arch": (c_int, []),
+    "goslam_strerror": (ctypes.c_char_p, [c_int]),
+    "goslam_corr_index_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    "goslam_corr_pyramid_lookup": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    "goslam_corr_build_workspace_bytes": (c_size_t, [c_int] * 4),
+    "goslam_corr_build": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "goslam_corr_build_f32": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "goslam_altcorr_forward": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
+    "goslam_frame_distance": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_float, c_void_p]),
+    "goslam_projmap": (c_int, [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),
+    "goslam_iproj": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
+    "goslam_depth_filter": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),
+    "goslam_reproject": (c_int, [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),
+    "goslam_ba_workspace_bytes": (c_size_t, [c_int] * 6),
+    "goslam_ba": (c_int, [c_void_p] * 7 + [c_int] + [c_void_p] * 2 + [c_int] * 7 +
+                  [c_float, c_float, c_int] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "goslam_ba_system_doubles": (c_size_t, [c_int, c_int]),
+    "goslam_ba_phase1": (c_int, [c_void_p] * 7 + [c_int] + [c_void_p] * 2 + [c_int] * 7 +
+                         [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "goslam_ba_phase2": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_float, c_float] + [c_int] * 3 +
+                         [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "goslam_neus_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "goslam_neus_forward": (c_int, [ctypes.POINTER(NeusParams)] + [c_void_p] * 4 + [c_int, c_int] +
+                            [ctypes.POINTER(NeusOut), c_void_p, c_size_t, c_void_p]),
+    "goslam_hashgrid_layout": (c_int64, [c_void_p, c_void_p, c_void_p]),
+    "goslam_corr_index_backward": (c_int, []),
+    "goslam_altcorr_backward": (c_int, []),
+}
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Return the loaded CDLL (building it first if the .so is absent)."""
+    global _LIB
+    with _lock:
+        if _LIB is not None:
+            return _LIB
+        path = lib_path()
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise RuntimeError("libgoslam_b200.so not built (run python -m __graft_entry__ or "
+                                   "go-slam_b200/build.py)")
+            _build.build()
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError => header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+        return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().goslam_strerror(int(rc))
+        raise RuntimeError("%s failed: %s (code %d)" % (what, msg.decode() if msg else "?", rc))
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

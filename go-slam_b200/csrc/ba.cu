@@ -1,0 +1,707 @@
+// ba.cu — dense Gauss-Newton bundle adjustment over SE3 poses x per-pixel inverse depth.
+//
+// Replaces droid_backends.ba = ba_cuda (src/lib/droid_kernels.cu:1314-1434) together with
+// projective_transform_kernel (:176-424), accum_kernel/accum_cuda (:854-998), EEt6x6 /
+// Ev6x1 / EvT6x1 (:1001-1115), pose/disp retraction (:898-946) and the host-side Eigen
+// pose-block assembly + Schur complement + SimplicialLLT (:1117-1311).
+//
+// What is different from the reference (same mathematics, same constants, same quirks):
+//   * NOTHING leaves the device: the frame set (`torch::_unique`), the edge->frame CSR that
+//     accum_cuda rebuilds on the CPU four times per iteration, the Schur pair list that
+//     schur_block builds with O(P^2 deg^2) host loops, and the float64 LLT all run in
+//     kernels; zero D2H/H2D copies and zero host synchronisation per call.
+//   * Linearisation is FRAME-major (one thread = one pixel of a source keyframe, looping
+//     over that keyframe's outgoing edges) so the per-pixel depth Hessian C, the depth
+//     gradient w, Q = 1/C and E_i = sum_e E_ii are complete in registers when the loop ends
+//     — no accum passes over [N,hw] temporaries.
+//   * J_i = -Ad^T J_j is linear, so only H_jj (21) and v_j (6) are reduced per edge (a
+//     27-value warp transpose-reduction, 31 shuffles instead of 90 block reductions);
+//     H_ii, H_ij, v_i follow from a 6x6 adjoint sandwich in the assembly step, in float64.
+//   * The reduced camera system is accumulated and solved in float64 on the device
+//     (the reference converts fp32 blocks to float64 and solves on the CPU).
+//
+// Reference quirks kept on purpose: the first optimised pose is skipped in the depth
+// back-substitution (`ix <= 0`, :1105); C/b_z use the stereo edge's weight before it is
+// zeroed (:320-323); stereo baseline (-0.1,0,0) (:219-229); MIN_DEPTH 0.25 (:26);
+// damping diag += ep + lm*diag (:1197); failed factorisation => dx = 0 (:1207-1210).
+#include "common.cuh"
+#include "se3.cuh"
+
+namespace {
+
+constexpr int kTP = 128;       // pixels (threads) per linearise / back-substitute block
+constexpr int kNRed = 27;      // 21 (H_jj upper) + 6 (v_j)
+constexpr float kAlpha = 0.05f;  // sensor-depth prior weight (src/lib/droid_kernels.cu:1396)
+
+struct BaWs {
+  // graph tables (built once per call by ba_prep_kernel)
+  int* slot_of_frame;  // [num]   slot in kx or -1
+  int* kx;             // [num]   frame id of slot
+  int* counts;         // [4]     M, total_entries, total_pairs, unused
+  int* row_ptr;        // [num+1] CSR over frame id: edges with ii == frame
+  int* edge_idx;       // [N]
+  int* entry_ptr;      // [num+1] per slot: Schur entries
+  int* entry_code;     // [num+N] >=0: edge id (E_ij), <0: -(pose+1) (E_i of that pose)
+  int* pair_ptr;       // [num+1] per slot: prefix of ne*(ne+1)/2
+  int* edge_j;         // [N]     jj as int (kept for the split phase-2 entry point)
+  // per-iteration buffers
+  float* Eij;          // [N,6,hw]
+  float* Ei;           // [num(slot),6,hw]
+  float* Q;            // [num(slot),hw]
+  float* w;            // [num(slot),hw]
+  float* part;         // [N,ntiles,27]
+  double* sys;         // [n*n + n]  reduced camera system (H row-major, then b)
+  double* chol;        // [n*n]      factor scratch (global path)
+  double* rhs;         // [n]        rhs / solution scratch (global path)
+  float* dx;           // [P,6]
+  int ntiles;
+};
+
+struct BaDims {
+  int N, num, ht, wd, hw, t0, t1, P, n;
+};
+
+size_t ba_layout(const BaDims& d, void* base, size_t cap, BaWs* ws) {
+  GsArena a(base, cap);
+  const int ntiles = gs_cdiv(d.hw, kTP);
+  BaWs w{};
+  w.slot_of_frame = a.take<int>(d.num);
+  w.kx = a.take<int>(d.num);
+  w.counts = a.take<int>(4);
+  w.row_ptr = a.take<int>(d.num + 1);
+  w.edge_idx = a.take<int>(d.N > 0 ? d.N : 1);
+  w.entry_ptr = a.take<int>(d.num + 1);
+  w.entry_code = a.take<int>(d.num + d.N);
+  w.pair_ptr = a.take<int>(d.num + 1);
+  w.edge_j = a.take<int>(d.N > 0 ? d.N : 1);
+  w.Eij = a.take<float>((size_t)(d.N > 0 ? d.N : 1) * 6 * d.hw);
+  w.Ei = a.take<float>((size_t)d.num * 6 * d.hw);
+  w.Q = a.take<float>((size_t)d.num * d.hw);
+  w.w = a.take<float>((size_t)d.num * d.hw);
+  w.part = a.take<float>((size_t)(d.N > 0 ? d.N : 1) * ntiles * kNRed);
+  w.sys = a.take<double>((size_t)d.n * d.n + d.n);
+  w.chol = a.take<double>((size_t)d.n * d.n);
+  w.rhs = a.take<double>(d.n > 0 ? d.n : 1);
+  w.dx = a.take<float>((size_t)(d.P > 0 ? d.P : 1) * 6);
+  w.ntiles = ntiles;
+  if (ws) *ws = w;
+  return a.off;
+}
+
+// ------------------------------------------------------------------------------------
+// Graph tables.  One block; everything is indexed by frame id so "sorted unique" is a
+// prefix sum over a presence bitmap (frame order == sorted order, as torch::_unique gives).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+ba_prep_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, BaDims d, BaWs ws) {
+  extern __shared__ int sm[];          // [num] scratch
+  const int tid = threadIdx.x, nt = blockDim.x;
+  int* present = sm;
+  for (int f = tid; f < d.num; f += nt) present[f] = (f >= d.t0 && f < d.t1) ? 1 : 0;
+  __syncthreads();
+  for (int e = tid; e < d.N; e += nt) {
+    const int f = (int)ii[e];
+    if (f >= 0 && f < d.num) present[f] = 1;     // benign race, all write 1
+    ws.edge_j[e] = (int)jj[e];
+  }
+  __syncthreads();
+  // serial scans by thread 0 are fine: num <= 4096, once per BA call.
+  if (tid == 0) {
+    int m = 0;
+    for (int f = 0; f < d.num; ++f) {
+      if (present[f]) { ws.slot_of_frame[f] = m; ws.kx[m] = f; ++m; }
+      else ws.slot_of_frame[f] = -1;
+    }
+    ws.counts[0] = m;
+  }
+  __syncthreads();
+  // CSR: one thread per frame scans the edge list => stable (edge-index) order
+  for (int f = tid; f < d.num; f += nt) {
+    int c = 0;
+    for (int e = 0; e < d.N; ++e) c += ((int)ii[e] == f);
+    present[f] = c;                     // reuse as per-frame degree
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int f = 0; f < d.num; ++f) { ws.row_ptr[f] = acc; acc += present[f]; }
+    ws.row_ptr[d.num] = acc;
+  }
+  __syncthreads();
+  for (int f = tid; f < d.num; f += nt) {
+    int o = ws.row_ptr[f];
+    if (present[f] > 0)
+      for (int e = 0; e < d.N; ++e)
+        if ((int)ii[e] == f) ws.edge_idx[o++] = e;
+  }
+  __syncthreads();
+  // Schur entries per slot: [E_i of the frame's own pose if optimised] + [E_ij of each
+  // outgoing edge whose target pose is optimised]  (schur_block graph, :1244-1253)
+  if (tid == 0) {
+    const int M = ws.counts[0];
+    int eo = 0, po = 0;
+    for (int k = 0; k < M; ++k) {
+      const int f = ws.kx[k];
+      ws.entry_ptr[k] = eo;
+      ws.pair_ptr[k] = po;
+      const int e0 = eo;
+      if (f >= d.t0 && f < d.t1) ws.entry_code[eo++] = -(f - d.t0 + 1);
+      for (int r = ws.row_ptr[f]; r < ws.row_ptr[f + 1]; ++r) {
+        const int e = ws.edge_idx[r];
+        const int j = (int)jj[e];
+        if (j >= d.t0 && j < d.t1) ws.entry_code[eo++] = e;
+      }
+      const int ne = eo - e0;
+      po += ne * (ne + 1) / 2;
+    }
+    ws.entry_ptr[M] = eo;
+    ws.pair_ptr[M] = po;
+    ws.counts[1] = eo;
+    ws.counts[2] = po;
+  }
+}
+
+// 32 values per lane -> lane L returns sum over lanes of v[L]   (31 shuffles)
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------------------------
+// Linearise: grid (ntiles, num); block = kTP pixels of slot blockIdx.y.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTP)
+ba_linearize_kernel(const float* __restrict__ poses, const float* __restrict__ disps,
+                    const float* __restrict__ intr, const float* __restrict__ disps_sens,
+                    const float* __restrict__ targets, const float* __restrict__ weights,
+                    const float* __restrict__ eta, int eta_rows,
+                    const int64_t* __restrict__ ii, const int64_t* __restrict__ jj,
+                    BaDims d, BaWs ws, int motion_only) {
+  const int k = blockIdx.y;
+  if (k >= ws.counts[0]) return;
+  const int f = ws.kx[k];
+  const int tile = blockIdx.x;
+  const int px = tile * kTP + threadIdx.x;
+  const bool act = px < d.hw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float red[kTP / 32][32];
+
+  const float fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3];
+  const float u = (float)(px % d.wd), v = (float)(px / d.wd);
+  const float di = act ? disps[(size_t)f * d.hw + px] : 1.0f;
+  float Xi[4] = {(u - cx) / fx, (v - cy) / fy, 1.0f, di};
+
+  float C = 0.f, wz = 0.f;
+  float Ei[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+  const int r0 = ws.row_ptr[f], r1 = ws.row_ptr[f + 1];
+  for (int r = r0; r < r1; ++r) {
+    const int e = ws.edge_idx[r];
+    const int jx = (int)jj[e];
+    const bool stereo = (jx == f);
+    GsSE3 G;
+    gs_edge_pose(poses, f, jx, G);
+
+    float Xj[4];
+    gs_act4(G, Xi, Xj);
+    const float x = Xj[0], y = Xj[1], h = Xj[3];
+    const bool behind = Xj[2] < GS_MIN_DEPTH;
+    const float dd = behind ? 0.0f : (float)(1.0 / (double)Xj[2]);
+    const float d2 = dd * dd;
+    float tu = 0.f, tv = 0.f, qu = 0.f, qv = 0.f;
+    if (act) {
+      const size_t o = ((size_t)e * 2) * d.hw + px;
+      tu = targets[o]; tv = targets[o + d.hw];
+      qu = weights[o]; qv = weights[o + d.hw];
+    }
+    float wu = (behind || !act) ? 0.0f : (float)(.001 * (double)qu);
+    float wv = (behind || !act) ? 0.0f : (float)(.001 * (double)qv);
+    const float ru = tu - (fx * dd * x + cx);
+    const float rv = tv - (fy * dd * y + cy);
+
+    float Ju[6], Jv[6];
+    Ju[0] = fx * (h * dd);       Ju[1] = fx * 0.f;
+    Ju[2] = fx * (-x * h * d2);  Ju[3] = fx * (-x * y * d2);
+    Ju[4] = fx * (1 + x * x * d2);  Ju[5] = fx * (-y * dd);
+    Jv[0] = fy * 0.f;            Jv[1] = fy * (h * dd);
+    Jv[2] = fy * (-y * h * d2);  Jv[3] = fy * (-1 - y * y * d2);
+    Jv[4] = fy * (x * y * d2);   Jv[5] = fy * (x * dd);
+    const float Jzu = fx * (G.t[0] * dd - G.t[2] * (x * d2));
+    const float Jzv = fy * (G.t[1] * dd - G.t[2] * (y * d2));
+
+    C += wu * Jzu * Jzu;  C += wv * Jzv * Jzv;
+    wz += wu * ru * Jzu;  wz += wv * rv * Jzv;
+    if (stereo) { wu = 0.f; wv = 0.f; }
+
+    // H_jj (upper triangle, row-major) and v_j
+    float val[32];
+    {
+      int l = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) val[l++] = wu * Ju[a] * Ju[b] + wv * Jv[a] * Jv[b];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) val[21 + a] = wu * ru * Ju[a] + wv * rv * Jv[a];
+#pragma unroll
+      for (int a = kNRed; a < 32; ++a) val[a] = 0.f;
+    }
+    const float tot = warp_transpose_reduce32(val, lane);
+    red[warp][lane] = tot;
+    __syncthreads();
+    if (threadIdx.x < kNRed) {
+      float s = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < kTP / 32; ++wq) s += red[wq][threadIdx.x];
+      ws.part[((size_t)e * ws.ntiles + tile) * kNRed + threadIdx.x] = s;
+    }
+    __syncthreads();
+
+    if (!motion_only) {
+      float Ee[6], Eii[6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) Ee[a] = wu * Jzu * Ju[a] + wv * Jzv * Jv[a];
+      gs_adjT(G, Ee, Eii);       // E_ii = -Ad^T E_ij
+      if (act) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          ws.Eij[((size_t)e * 6 + a) * d.hw + px] = Ee[a];
+          Ei[a] -= Eii[a];
+        }
+      }
+    }
+  }
+
+  if (!motion_only && act) {
+    // depth prior where the sensor has a reading, eta-damping elsewhere (:1396-1400)
+    const float ds = disps_sens[(size_t)f * d.hw + px];
+    const float m = (ds > 0.f) ? 1.0f : 0.0f;
+    const int er = (eta_rows == 1) ? 0 : min(k, eta_rows - 1);
+    const float et = eta[(size_t)er * d.hw + px];
+    C = C + m * kAlpha + (1.0f - m) * et;
+    wz = wz - m * kAlpha * (di - ds);
+    const size_t o = (size_t)k * d.hw + px;
+    ws.Q[o] = 1.0f / C;
+    ws.w[o] = wz;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) ws.Ei[((size_t)k * 6 + a) * d.hw + px] = Ei[a];
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Reduced camera system accumulation (persistent blocks):
+//   items [0, N)            pose blocks of edge e from its H_jj/v_j partials (A, :1376-1383)
+//   items [N, N + npairs)   Schur pair (a,b) of a depth frame: S_ab = sum_px E_a Q E_b^T,
+//                           and for a == b also v_a = sum_px E_a Q w   (:1001-1093,:1257-1311)
+// sys = (A - S | b_A - b_S) in float64.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ba_system_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ii,
+                 const int64_t* __restrict__ jj, BaDims d, BaWs ws, int motion_only) {
+  __shared__ float red[8][64];
+  __shared__ double Hs[36], Ms[36], Ts[36], vs[6];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = ws.counts[0];
+  const int npairs = motion_only ? 0 : ws.counts[2];
+  const int nitems = d.N + npairs;
+  double* H = ws.sys;
+  double* bvec = ws.sys + (size_t)d.n * d.n;
+
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    if (item < d.N) {
+      // ---------------- pose blocks of one edge ----------------
+      const int e = item;
+      const int ix = (int)ii[e], jx = (int)jj[e];
+      const int pi = ix - d.t0, pj = jx - d.t0;
+      const bool vi_ok = pi >= 0 && pi < d.P, vj_ok = pj >= 0 && pj < d.P;
+      if ((!vi_ok && !vj_ok) || ix < 0 || ix >= d.num) continue;
+      if (tid < kNRed) {
+        double s = 0.0;
+        for (int t = 0; t < ws.ntiles; ++t)
+          s += (double)ws.part[((size_t)e * ws.ntiles + t) * kNRed + tid];
+        if (tid < 21) {
+          // unpack upper-triangular index -> (a,b)
+          int a = 0, l = tid;
+          while (l >= 6 - a) { l -= 6 - a; ++a; }
+          const int b = a + l;
+          Hs[a * 6 + b] = s; Hs[b * 6 + a] = s;
+        } else {
+          vs[tid - 21] = s;
+        }
+      }
+      if (tid >= 32 && tid < 38) {
+        // column c of M = Ad^T (apply the dual adjoint to unit vector c)
+        const int c = tid - 32;
+        GsSE3 G;
+        gs_edge_pose(poses, ix, jx, G);
+        float X[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Y[6];
+        X[c] = 1.0f;
+        gs_adjT(G, X, Y);
+        for (int r = 0; r < 6; ++r) Ms[r * 6 + c] = (double)Y[r];
+      }
+      __syncthreads();
+      // T = M * Hjj
+      if (tid < 36) {
+        const int r = tid / 6, c = tid % 6;
+        double s = 0.0;
+        for (int q = 0; q < 6; ++q) s += Ms[r * 6 + q] * Hs[q * 6 + c];
+        Ts[tid] = s;
+      }
+      __syncthreads();
+      if (tid < 36) {
+        const int r = tid / 6, c = tid % 6;
+        // Hii = M Hjj M^T = T M^T ; Hij = -M Hjj = -T ; Hji = Hij^T ; vi = -M vj
+        if (vi_ok) {
+          double s = 0.0;
+          for (int q = 0; q < 6; ++q) s += Ts[r * 6 + q] * Ms[c * 6 + q];
+          atomicAdd(&H[(size_t)(6 * pi + r) * d.n + 6 * pi + c], s);
+        }
+        if (vi_ok && vj_ok) {
+          atomicAdd(&H[(size_t)(6 * pi + r) * d.n + 6 * pj + c], -Ts[r * 6 + c]);
+          atomicAdd(&H[(size_t)(6 * pj + r) * d.n + 6 * pi + c], -Ts[c * 6 + r]);
+        }
+        if (vj_ok) atomicAdd(&H[(size_t)(6 * pj + r) * d.n + 6 * pj + c], Hs[r * 6 + c]);
+      } else if (tid >= 64 && tid < 70) {
+        const int r = tid - 64;
+        if (vj_ok) atomicAdd(&bvec[6 * pj + r], vs[r]);
+        if (vi_ok) {
+          double s = 0.0;
+          for (int q = 0; q < 6; ++q) s += Ms[r * 6 + q] * vs[q];
+          atomicAdd(&bvec[6 * pi + r], -s);
+        }
+      }
+      __syncthreads();
+    } else {
+      // ---------------- one Schur pair ----------------
+      const int p = item - d.N;
+      // slot k with pair_ptr[k] <= p < pair_ptr[k+1]
+      int lo = 0, hi = M;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (ws.pair_ptr[mid] <= p) lo = mid; else hi = mid;
+      }
+      const int k = lo;
+      const int ne = ws.entry_ptr[k + 1] - ws.entry_ptr[k];
+      int q = p - ws.pair_ptr[k];
+      int a = 0;
+      while (q >= ne - a) { q -= ne - a; ++a; }      // row a of the upper triangle
+      const int b = a + q;
+      const int ca = ws.entry_code[ws.entry_ptr[k] + a];
+      const int cb = ws.entry_code[ws.entry_ptr[k] + b];
+      const float* Ea = (ca >= 0) ? ws.Eij + (size_t)ca * 6 * d.hw : ws.Ei + (size_t)k * 6 * d.hw;
+      const float* Eb = (cb >= 0) ? ws.Eij + (size_t)cb * 6 * d.hw : ws.Ei + (size_t)k * 6 * d.hw;
+      const int pa = (ca >= 0) ? (int)jj[ca] - d.t0 : -ca - 1;
+      const int pb = (cb >= 0) ? (int)jj[cb] - d.t0 : -cb - 1;
+      const float* Qk = ws.Q + (size_t)k * d.hw;
+      const float* wk = ws.w + (size_t)k * d.hw;
+
+      float acc[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      for (int px = tid; px < d.hw; px += 256) {
+        const float qv = Qk[px];
+        float ea[6], eb[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { ea[r] = Ea[(size_t)r * d.hw + px] * qv; eb[r] = Eb[(size_t)r * d.hw + px]; }
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc[r * 6 + c] += ea[r] * eb[c];
+        if (a == b) {
+          const float wv = wk[px];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) acc[36 + r] += ea[r] * wv;
+        }
+      }
+      // two 32-wide transpose reductions: values [0,32) and [32,64)
+      float lo32[32], hi32[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { lo32[i] = acc[i]; hi32[i] = acc[32 + i]; }
+      const float s0 = warp_transpose_reduce32(lo32, lane);
+      const float s1 = warp_transpose_reduce32(hi32, lane);
+      red[warp][lane] = s0;
+      red[warp][32 + lane] = s1;
+      __syncthreads();
+      if (tid < 42) {
+        double s = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) s += (double)red[wq][tid];
+        if (tid < 36) {
+          const int r = tid / 6, c = tid % 6;
+          atomicAdd(&H[(size_t)(6 * pa + r) * d.n + 6 * pb + c], -s);
+          if (a != b) atomicAdd(&H[(size_t)(6 * pb + c) * d.n + 6 * pa + r], -s);
+        } else {
+          atomicAdd(&bvec[6 * pa + (tid - 36)], -s);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Damp + Cholesky (float64) + solve + pose retraction.  One block.
+// A lives in shared memory when it fits, else in the global scratch.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __restrict__ sys_in,
+                float lm, float ep, int use_smem, float* __restrict__ dx_out,
+                int* __restrict__ status_out) {
+  extern __shared__ double smd[];
+  __shared__ int fail;
+  const int n = d.n, tid = threadIdx.x, nt = blockDim.x;
+  double* A = use_smem ? smd : ws.chol;
+  double* b = use_smem ? smd + (size_t)n * n : ws.rhs;
+  if (tid == 0) fail = 0;
+  for (size_t idx = tid; idx < (size_t)n * n; idx += nt) {
+    const int r = (int)(idx / n), c = (int)(idx % n);
+    double val = sys_in[idx];
+    if (r == c) val += (double)ep + (double)lm * val;
+    A[idx] = val;
+  }
+  for (int i = tid; i < n; i += nt) b[i] = sys_in[(size_t)n * n + i];
+  __syncthreads();
+
+  // right-looking Cholesky on the lower triangle
+  for (int j = 0; j < n; ++j) {
+    const double ajj = A[(size_t)j * n + j];
+    if (!(ajj > 0.0)) { if (tid == 0) fail = 1; }
+    __syncthreads();
+    if (fail) break;
+    const double ljj = sqrt(ajj);
+    for (int i = j + 1 + tid; i < n; i += nt) A[(size_t)i * n + j] /= ljj;
+    if (tid == 0) A[(size_t)j * n + j] = ljj;
+    __syncthreads();
+    // trailing update: A[i][c] -= L[i][j] * L[c][j], j < c <= i < n
+    const int m = n - j - 1;
+    const long long tot = (long long)m * m;
+    for (long long idx = tid; idx < tot; idx += nt) {
+      const int i = j + 1 + (int)(idx / m), c = j + 1 + (int)(idx % m);
+      if (c <= i) A[(size_t)i * n + c] -= A[(size_t)i * n + j] * A[(size_t)c * n + j];
+    }
+    __syncthreads();
+  }
+
+  if (!fail) {
+    // forward substitution L y = b (column sweep), then L^T x = y
+    for (int j = 0; j < n; ++j) {
+      if (tid == 0) b[j] /= A[(size_t)j * n + j];
+      __syncthreads();
+      const double yj = b[j];
+      for (int i = j + 1 + tid; i < n; i += nt) b[i] -= A[(size_t)i * n + j] * yj;
+      __syncthreads();
+    }
+    for (int j = n - 1; j >= 0; --j) {
+      if (tid == 0) b[j] /= A[(size_t)j * n + j];
+      __syncthreads();
+      const double xj = b[j];
+      for (int i = tid; i < j; i += nt) b[i] -= A[(size_t)j * n + i] * xj;
+      __syncthreads();
+    }
+    // all entries must be finite, else treat as a failed solve
+    int bad = 0;
+    for (int i = tid; i < n; i += nt) bad |= !isfinite(b[i]);
+    if (bad) fail = 1;
+    __syncthreads();
+  }
+
+  for (int i = tid; i < n; i += nt) {
+    const float val = fail ? 0.0f : (float)b[i];
+    ws.dx[i] = val;
+    if (dx_out) dx_out[i] = val;
+  }
+  if (tid == 0 && status_out) *status_out = fail;
+  __syncthreads();
+  // retraction  poses[k] <- exp(dx[k-t0]) * poses[k]   (:898-931)
+  for (int k = tid; k < d.P; k += nt) {
+    float* p = poses + 7 * (size_t)(d.t0 + k);
+    float t1[3], q1[4];
+    gs_retr(ws.dx + 6 * k, p, p + 3, t1, q1);
+    p[0] = t1[0]; p[1] = t1[1]; p[2] = t1[2];
+    p[3] = q1[0]; p[4] = q1[1]; p[5] = q1[2]; p[6] = q1[3];
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Depth back-substitution + retraction: dz = Q (w - sum_a E_a^T dx[pose_a]), disps += dz.
+// (EvT6x1 + accum + disp_retr, :1095-1115,:1417,:933-946)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTP)
+ba_backsub_kernel(float* __restrict__ disps, BaDims d, BaWs ws,
+                  int owner_lo, int owner_hi, float* __restrict__ dz_out) {
+  const int k = blockIdx.y;
+  if (k >= ws.counts[0]) return;
+  const int f = ws.kx[k];
+  if (f < owner_lo || f >= owner_hi) return;
+  const int px = blockIdx.x * kTP + threadIdx.x;
+  if (px >= d.hw) return;
+  float acc = 0.f;
+  // own pose entry E_i: pose index f - t0, skipped when <= 0 (reference quirk) or >= P
+  {
+    const int ix = f - d.t0;
+    if (ix > 0 && ix < d.P) {
+      float dw = 0.f;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) dw += ws.Ei[((size_t)k * 6 + a) * d.hw + px] * ws.dx[6 * ix + a];
+      acc += dw;
+    }
+  }
+  for (int r = ws.row_ptr[f]; r < ws.row_ptr[f + 1]; ++r) {
+    const int e = ws.edge_idx[r];
+    const int ix = ws.edge_j[e] - d.t0;
+    if (ix <= 0 || ix >= d.P) continue;
+    float dw = 0.f;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) dw += ws.Eij[((size_t)e * 6 + a) * d.hw + px] * ws.dx[6 * ix + a];
+    acc += dw;
+  }
+  const size_t o = (size_t)k * d.hw + px;
+  const float dz = ws.Q[o] * (ws.w[o] - acc);
+  disps[(size_t)f * d.hw + px] += dz;
+  if (dz_out) dz_out[(size_t)f * d.hw + px] = dz;
+}
+
+bool make_dims(int N, int num, int ht, int wd, int t0, int t1, BaDims* d) {
+  if (N < 0 || num <= 0 || num > 4096 || ht <= 0 || wd <= 0) return false;
+  d->N = N; d->num = num; d->ht = ht; d->wd = wd; d->hw = ht * wd;
+  d->t0 = t0; d->t1 = t1; d->P = t1 - t0 > 0 ? t1 - t0 : 0; d->n = 6 * d->P;
+  if (t0 < 0 || t1 > num) return false;
+  return true;
+}
+
+constexpr int kSmemSolveMaxN = 160;   // (160*160 + 160) * 8 B = 206 KB of the 227 KB
+
+int launch_phase1(const float* poses, const float* disps, const float* intr,
+                  const float* disps_sens, const float* targets, const float* weights,
+                  const float* eta, int eta_rows, const int64_t* ii, const int64_t* jj,
+                  const BaDims& d, const BaWs& ws, int motion_only, bool prep, cudaStream_t st) {
+  if (prep) {
+    ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws);
+    GS_CHECK_LAUNCH();
+  }
+  cudaMemsetAsync(ws.sys, 0, ((size_t)d.n * d.n + d.n) * sizeof(double), st);
+  if (d.N > 0) {
+    dim3 grid(ws.ntiles, d.num);
+    ba_linearize_kernel<<<grid, kTP, 0, st>>>(poses, disps, intr, disps_sens, targets, weights,
+                                              eta, eta_rows, ii, jj, d, ws, motion_only);
+    GS_CHECK_LAUNCH();
+  } else if (!motion_only) {
+    dim3 grid(ws.ntiles, d.num);   // still need Q / w / Ei (= prior only) for every slot
+    ba_linearize_kernel<<<grid, kTP, 0, st>>>(poses, disps, intr, disps_sens, targets, weights,
+                                              eta, eta_rows, ii, jj, d, ws, motion_only);
+    GS_CHECK_LAUNCH();
+  }
+  ba_system_kernel<<<148 * 4, 256, 0, st>>>(poses, ii, jj, d, ws, motion_only);
+  GS_CHECK_LAUNCH();
+  return GOSLAM_OK;
+}
+
+int launch_phase2(float* poses, float* disps, const double* sys_in,
+                  const BaDims& d, const BaWs& ws, float lm, float ep, int motion_only,
+                  int owner_lo, int owner_hi, float* dx_out, float* dz_out, int* status_out,
+                  cudaStream_t st) {
+  const int use_smem = d.n <= kSmemSolveMaxN;
+  const size_t smem = use_smem ? ((size_t)d.n * d.n + d.n) * sizeof(double) : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(((size_t)kSmemSolveMaxN * kSmemSolveMaxN + kSmemSolveMaxN) * 8));
+    attr_set = true;
+  }
+  ba_solve_kernel<<<1, 1024, smem, st>>>(poses, d, ws, sys_in, lm, ep, use_smem, dx_out,
+                                         status_out);
+  GS_CHECK_LAUNCH();
+  if (!motion_only) {
+    dim3 grid(ws.ntiles, d.num);
+    ba_backsub_kernel<<<grid, kTP, 0, st>>>(disps, d, ws, owner_lo, owner_hi, dz_out);
+    GS_CHECK_LAUNCH();
+  }
+  return GOSLAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t goslam_ba_workspace_bytes(int N, int num, int ht, int wd, int t0, int t1) {
+  BaDims d;
+  if (!make_dims(N, num, ht, wd, t0, t1, &d)) return 0;
+  return ba_layout(d, nullptr, 0, nullptr) + 256;
+}
+
+size_t goslam_ba_system_doubles(int t0, int t1) {
+  const size_t n = 6 * (size_t)(t1 > t0 ? t1 - t0 : 0);
+  return n * n + n;
+}
+
+int goslam_ba(float* poses, float* disps, const float* intrinsics, const float* disps_sens,
+              const float* targets, const float* weights, const float* eta, int eta_rows,
+              const int64_t* ii, const int64_t* jj, int N, int num, int ht, int wd, int t0,
+              int t1, int iterations, float lm, float ep, int motion_only, float* dx_out,
+              float* dz_out, int* status_out, void* workspace, size_t workspace_bytes,
+              void* stream) {
+  BaDims d;
+  if (!make_dims(N, num, ht, wd, t0, t1, &d)) return GOSLAM_EINVAL;
+  if (!motion_only && (eta == nullptr || eta_rows < 1)) return GOSLAM_EINVAL;
+  if (d.P == 0 || iterations <= 0) return GOSLAM_OK;
+  BaWs ws;
+  const size_t need = ba_layout(d, workspace, workspace_bytes, &ws);
+  if (workspace == nullptr || need > workspace_bytes) return GOSLAM_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dz_out) cudaMemsetAsync(dz_out, 0, (size_t)num * d.hw * sizeof(float), st);
+  for (int it = 0; it < iterations; ++it) {
+    int rc = launch_phase1(poses, disps, intrinsics, disps_sens, targets, weights, eta, eta_rows,
+                           ii, jj, d, ws, motion_only, it == 0, st);
+    if (rc) return rc;
+    rc = launch_phase2(poses, disps, ws.sys, d, ws, lm, ep, motion_only, 0, num, dx_out,
+                       dz_out, status_out ? status_out + it : nullptr, st);
+    if (rc) return rc;
+  }
+  return GOSLAM_OK;
+}
+
+int goslam_ba_phase1(const float* poses, const float* disps, const float* intrinsics,
+                     const float* disps_sens, const float* targets, const float* weights,
+                     const float* eta, int eta_rows, const int64_t* ii, const int64_t* jj, int N,
+                     int num, int ht, int wd, int t0, int t1, int motion_only, double* system,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  BaDims d;
+  if (!make_dims(N, num, ht, wd, t0, t1, &d)) return GOSLAM_EINVAL;
+  if (d.P == 0) return GOSLAM_OK;
+  BaWs ws;
+  const size_t need = ba_layout(d, workspace, workspace_bytes, &ws);
+  if (workspace == nullptr || need > workspace_bytes) return GOSLAM_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_phase1(poses, disps, intrinsics, disps_sens, targets, weights, eta, eta_rows, ii,
+                         jj, d, ws, motion_only, true, st);
+  if (rc) return rc;
+  if (system != ws.sys)
+    cudaMemcpyAsync(system, ws.sys, ((size_t)d.n * d.n + d.n) * sizeof(double),
+                    cudaMemcpyDeviceToDevice, st);
+  return GOSLAM_OK;
+}
+
+int goslam_ba_phase2(float* poses, float* disps, const double* system, int N, int num, int ht,
+                     int wd, int t0, int t1, float lm, float ep, int motion_only, int owner_lo,
+                     int owner_hi, float* dx_out, float* dz_out, int* status_out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  BaDims d;
+  if (!make_dims(N, num, ht, wd, t0, t1, &d)) return GOSLAM_EINVAL;
+  if (d.P == 0) return GOSLAM_OK;
+  BaWs ws;
+  const size_t need = ba_layout(d, workspace, workspace_bytes, &ws);
+  if (workspace == nullptr || need > workspace_bytes) return GOSLAM_EWORKSPACE;
+  return launch_phase2(poses, disps, system, d, ws, lm, ep, motion_only, owner_lo, owner_hi, dx_out,
+                       dz_out, status_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

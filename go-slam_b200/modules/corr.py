@@ -1,0 +1,131 @@
+"""CorrBlock / AltCorrBlock with the reference's constructor and call signatures
+(src/modules/corr.py:25-65,97-145), backed by the sm_100a kernels.
+
+CorrBlock(fmap1, fmap2)      -> tcgen05 all-pairs build + in-epilogue 4-level pyramid
+                                (goslam_corr_build; reference: torch.matmul + 3x avg_pool2d)
+CorrBlock.__call__(coords)   -> ONE fused 4-level radius-3 lookup (goslam_corr_pyramid_lookup;
+                                reference: 4 x corr_index_forward + torch.cat)
+AltCorrBlock(fmaps)(coords, ii, jj) -> windowed correlation per level (goslam_altcorr_forward)
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+from ..droid_backends import _workspace, altcorr_forward
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+class CorrBlock:
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=3, impl=0):
+        self.num_levels = num_levels
+        self.radius = radius
+        if not fmap1.is_cuda:
+            raise RuntimeError("CorrBlock: CUDA tensors required (no CPU fallback)")
+        batch, num, dim, ht, wd = fmap1.shape
+        N = batch * num
+        self.ht, self.wd = ht, wd
+        dev = fmap1.device
+        f1 = fmap1.reshape(N, dim, ht, wd).contiguous()
+        f2 = fmap2.reshape(N, dim, ht, wd).contiguous()
+        lib = _lib.load()
+        if f1.dtype == torch.float16:
+            levels = [torch.empty((N, ht, wd, ht >> i, wd >> i), dtype=torch.float16, device=dev)
+                      for i in range(num_levels)]
+            with torch.cuda.device(dev):
+                nbytes = lib.goslam_corr_build_workspace_bytes(N, dim, ht, wd)
+                ws = _workspace(nbytes, dev)
+                rc = lib.goslam_corr_build(
+                    _lib.ptr(f1), _lib.ptr(f2.half()), _ptr_array(levels), num_levels, N, dim, ht, wd,
+                    int(impl), _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_ptr())
+            _lib.check(rc, "corr_build")
+        else:
+            f1, f2 = f1.float(), f2.float()
+            levels = [torch.empty((N, ht, wd, ht >> i, wd >> i), dtype=torch.float32, device=dev)
+                      for i in range(num_levels)]
+            with torch.cuda.device(dev):
+                rc = lib.goslam_corr_build_f32(_lib.ptr(f1), _lib.ptr(f2), _ptr_array(levels),
+                                               num_levels, N, dim, ht, wd, _lib.stream_ptr())
+            _lib.check(rc, "corr_build_f32")
+        self.corr_pyramid = levels
+
+    def __call__(self, coords):
+        batch, num, ht, wd, _ = coords.shape
+        N = batch * num
+        vol0 = self.corr_pyramid[0]
+        rd = 2 * self.radius + 1
+        coords = coords.reshape(N, ht, wd, 2).contiguous().float()
+        out = torch.empty((batch, num, self.num_levels * rd * rd, ht, wd), dtype=vol0.dtype,
+                          device=vol0.device)
+        pyr = [p.contiguous() for p in self.corr_pyramid]
+        with torch.cuda.device(vol0.device):
+            rc = _lib.load().goslam_corr_pyramid_lookup(
+                _ptr_array(pyr), 1 if vol0.dtype == torch.float16 else 0, self.num_levels,
+                _lib.ptr(coords), _lib.ptr(out), N, ht, wd, vol0.shape[3], vol0.shape[4],
+                int(self.radius), _lib.stream_ptr())
+        _lib.check(rc, "corr_pyramid_lookup")
+        return out
+
+    def cat(self, other):
+        for i in range(self.num_levels):
+            self.corr_pyramid[i] = torch.cat([self.corr_pyramid[i], other.corr_pyramid[i]], dim=0)
+        return self
+
+    def __getitem__(self, index):
+        for i in range(self.num_levels):
+            self.corr_pyramid[i] = self.corr_pyramid[i][index]
+        return self
+
+    @staticmethod
+    def corr(fmap1, fmap2):
+        """all-pairs correlation, level 0 only ([batch, num, h, w, h, w])."""
+        blk = CorrBlock(fmap1, fmap2, num_levels=1)
+        batch, num, _, ht, wd = fmap1.shape
+        return blk.corr_pyramid[0].view(batch, num, ht, wd, ht, wd)
+
+
+class AltCorrBlock:
+    def __init__(self, fmaps, num_levels=4, radius=3):
+        self.num_levels = num_levels
+        self.radius = radius
+        B, N, C, H, W = fmaps.shape
+        fmaps = fmaps.view(B * N, C, H, W) / 4.0
+        self.pyramid = []
+        for i in range(self.num_levels):
+            sz = (B, N, H // 2 ** i, W // 2 ** i, C)
+            fmap_lvl = fmaps.permute(0, 2, 3, 1).contiguous()
+            self.pyramid.append(fmap_lvl.view(*sz))
+            fmaps = F.avg_pool2d(fmaps, kernel_size=2, stride=2)
+
+    def corr_fn(self, coords, ii, jj):
+        B, N, H, W, S, _ = coords.shape
+        coords = coords.permute(0, 1, 4, 2, 3, 5)
+        corr_list = []
+        for i in range(self.num_levels):
+            fmap1_i = self.pyramid[0][:, ii]
+            fmap2_i = self.pyramid[i][:, jj]
+            coords_i = (coords / 2 ** i).reshape(B * N, S, H, W, 2).contiguous()
+            fmap1_i = fmap1_i.reshape((B * N,) + fmap1_i.shape[2:])
+            fmap2_i = fmap2_i.reshape((B * N,) + fmap2_i.shape[2:])
+            corr, = altcorr_forward(fmap1_i.float().contiguous(), fmap2_i.float().contiguous(),
+                                    coords_i, self.radius)
+            corr = corr.view(B, N, S, -1, H, W).permute(0, 1, 3, 4, 5, 2)
+            corr_list.append(corr)
+        return torch.cat(corr_list, dim=2)
+
+    def __call__(self, coords, ii, jj):
+        squeeze_output = False
+        if len(coords.shape) == 5:
+            coords = coords.unsqueeze(dim=-2)
+            squeeze_output = True
+        corr = self.corr_fn(coords, ii, jj)
+        if squeeze_output:
+            corr = corr.squeeze(dim=-1)
+        return corr.contiguous()

@@ -1,0 +1,200 @@
+/*
+ * goslam_b200.h — C-ABI of libgoslam_b200.so (sm_100a).
+ *
+ * One entry point per operator of GO-SLAM's per-keyframe dense-update path.  Every
+ * function takes raw DEVICE pointers + shapes + a cudaStream_t (passed as void*) and
+ * returns 0 on success or a negative GOSLAM_E* code; nothing is retained, nothing is
+ * allocated (callers hand in workspaces sized by the *_workspace_bytes helpers), no
+ * host<->device synchronisation happens inside.  No torch types cross this boundary.
+ *
+ * Each entry cites the reference interface (file:line under /root/reference) it
+ * replaces.  The Python shim `droid_backends` (go-slam_b200/droid_backends.py) binds
+ * these through ctypes under the reference's own function names.
+ */
+#ifndef GOSLAM_B200_H_
+#define GOSLAM_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOSLAM_OK            0
+#define GOSLAM_EINVAL       (-1)  /* bad shape / argument                         */
+#define GOSLAM_ELAUNCH      (-2)  /* cudaGetLastError() != cudaSuccess after launch */
+#define GOSLAM_EWORKSPACE   (-3)  /* workspace too small                          */
+#define GOSLAM_EUNSUPPORTED (-4)  /* e.g. training-only backward entry points     */
+
+/* element types of correlation volumes / feature maps */
+#define GOSLAM_F32 0
+#define GOSLAM_F16 1
+
+/* library identification; returns e.g. 100 for "1.0.0" and the SM arch compiled for */
+int goslam_version(void);
+int goslam_sm_arch(void);
+const char* goslam_strerror(int code);
+
+/* ------------------------------------------------------------------------------------
+ * Correlation volume — radius-r bilinear window lookup, one pyramid level.
+ * Replaces droid_backends.corr_index_forward  (src/lib/droid.cpp:170-178,
+ * src/lib/correlation_kernels.cu:19-70,126-155).
+ *   volume [N,h1,w1,h2,w2] (f16|f32), coords [N,2,h1,w1] f32 (x then y),
+ *   corr   [N,2r+1,2r+1,h1,w1] same dtype as volume, x-offset-major, fully overwritten.
+ * ---------------------------------------------------------------------------------- */
+int goslam_corr_index_forward(const void* volume, int dtype, const float* coords,
+                              void* corr, int N, int h1, int w1, int h2, int w2,
+                              int radius, void* stream);
+
+/* Fused 4-level form of CorrBlock.__call__ (src/modules/corr.py:43-53): level i samples
+ * pyramid[i] (dims h2>>i, w2>>i, floor) at coords/2^i and writes channels
+ * [i*(2r+1)^2, (i+1)*(2r+1)^2) of out [N, L*(2r+1)^2, h1, w1].
+ *   coords_hw2 [N,h1,w1,2] f32 — the *un-permuted* reproject output (x,y interleaved).
+ *   pyramid[L] device pointers to the L level volumes (host array of L pointers). */
+int goslam_corr_pyramid_lookup(const void* const* pyramid, int dtype, int num_levels,
+                               const float* coords_hw2, void* out,
+                               int N, int h1, int w1, int h2, int w2, int radius,
+                               void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Correlation volume — all-pairs build + 2x2 average-pool pyramid.
+ * Replaces CorrBlock.__init__/CorrBlock.corr (src/modules/corr.py:25-41,67-76):
+ *   corr[n] = (fmap1[n]/4)^T (fmap2[n]/4)  -> level0 [N,h,w,h,w]; level i+1 = avg_pool2d(level i,2,2).
+ *   fmap1,fmap2 [N,D,h,w] f16 (channel-major, as DepthVideo.fmaps stores them),
+ *   levels[L] output pointers, f16, level i dims [N,h,w,h>>i,w>>i].
+ * impl: 0 = auto, 1 = tcgen05/TMA tensor-core kernel, 2 = SIMT reference kernel.
+ * workspace: goslam_corr_build_workspace_bytes(N,D,h,w) bytes (K-major staging). */
+size_t goslam_corr_build_workspace_bytes(int N, int D, int h, int w);
+int goslam_corr_build(const void* fmap1, const void* fmap2, void* const* levels,
+                      int num_levels, int N, int D, int h, int w, int impl,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* fp32 variant used by the CPU-shaped config (fmaps f32, volume f32); SIMT only. */
+int goslam_corr_build_f32(const float* fmap1, const float* fmap2, float* const* levels,
+                          int num_levels, int N, int D, int h, int w, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * On-the-fly windowed correlation (no volume).
+ * Replaces droid_backends.altcorr_forward (src/lib/droid.cpp:193-203,
+ * src/lib/altcorr_kernel.cu:27-149,290-319).
+ *   fmap1 [B,H,W,C] f32, fmap2 [B,H2,W2,C] f32 (NHWC), coords [B,S,H,W,2] f32,
+ *   corr [B,S,(2r+1)^2,H,W] f32, channel = xoff*(2r+1)+yoff, fully overwritten. */
+int goslam_altcorr_forward(const float* fmap1, const float* fmap2, const float* coords,
+                           float* corr, int B, int S, int H, int W, int H2, int W2,
+                           int C, int radius, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Geometry kernels of droid_backends (src/lib/droid.cpp:120-160,220-225).
+ *   poses [num,7] f32 (tx,ty,tz,qx,qy,qz,qw); disps [num,ht,wd] f32; intrinsics [4]
+ *   f32 (fx,fy,cx,cy); ii,jj int64.
+ * ---------------------------------------------------------------------------------- */
+/* frame_distance (src/lib/droid_kernels.cu:518-657,1438-1460): dist [K] f32.
+ * Reduction order reproduces the reference's 256-thread strided sum + 128/64/32..1 tree
+ * so thresholded edge lists are bit-identical. */
+int goslam_frame_distance(const float* poses, const float* disps, const float* intrinsics,
+                          const int64_t* ii, const int64_t* jj, float* dist,
+                          int K, int ht, int wd, float beta, void* stream);
+/* projmap (src/lib/droid_kernels.cu:427-516,1463-1488): coords [K,ht,wd,3] (3rd
+ * component left zero, as the reference does), valid [K,ht,wd,1]. */
+int goslam_projmap(const float* poses, const float* disps, const float* intrinsics,
+                   const int64_t* ii, const int64_t* jj, float* coords, float* valid,
+                   int K, int ht, int wd, void* stream);
+/* iproj (src/lib/droid_kernels.cu:779-850,1518-1541): points [num,ht,wd,3]. */
+int goslam_iproj(const float* poses, const float* disps, const float* intrinsics,
+                 float* points, int num, int ht, int wd, void* stream);
+/* depth_filter (src/lib/droid_kernels.cu:661-775,1491-1515): counter [K,ht,wd],
+ * fully overwritten (zeroed inside). */
+int goslam_depth_filter(const float* poses, const float* disps, const float* intrinsics,
+                        const int64_t* ix, const float* thresh, float* counter,
+                        int K, int num, int ht, int wd, void* stream);
+/* reproject = pops.projective_transform(jacobian=False) as called by DepthVideo.reproject
+ * (src/depth_video.py:207-217, src/geom/projective_ops.py:114-144) with the lietorch SE3
+ * algebra restated from src/lib/droid_kernels.cu:58-107.  intrinsics_all [num,4] (per
+ * frame, as DepthVideo.intrinsics); coords [K,ht,wd,2], valid [K,ht,wd,1]. */
+int goslam_reproject(const float* poses, const float* disps, const float* intrinsics_all,
+                     const int64_t* ii, const int64_t* jj, float* coords, float* valid,
+                     int K, int ht, int wd, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense bundle adjustment.  Replaces droid_backends.ba (src/lib/droid.cpp:88-117,
+ * src/lib/droid_kernels.cu:1314-1434 + kernels :176-424,:854-1115 + the host Eigen
+ * Schur/LLT :1117-1311).  poses and disps are updated IN PLACE.
+ *   targets,weights [N,2,ht,wd] f32; eta [M,ht,wd] f32 with M = |unique([t0,t1) U ii)|
+ *   (or a single row, broadcast); disps_sens [num,ht,wd].
+ *   dx_out [t1-t0,6] (nullable), dz_out [num,ht*wd] indexed by FRAME id (nullable).
+ *   status_out: device int[iterations] (nullable), 0 = solved, 1 = factorisation failed
+ *   (then dx = 0 for that iteration, like src/lib/droid_kernels.cu:1207-1210).
+ * Limits: num <= 4096 frames.
+ * ---------------------------------------------------------------------------------- */
+size_t goslam_ba_workspace_bytes(int N, int num, int ht, int wd, int t0, int t1);
+int goslam_ba(float* poses, float* disps, const float* intrinsics, const float* disps_sens,
+              const float* targets, const float* weights, const float* eta, int eta_rows,
+              const int64_t* ii, const int64_t* jj, int N, int num, int ht, int wd,
+              int t0, int t1, int iterations, float lm, float ep, int motion_only,
+              float* dx_out, float* dz_out, int* status_out,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/* Multi-GPU split form of one BA iteration (edges sharded by source frame ii):
+ *   phase 1  linearise local edges and accumulate the local reduced system
+ *            Hred [6P*6P] f64 + bred [6P] f64 into `system` (caller all-reduces it),
+ *   phase 2  damp + factorise + back-substitute + retract with the reduced system.
+ * goslam_ba == phase1 + phase2 per iteration on one GPU. */
+size_t goslam_ba_system_doubles(int t0, int t1);
+int goslam_ba_phase1(const float* poses, const float* disps, const float* intrinsics,
+                     const float* disps_sens, const float* targets, const float* weights,
+                     const float* eta, int eta_rows, const int64_t* ii, const int64_t* jj,
+                     int N, int num, int ht, int wd, int t0, int t1, int motion_only,
+                     double* system, void* workspace, size_t workspace_bytes, void* stream);
+int goslam_ba_phase2(float* poses, float* disps, const double* system,
+                     int N, int num, int ht, int wd, int t0, int t1,
+                     float lm, float ep, int motion_only, int owner_lo, int owner_hi,
+                     float* dx_out, float* dz_out, int* status_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Hash-grid neural-surface ray marcher.  Replaces InstantNeuS.forward
+ * (src/InstantNeuS.py:295-370) incl. tiny-cuda-nn HashGrid + FullyFusedMLP
+ * (src/InstantNeuS.py:44-66,184-205), SDFNetwork.sdf + autograd normal (:97-160),
+ * get_alpha (:276-293) and the compositing (:343-370).
+ * ---------------------------------------------------------------------------------- */
+typedef struct goslam_neus_params {
+  const void*  grid;        /* f16 [total_params] tcnn HashGrid layout, 16 levels x 2 feats */
+  const float* sdf_w;       /* [32,35] nn.Linear weight (row-major out x in)               */
+  const float* sdf_b;       /* [32]                                                        */
+  const float* color_B;     /* [3,33]  ColorNetwork._B                                     */
+  const void*  mlp_w;       /* f16 tcnn FullyFusedMLP params: [64,80] | [64,64] | [16,64]  */
+  float bound[6];           /* self.bound  (xmin,xmax,ymin,ymax,zmin,zmax) — normalisation */
+  float rt_bound[6];        /* self.realtime_bound — in_bound mask                         */
+  float inv_s;              /* exp(variance*scale_factor) clipped to [1e-6,1e6]            */
+  float cos_anneal_ratio;   /* self.cos_anneal_ratio (1.0)                                 */
+} goslam_neus_params;
+
+typedef struct goslam_neus_out {
+  float* color;          /* [R,3]  */
+  float* depth;          /* [R,1]  */
+  float* depth_variance; /* [R,1]  */
+  float* normal;         /* [R,3]  */
+  float* weight_sum;     /* [R,1]  */
+  float* sdf;            /* [R,S]  */
+  float* z_mid;          /* [R,S]  (z_vals + dists/2)                    */
+  float* gradient_error; /* [1]    */
+} goslam_neus_out;
+
+size_t goslam_neus_workspace_bytes(int R, int S);
+int goslam_neus_forward(const goslam_neus_params* params, const float* rays_o,
+                        const float* rays_d, const float* z_vals, const float* dists,
+                        int R, int S, const goslam_neus_out* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* hash-grid geometry helper (host side, no GPU): fills offsets[17] (in PARAMS, i.e.
+ * entries*2), resolutions[16], scales[16]; returns total number of f16 params. */
+int64_t goslam_hashgrid_layout(int64_t* offsets, int* resolutions, float* scales);
+
+/* Training-only entry points of the reference module are exported for ABI completeness
+ * and return GOSLAM_EUNSUPPORTED (inference path is torch.no_grad, src/slam.py:45). */
+int goslam_corr_index_backward(void);
+int goslam_altcorr_backward(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOSLAM_B200_H_ */

@@ -1,0 +1,294 @@
+"""GPU parity tests (run on the B200 box): every kernel of the hot path, called through the
+C-ABI (via the droid_backends / CorrBlock / InstantNeuS shims), against the CPU oracle on the
+same seeded inputs.  Tolerances are written next to each assertion."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ba_oracle, corr_oracle, geom_oracle, neus_oracle  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+# ------------------------------------------------------------------------------ lookup
+def _lookup_case(dtype, N, h1, w1, h2, w2, seed):
+    g = torch.Generator().manual_seed(seed)
+    vol = torch.randn(N, h1, w1, h2, w2, generator=g)
+    vol = vol.half() if dtype == "f16" else vol
+    base = torch.stack(torch.meshgrid(torch.arange(w1).float(), torch.arange(h1).float(), indexing="xy"), 0)
+    coords = base[None].repeat(N, 1, 1, 1) * (w2 / w1) + 3.0 * torch.randn(N, 2, h1, w1, generator=g)
+    coords[0, :, 0, 0] = torch.tensor([-7.5, -9.25])           # fully outside
+    coords[0, :, 0, 1] = torch.tensor([w2 + 2.5, h2 + 1.0])
+    coords[0, :, 1, 0] = torch.tensor([-0.5, 0.5])             # straddling the border
+    coords[0, :, 1, 1] = torch.tensor([float(w2 - 1), float(h2 - 1)])   # integer coords (dx = 0)
+    return vol, coords.contiguous()
+
+
+@pytest.mark.parametrize("dtype", ["f16", "f32"])
+@pytest.mark.parametrize("shape", [(3, 12, 16, 12, 16), (2, 9, 11, 7, 10), (2, 6, 8, 3, 5)])
+def test_corr_index_forward(dtype, shape):
+    from goslam_b200 import droid_backends
+    vol, coords = _lookup_case(dtype, *shape, seed=1)
+    out, = droid_backends.corr_index_forward(vol.to(dev()), coords.to(dev()), 3)
+    ref = corr_oracle.corr_index_forward(vol.numpy(), coords.numpy(), 3)
+    got = out.cpu().numpy()
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    if dtype == "f16":
+        # the half instantiation is a fixed sequence of correctly-rounded half ops: bit-exact
+        np.testing.assert_array_equal(got.astype(np.float32), ref.astype(np.float32))
+    else:
+        # chained FMAs in the reference's order; the oracle emulates FMA in float64: <= 1 ulp
+        np.testing.assert_allclose(got, ref, rtol=2e-7, atol=1e-7)
+
+
+def test_corr_index_forward_vs_grid_sample():
+    from goslam_b200 import droid_backends
+    vol, coords = _lookup_case("f32", 2, 12, 16, 12, 16, seed=2)
+    out, = droid_backends.corr_index_forward(vol.to(dev()), coords.to(dev()), 3)
+    ref = corr_oracle.corr_index_forward_grid_sample(vol.numpy(), coords.numpy(), 3)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("dtype", ["f16", "f32"])
+@pytest.mark.parametrize("hw", [(16, 16), (12, 20), (30, 40)])
+def test_corr_block_build_and_lookup(dtype, hw):
+    """CorrBlock(fmap1, fmap2)(coords): build (auto impl) + fused 4-level lookup."""
+    from goslam_b200.modules import CorrBlock
+    h, w = hw
+    N = 2
+    g = torch.Generator().manual_seed(3)
+    f1 = torch.randn(1, N, 128, h, w, generator=g)
+    f2 = torch.randn(1, N, 128, h, w, generator=g)
+    if dtype == "f16":
+        f1, f2 = f1.half(), f2.half()
+    blk = CorrBlock(f1.to(dev()), f2.to(dev()))
+    ref = corr_oracle.corr_build(f1[0], f2[0], 4)
+    for i in range(4):
+        got = blk.corr_pyramid[i].float().cpu().numpy()
+        want = ref[i].float().numpy()
+        assert got.shape == want.shape
+        if dtype == "f16":
+            # fp32 accumulate in a different order, one rounding to half: <= 1 half-ulp
+            np.testing.assert_allclose(got, want, rtol=1.5e-3, atol=1e-3)
+            assert (got == want).mean() > 0.97
+        else:
+            np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+    coords = torch.stack(torch.meshgrid(torch.arange(w).float(), torch.arange(h).float(), indexing="xy"), -1)
+    coords = coords[None, None].repeat(1, N, 1, 1, 1) + 2.5 * torch.randn(1, N, h, w, 2, generator=g)
+    out = blk(coords.to(dev()))
+    pyr = [p.cpu().numpy() for p in blk.corr_pyramid]
+    want = corr_oracle.corr_pyramid_lookup(pyr, coords[0].numpy(), 3)
+    got = out[0].cpu().numpy()
+    assert got.shape == want.shape
+    if dtype == "f16":
+        np.testing.assert_array_equal(got.astype(np.float32), want.astype(np.float32))
+    else:
+        np.testing.assert_allclose(got, want, rtol=2e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize("hw", [(40, 80), (30, 40), (12, 20)])
+def test_corr_build_tcgen05_matches_simt(hw):
+    """the tensor-core kernel (impl=1) and its CUDA-core twin (impl=2) share one numerics
+    contract; they may differ only where fp32 summation order flips a half rounding."""
+    from goslam_b200.modules import CorrBlock
+    h, w = hw
+    g = torch.Generator().manual_seed(4)
+    f1 = torch.randn(1, 3, 128, h, w, generator=g).half().to(dev())
+    f2 = torch.randn(1, 3, 128, h, w, generator=g).half().to(dev())
+    a = CorrBlock(f1, f2, impl=1)
+    b = CorrBlock(f1, f2, impl=2)
+    for i in range(4):
+        x, y = a.corr_pyramid[i].float(), b.corr_pyramid[i].float()
+        assert x.shape == y.shape
+        assert torch.isfinite(x).all()
+        assert (x - y).abs().max().item() <= 2e-3 * max(1.0, y.abs().max().item())
+        assert (x == y).float().mean().item() > 0.97
+    # cuBLAS-style check of level 0 against torch on the device
+    want = torch.matmul((f1[0] / 4).reshape(3, 128, h * w).transpose(1, 2).float(),
+                        (f2[0] / 4).reshape(3, 128, h * w).float()).half().float()
+    got = a.corr_pyramid[0].reshape(3, h * w, h * w).float()
+    assert (got - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+
+
+# ------------------------------------------------------------------------------ altcorr
+def test_altcorr_forward():
+    from goslam_b200 import droid_backends
+    g = torch.Generator().manual_seed(5)
+    B, H, W, C, S = 3, 10, 12, 128, 2
+    f1 = torch.randn(B, H, W, C, generator=g)
+    f2 = torch.randn(B, H // 2, W // 2, C, generator=g)
+    base = torch.stack(torch.meshgrid(torch.arange(W).float(), torch.arange(H).float(), indexing="xy"), -1)
+    coords = (base[None, None].repeat(B, S, 1, 1, 1) + 2 * torch.randn(B, S, H, W, 2, generator=g)) / 2
+    coords[0, 0, 0, 0] = torch.tensor([-20.0, 3.0])
+    out, = droid_backends.altcorr_forward(f1.to(dev()), f2.to(dev()), coords.to(dev()).contiguous(), 3)
+    ref = corr_oracle.altcorr_forward(f1.numpy(), f2.numpy(), coords.numpy(), 3)
+    # fp32 dot products of 128 terms in a different order: 1e-5 relative to the value scale
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------ geometry
+def _scene(num_kf=6, ht=12, wd=16, **kw):
+    from goslam_b200 import synthetic
+    return synthetic.make_scene(num_kf=num_kf, ht=ht, wd=wd, **kw)
+
+
+def _to_dev(sc, *keys):
+    return [sc[k].to(dev()).contiguous() for k in keys]
+
+
+@pytest.mark.parametrize("size", [(6, 12, 16), (8, 40, 80)])
+def test_frame_distance(size):
+    from goslam_b200 import droid_backends
+    sc, g = _scene(*size, with_fmaps=False)
+    n = size[0]
+    ii, jj = torch.meshgrid(torch.arange(n), torch.arange(n), indexing="ij")
+    ii, jj = ii.reshape(-1), jj.reshape(-1)
+    poses, disps, intr = _to_dev(sc, "poses", "disps", "intrinsics")
+    for beta in (0.3, 0.75):
+        d = droid_backends.frame_distance(poses, disps, intr[0].contiguous(), ii.to(dev()), jj.to(dev()), beta)
+        ref = geom_oracle.frame_distance(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"][0].numpy(),
+                                         ii.numpy(), jj.numpy(), beta)
+        got = d.cpu().numpy()
+        # same summation tree; remaining differences are FMA contraction inside the projection
+        np.testing.assert_allclose(got, ref, rtol=2e-5, atol=1e-6)
+        # the edge set the frontend derives from it (distance < thresh) must be identical
+        for thresh in (2.0, 8.0, 16.0):
+            assert ((got < thresh) == (ref < thresh)).all()
+        assert (np.argsort(got, kind="stable") == np.argsort(ref, kind="stable")).mean() > 0.95
+
+
+def test_projmap_iproj_depth_filter_reproject():
+    from goslam_b200 import droid_backends
+    sc, g = _scene(7, 12, 16, with_fmaps=False)
+    poses, disps, intr = _to_dev(sc, "poses", "disps", "intrinsics")
+    ii, jj = sc["ii"], sc["jj"]
+    c, v = droid_backends.projmap(poses, disps, intr[0].contiguous(), ii.to(dev()), jj.to(dev()))
+    rc, rv = geom_oracle.projmap(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"][0].numpy(), ii.numpy(), jj.numpy())
+    np.testing.assert_allclose(c.cpu().numpy(), rc, rtol=1e-5, atol=1e-4)
+    np.testing.assert_array_equal(v.cpu().numpy(), rv)
+    pts = droid_backends.iproj(poses, disps, intr[0].contiguous())
+    np.testing.assert_allclose(pts.cpu().numpy(), geom_oracle.iproj(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"][0].numpy()),
+                               rtol=1e-5, atol=1e-5)
+    ix = torch.arange(7)
+    th = torch.full((7,), 0.05)
+    cnt = droid_backends.depth_filter(poses, disps, intr[0].contiguous(), ix.to(dev()), th.to(dev()))
+    ref = geom_oracle.depth_filter(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"][0].numpy(), ix.numpy(), th.numpy())
+    assert (cnt.cpu().numpy() == ref).mean() > 0.995     # counts are integers; borderline |.|<t may flip
+    co, va = droid_backends.reproject(poses, disps, intr, ii.to(dev()), jj.to(dev()))
+    rco, rva = geom_oracle.reproject(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"].numpy(), ii.numpy(), jj.numpy())
+    np.testing.assert_allclose(co.cpu().numpy(), rco, rtol=1e-5, atol=1e-4)
+    np.testing.assert_array_equal(va.cpu().numpy(), rva)
+
+
+# ------------------------------------------------------------------------------ bundle adjustment
+def _ba_case(num_kf, ht, wd, rgbd, stereo_edges=0, seed=43, t0=1):
+    from goslam_b200 import synthetic
+    sc, g = synthetic.make_scene(num_kf=num_kf, ht=ht, wd=wd, rgbd=rgbd, seed=seed, with_fmaps=False,
+                                 stereo_edges=stereo_edges, buffer=num_kf + 3)
+    sc["t0"] = t0
+    coords, _ = geom_oracle.reproject(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"].numpy(),
+                                      sc["ii"].numpy(), sc["jj"].numpy())
+    targets, weights, eta = synthetic.make_update(sc, torch.from_numpy(coords[0]), g, noise=0.7)
+    # perturb the state so that BA has something to do
+    sc["poses"][1:num_kf, :3] += 0.01 * torch.randn(num_kf - 1, 3, generator=g)
+    sc["disps"][:num_kf] *= 1 + 0.03 * torch.randn(num_kf, ht, wd, generator=g)
+    return sc, targets, weights, eta
+
+
+@pytest.mark.parametrize("case", [
+    dict(num_kf=6, ht=12, wd=16, rgbd=True),
+    dict(num_kf=6, ht=12, wd=16, rgbd=False),
+    dict(num_kf=5, ht=9, wd=13, rgbd=True, stereo_edges=3),
+    dict(num_kf=8, ht=40, wd=80, rgbd=True),
+    dict(num_kf=8, ht=40, wd=80, rgbd=False, t0=2),
+])
+@pytest.mark.parametrize("motion_only", [False, True])
+def test_ba(case, motion_only):
+    from goslam_b200 import droid_backends
+    sc, targets, weights, eta = _ba_case(**case)
+    t0, t1 = sc["t0"], sc["t1"]
+    iters, lm, ep = 3, 1e-4, 0.1
+    poses = sc["poses"].clone().to(dev())
+    disps = sc["disps"].clone().to(dev())
+    dx, dz, status = droid_backends.ba(
+        poses, disps, sc["intrinsics"][0].to(dev()).contiguous(), sc["disps_sens"].to(dev()),
+        targets.to(dev()), weights.to(dev()), eta.to(dev()), sc["ii"].to(dev()), sc["jj"].to(dev()),
+        t0, t1, iters, lm, ep, motion_only, return_status=True)
+    rp, rd, rdx, rdz, rst = ba_oracle.ba(
+        sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"][0].numpy(), sc["disps_sens"].numpy(),
+        targets.numpy(), weights.numpy(), eta.numpy(), sc["ii"].numpy(), sc["jj"].numpy(),
+        t0, t1, iters, lm, ep, motion_only, dtype=np.float64)
+    assert status.cpu().numpy().tolist() == rst.tolist() == [0] * iters
+    # north_star tolerance: 1e-4 relative (fp32) on the updated state and the last step
+    assert _rel(poses.cpu().numpy(), rp) < 1e-4
+    assert _rel(dx.cpu().numpy(), rdx) < 2e-3          # dx is the *difference* of two ~equal iterates' worth
+    if not motion_only:
+        assert _rel(disps.cpu().numpy(), rd) < 1e-4
+        assert np.abs(dz.cpu().numpy() - rdz).max() < 1e-4 * max(np.abs(rd).max(), 1.0)
+    else:
+        assert torch.equal(disps.cpu(), sc["disps"])
+        assert dz is None
+    # frames outside [t0,t1) keep their pose
+    assert torch.equal(poses[:t0].cpu(), sc["poses"][:t0])
+    assert torch.equal(poses[t1:].cpu(), sc["poses"][t1:])
+
+
+def test_ba_failed_factorisation_gives_zero_step():
+    """negative weights make the reduced system indefinite: the reference falls back to dx = 0
+    (src/lib/droid_kernels.cu:1207-1210)."""
+    from goslam_b200 import droid_backends
+    sc, targets, weights, eta = _ba_case(num_kf=5, ht=9, wd=13, rgbd=False)
+    poses = sc["poses"].clone().to(dev())
+    disps = sc["disps"].clone().to(dev())
+    dx, dz, status = droid_backends.ba(
+        poses, disps, sc["intrinsics"][0].to(dev()).contiguous(), sc["disps_sens"].to(dev()),
+        targets.to(dev()), (-1e6 * weights).to(dev()), eta.to(dev()), sc["ii"].to(dev()), sc["jj"].to(dev()),
+        1, 5, 1, 1e-4, 0.1, True, return_status=True)
+    assert status.cpu().tolist() == [1]
+    assert float(dx.abs().max()) == 0.0
+    assert torch.equal(poses.cpu(), sc["poses"])
+
+
+# ------------------------------------------------------------------------------ renderer
+@pytest.mark.parametrize("R", [37, 256])
+def test_neus_forward(R):
+    from goslam_b200 import neus, synthetic
+    offs, ress, _, total = neus.hashgrid_layout()
+    metas, tot_entries = neus_oracle.hashgrid_meta()
+    assert total == 2 * tot_entries
+    w = synthetic.make_neus_weights(seed=7, total_grid_params=total, layout=(offs, ress))
+    bound = [[-2.0, 2.0], [-2.0, 2.0], [-2.0, 2.0]]
+    net = neus.InstantNeuS(synthetic.NEUS_CFG, bound)
+    with torch.no_grad():
+        net.sdf_network.encoding.encoding.params.copy_(w["grid"])
+        net.sdf_network.sdf_layer.weight.copy_(w["sdf_w"])
+        net.sdf_network.sdf_layer.bias.copy_(w["sdf_b"])
+        net.color_network._B.copy_(w["color_B"])
+        net.color_network.network.params.copy_(w["mlp"])
+    net = net.to(dev())
+    net.update_bound(torch.tensor([[-1.8, 1.9], [-2.0, 2.0], [-1.5, 2.0]]))
+    ro, rd, zv, ds = synthetic.make_rays(R, S=72, seed=11)
+    out = net(ro.to(dev()), rd.to(dev()), zv.to(dev()), ds.to(dev()))
+    ref = neus_oracle.forward(
+        w["grid"].half().numpy(), w["sdf_w"].numpy(), w["sdf_b"].numpy(), w["color_B"].numpy(),
+        w["mlp"].half().numpy(), np.array(bound, np.float32), net.realtime_bound.cpu().numpy(),
+        0.2, 10.0, ro.numpy(), rd.numpy(), zv.numpy(), ds.numpy())
+    assert set(out.keys()) == set(ref.keys())
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    assert (ref["weight_sum"] > 1e-3).mean() > 0.2, "degenerate test scene: nothing is rendered"
+    # fp32 quantities: 1e-4 relative to the tensor scale (north_star)
+    for k in ("z_vals", "sdf", "depth", "weight_sum", "normal", "depth_variance", "sdf_variance", "gradient_error"):
+        assert got[k].shape == ref[k].shape, k
+        assert _rel(got[k], ref[k]) < 2e-4, (k, _rel(got[k], ref[k]))
+    # rgb passes through fp16 activations and an fp16 sigmoid (the reference's own output dtype):
+    # one half-ulp of a value in [0.5,1) is 4.9e-4
+    assert np.abs(got["color"] - ref["color"]).max() < 1.5e-3
