@@ -149,14 +149,14 @@ __device__ __forceinline__ void store_relu_half(const float (&acc)[2][NT][4], __
 }
 
 struct Smem {
-  __half W1[kHid * kInPad];
-  __half W2[kHid * kHidPad];
-  __half W3[kOutW * kHidPad];
-  float sdfWT[35 * 32];          // transposed Linear weight: [k][out]
+  alignas(16) __half W1[kHid * kInPad];
+  alignas(16) __half W2[kHid * kHidPad];
+  alignas(16) __half W3[kOutW * kHidPad];
+  alignas(16) float sdfWT[35 * 32];          // transposed Linear weight: [k][out]
   float sdfB[32];
   float colB[3 * 33];
-  __half actA[kWarpsN][32 * kInPad];
-  __half actB[kWarpsN][32 * kHidPad];
+  alignas(16) __half actA[kWarpsN][32 * kInPad];
+  alignas(16) __half actB[kWarpsN][32 * kHidPad];
   // per-sample results of the current ray group
   float alpha[kRaysPerGroup * 128];
   float zmid[kRaysPerGroup * 128];
