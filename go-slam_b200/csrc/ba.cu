@@ -483,9 +483,10 @@ ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __re
     __syncthreads();
     // trailing update: A[i][c] -= L[i][j] * L[c][j], j < c <= i < n
     const int m = n - j - 1;
-    const long long tot = (long long)m * m;
-    for (long long idx = tid; idx < tot; idx += nt) {
-      const int i = j + 1 + (int)(idx / m), c = j + 1 + (int)(idx % m);
+    const int tot = m * m;                       // n <= 6*4096 => fits in int
+    for (int idx = tid; idx < tot; idx += nt) {
+      const int q = idx / m;
+      const int i = j + 1 + q, c = j + 1 + (idx - q * m);
       if (c <= i) A[(size_t)i * n + c] -= A[(size_t)i * n + j] * A[(size_t)c * n + j];
     }
     __syncthreads();
@@ -617,8 +618,10 @@ int launch_phase2(float* poses, float* disps, const double* sys_in,
                          (int)(((size_t)kSmemSolveMaxN * kSmemSolveMaxN + kSmemSolveMaxN) * 8));
     attr_set = true;
   }
-  ba_solve_kernel<<<1, 1024, smem, st>>>(poses, d, ws, sys_in, lm, ep, use_smem, dx_out,
-                                         status_out);
+  // barrier cost dominates small systems: use only as many warps as the trailing update can feed
+  const int threads = d.n <= 48 ? 64 : d.n <= 96 ? 128 : d.n <= kSmemSolveMaxN ? 256 : 1024;
+  ba_solve_kernel<<<1, threads, smem, st>>>(poses, d, ws, sys_in, lm, ep, use_smem, dx_out,
+                                            status_out);
   GS_CHECK_LAUNCH();
   if (!motion_only) {
     dim3 grid(ws.ntiles, d.num);

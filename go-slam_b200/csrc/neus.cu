@@ -220,11 +220,13 @@ neus_forward_kernel(const NeusArgs a) {
       bool inb = false;
       if (valid) {
         dist = a.dists[gidx];
-        zm = a.z_vals[gidx] + dist / 2.0f;
+        zm = __fadd_rn(a.z_vals[gidx], dist / 2.0f);
+        // op-by-op fp32 like the reference's separate torch kernels (no FMA contraction): the
+        // hash grid turns a 1-ulp difference in the position into a different fine-level cell
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           dir[c] = a.rays_d[(size_t)ray * 3 + c];
-          pt[c] = a.rays_o[(size_t)ray * 3 + c] + dir[c] * zm;
+          pt[c] = __fadd_rn(a.rays_o[(size_t)ray * 3 + c], __fmul_rn(dir[c], zm));
         }
         inb = pt[0] < a.p.rt_bound[1] && pt[0] > a.p.rt_bound[0] &&
               pt[1] < a.p.rt_bound[3] && pt[1] > a.p.rt_bound[2] &&
@@ -242,10 +244,10 @@ neus_forward_kernel(const NeusArgs a) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float b0 = a.p.bound[2 * c], b1 = a.p.bound[2 * c + 1];
-          const float raw = (pt[c] - b0) / (b1 - b0) * 2.0f - 1.0f;
+          const float raw = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(pt[c], b0), __fsub_rn(b1, b0)), 2.0f), 1.0f);
           xn[c] = fminf(fmaxf(raw, -1.0f), 1.0f);
           dscale[c] = (raw >= -1.0f && raw <= 1.0f) ? 2.0f / (b1 - b0) : 0.0f;
-          x01[c] = (xn[c] + 1.0f) / 2.0f;
+          x01[c] = __fdiv_rn(__fadd_rn(xn[c], 1.0f), 2.0f);
         }
         // SDF head accumulators start from bias + xyz part
         float out[32];

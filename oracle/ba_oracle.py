@@ -102,8 +102,11 @@ def _adj_se3_any(t, q, X):
 
 
 def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iterations,
-       lm, ep, motion_only, dtype=np.float32, return_debug=False):
-    """In-place-free restatement of droid_backends.ba: returns (poses, disps, dx, dz_by_frame, status)."""
+       lm, ep, motion_only, dtype=np.float32, return_debug=False, damping="reduced"):
+    """In-place-free restatement of droid_backends.ba: returns (poses, disps, dx, dz_by_frame, status).
+    damping="reduced" is the CUDA path (diag(A-S) += ep + lm*diag(A-S), :1196-1197);
+    damping="pose_block" is the convention of the reference's pure-torch BA (src/geom/chol.py:56-57:
+    damp H before subtracting E Q E^T) and exists only to cross-check against that code."""
     T = dtype
     poses = np.array(poses, np.float32, copy=True)
     disps = np.array(disps, np.float32, copy=True)
@@ -176,8 +179,8 @@ def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, 
             Hred, bred = A - S, b - v
         # ---- damped float64 LLT
         L = Hred.copy()
-        dg = np.diag(L).copy()
-        L[np.diag_indices(n)] = dg + np.float64(np.float32(ep)) + np.float64(np.float32(lm)) * dg
+        dg = np.diag(L).copy() if damping == "reduced" else np.diag(A).copy()
+        L[np.diag_indices(n)] = np.diag(L) + np.float64(np.float32(ep)) + np.float64(np.float32(lm)) * dg
         ok = True
         try:
             c = np.linalg.cholesky(L)

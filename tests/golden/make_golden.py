@@ -1,0 +1,261 @@
+"""Generate tests/golden/*.npz by running THE REFERENCE'S OWN PYTHON (imported from
+/root/reference, which exists only in the build container) on small seeded inputs.
+
+Stub modules stand in for natives that are absent from the snapshot:
+    droid_backends -> oracle.corr_oracle lookup (only CorrBlock.__call__ needs it)
+    lietorch       -> go-slam_b200/lietorch.py (host-side SE3 algebra, pinned by the CUDA twins)
+    torch_scatter  -> 6-line scatter_sum / scatter_mean
+    tinycudann     -> oracle.neus_oracle restatement (hash grid with autograd input-gradient, MLP)
+    mcubes, trimesh-> empty modules (only used by mesh extraction)
+What each fixture pins:
+    corr_block.npz    CorrBlock.__init__/corr/__call__           src/modules/corr.py:25-76
+    reproject.npz     pops.projective_transform (jacobian=False)  src/geom/projective_ops.py:114-144
+    ba_torch.npz      dx of the reference's dense pure-torch BA   src/geom/ba.py:26-101 + chol.py
+    neus.npz          InstantNeuS.forward (9 outputs)             src/InstantNeuS.py:295-370
+    render_z.npz      Renderer.render_batch_ray z-sampling        src/render.py:99-171
+Run:  python tests/golden/make_golden.py      (writes next to this file)
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from oracle import corr_oracle, neus_oracle  # noqa: E402
+
+
+def install_stubs():
+    import goslam_b200  # noqa: F401
+    from goslam_b200 import lietorch as lt
+    sys.modules["lietorch"] = lt
+
+    db = types.ModuleType("droid_backends")
+
+    def corr_index_forward(volume, coords, radius):
+        out = corr_oracle.corr_index_forward(volume.numpy(), coords.numpy(), radius)
+        return [torch.from_numpy(out)]
+    db.corr_index_forward = corr_index_forward
+    sys.modules["droid_backends"] = db
+
+    ts = types.ModuleType("torch_scatter")
+
+    def scatter_sum(src, index, dim=-1, dim_size=None):
+        shape = list(src.shape)
+        shape[dim] = dim_size if dim_size is not None else int(index.max()) + 1
+        out = torch.zeros(shape, dtype=src.dtype)
+        return out.index_add_(dim, index, src)
+
+    def scatter_mean(src, index, dim=-1, dim_size=None):
+        s = scatter_sum(src, index, dim, dim_size)
+        c = scatter_sum(torch.ones_like(src), index, dim, dim_size).clamp_min(1)
+        return s / c
+    ts.scatter_sum, ts.scatter_mean = scatter_sum, scatter_mean
+    sys.modules["torch_scatter"] = ts
+
+    for name in ("mcubes", "trimesh"):
+        sys.modules[name] = types.ModuleType(name)
+
+    # ---- tinycudann restatement ----------------------------------------------------------
+    tcnn = types.ModuleType("tinycudann")
+    metas, total_entries = neus_oracle.hashgrid_meta()
+
+    class _GridFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, params):
+            table = params.detach().half().numpy().reshape(-1, 2)
+            ctx.save_for_backward(x, params)
+            enc = neus_oracle.hashgrid_encode(x.detach().numpy().astype(np.float32), table)
+            return torch.from_numpy(enc)          # float16, like tcnn
+
+        @staticmethod
+        def backward(ctx, dy):
+            x, params = ctx.saved_tensors
+            table = params.detach().half().numpy().reshape(-1, 2)
+            # tcnn: per-sample dL/dy (cast to half) times d(enc)/dx in fp32
+            dyn = dy.detach().float().numpy()
+            assert np.allclose(dyn, dyn[:1]), "restatement assumes a sample-independent dL/dy"
+            g = neus_oracle.hashgrid_input_grad(x.detach().numpy().astype(np.float32), table, dyn[0])
+            return torch.from_numpy(g), None
+
+    class Encoding(torch.nn.Module):
+        def __init__(self, n_input_dims, encoding_config):
+            super().__init__()
+            assert encoding_config["otype"] == "HashGrid"
+            self.n_output_dims = 32
+            self.params = torch.nn.Parameter((torch.rand(total_entries * 2) * 2 - 1) * 1e-4)
+
+        def forward(self, x):
+            return _GridFn.apply(x, self.params)
+
+    class Network(torch.nn.Module):
+        def __init__(self, n_input_dims, n_output_dims, network_config):
+            super().__init__()
+            assert (n_input_dims, n_output_dims, network_config["n_neurons"]) == (67, 3, 64)
+            self.params = torch.nn.Parameter(torch.zeros(64 * 80 + 64 * 64 + 16 * 64))
+
+        def forward(self, x):
+            out = neus_oracle.mlp_forward(x.detach().float().numpy(), self.params.detach().half().numpy())
+            return torch.from_numpy(out)          # float16 [n,3]
+
+    tcnn.Encoding, tcnn.Network = Encoding, Network
+    sys.modules["tinycudann"] = tcnn
+
+    # torch.cuda.device(...) context is used at model construction; make it a no-op on CPU
+    class _NoDev:
+        def __init__(self, *a, **k):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+    torch.cuda.device = _NoDev
+
+
+def ref_import(name):
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    return importlib.import_module(name)
+
+
+def gen_corr_block():
+    corr_mod = ref_import("src.modules.corr")
+    g = torch.Generator().manual_seed(43)
+    N, h, w = 2, 16, 24      # >= 16: the reference pools once more after the last level
+    out = {}
+    for tag, dt in (("f32", torch.float32), ("f16", torch.float16)):
+        f1 = torch.randn(1, N, 128, h, w, generator=g).to(dt)
+        f2 = torch.randn(1, N, 128, h, w, generator=g).to(dt)
+        blk = corr_mod.CorrBlock(f1, f2)
+        coords = torch.stack(torch.meshgrid(torch.arange(w).float(), torch.arange(h).float(), indexing="xy"), -1)
+        coords = coords[None, None].repeat(1, N, 1, 1, 1) + 2.0 * torch.randn(1, N, h, w, 2, generator=g)
+        sampled = blk(coords)
+        out.update({tag + "_fmap1": f1.numpy(), tag + "_fmap2": f2.numpy(), tag + "_coords": coords.numpy(),
+                    tag + "_sampled": sampled.numpy()})
+        for i, p in enumerate(blk.corr_pyramid):
+            out["%s_level%d" % (tag, i)] = p.numpy()
+    np.savez_compressed(os.path.join(HERE, "corr_block.npz"), **out)
+
+
+def small_scene():
+    from goslam_b200 import synthetic
+    return synthetic.make_scene(num_kf=6, ht=12, wd=16, seed=43, rgbd=False, with_fmaps=False)
+
+
+def gen_reproject():
+    pops = ref_import("src.geom.projective_ops")
+    import lietorch
+    sc, g = small_scene()
+    ii = torch.cat([sc["ii"], torch.tensor([2, 3])])       # + two stereo (ii == jj) edges
+    jj = torch.cat([sc["jj"], torch.tensor([2, 3])])
+    coords, valid = pops.projective_transform(lietorch.SE3(sc["poses"][None]), sc["disps"][None],
+                                              sc["intrinsics"][None], ii, jj)
+    np.savez_compressed(os.path.join(HERE, "reproject.npz"), poses=sc["poses"].numpy(), disps=sc["disps"].numpy(),
+                        intrinsics=sc["intrinsics"].numpy(), ii=ii.numpy(), jj=jj.numpy(),
+                        coords=coords.numpy(), valid=valid.numpy())
+
+
+def gen_ba_torch():
+    """dx / dz of the reference's dense torch BA on a scene where its formulation and the CUDA one
+    coincide: no sensor depth (no prior), all points in front of both cameras (no MIN_DEPTH
+    clipping: 0.2 vs 0.25 never triggers), no stereo edges."""
+    sys.path.insert(0, os.path.join(REF, "src", "geom"))     # `import projective_ops` inside ba.py
+    ba_mod = ref_import("src.geom.ba")
+    import lietorch
+    from goslam_b200 import synthetic
+    from oracle import geom_oracle
+    sc, g = small_scene()
+    coords, _ = geom_oracle.reproject(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"].numpy(),
+                                      sc["ii"].numpy(), sc["jj"].numpy())
+    targets, weights, eta = synthetic.make_update(sc, torch.from_numpy(coords[0]), g, noise=0.7)
+    cap = {}
+    orig = ba_mod.schur_solve
+
+    def spy(H, E, C, v, w, **kw):
+        dx, dz = orig(H, E, C, v, w, **kw)
+        cap["dx"], cap["dz"] = dx, dz
+        return dx, dz
+    ba_mod.schur_solve = spy
+    N, ht, wd = sc["ii"].numel(), sc["ht"], sc["wd"]
+    tgt = targets.permute(0, 2, 3, 1)[None].contiguous()   # [1,N,h,w,2]
+    wgt = weights.permute(0, 2, 3, 1)[None].contiguous()
+    t0 = 1
+    kx = torch.unique(sc["ii"])
+    assert kx.numel() == eta.shape[0]
+    res = {}
+    for tag, dt in (("", torch.float32), ("64", torch.float64)):
+        torch.set_default_dtype(dt)      # the reference builds its stereo constant with torch.tensor([...])
+        poses = lietorch.SE3(sc["poses"][None].clone().to(dt))
+        ba_mod.BA(tgt.to(dt), wgt.to(dt), (eta[None] - 1e-7).to(dt), poses, sc["disps"][None].clone().to(dt),
+                  sc["intrinsics"][None].to(dt), sc["ii"], sc["jj"], fixedp=t0)
+        res["dx" + tag] = cap["dx"][0].numpy()
+        res["dz" + tag] = cap["dz"][0].numpy()
+    torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(HERE, "ba_torch.npz"), poses=sc["poses"].numpy(), disps=sc["disps"].numpy(),
+                        intrinsics=sc["intrinsics"].numpy(), ii=sc["ii"].numpy(), jj=sc["jj"].numpy(),
+                        targets=targets.numpy(), weights=weights.numpy(), eta=eta.numpy(), t0=t0, **res)
+
+
+def gen_neus():
+    neus_mod = ref_import("src.InstantNeuS")
+    from goslam_b200 import synthetic
+    metas, total_entries = neus_oracle.hashgrid_meta()
+    offs = [m["offset"] * 2 for m in metas] + [total_entries * 2]
+    ress = [m["res"] for m in metas]
+    w = synthetic.make_neus_weights(seed=7, total_grid_params=total_entries * 2, layout=(offs, ress))
+    bound = [[-2.0, 2.0], [-2.0, 2.0], [-2.0, 2.0]]
+    net = neus_mod.InstantNeuS(synthetic.NEUS_CFG, bound, device="cpu")
+    with torch.no_grad():
+        net.sdf_network.encoding.encoding.params.copy_(w["grid"])
+        net.sdf_network.sdf_layer.weight.copy_(w["sdf_w"])
+        net.sdf_network.sdf_layer.bias.copy_(w["sdf_b"])
+        net.color_network._B.copy_(w["color_B"])
+        net.color_network.network.params.copy_(w["mlp"])
+    rt = torch.tensor([[-1.8, 1.9], [-2.0, 2.0], [-1.5, 2.0]])
+    net.update_bound(rt)
+    ro, rd, zv, ds = synthetic.make_rays(48, S=72, seed=11)
+    out = net(ro, rd, zv, ds)
+    np.savez_compressed(os.path.join(HERE, "neus.npz"), rays_o=ro.numpy(), rays_d=rd.numpy(), z_vals_in=zv.numpy(),
+                        dists=ds.numpy(), rt_bound=rt.numpy(), bound=np.array(bound, np.float32), weights_seed=7,
+                        **{"out_" + k: v.detach().float().numpy() for k, v in out.items()})
+
+
+def gen_render_z():
+    render_mod = ref_import("src.render")
+    cfg = {"rendering": {"lindisp": False, "perturb": 1.0, "N_samples": 24, "N_surface": 48}}
+    slam = types.SimpleNamespace(H=64, W=64, fx=50.0, fy=50.0, cx=32.0, cy=32.0)
+    r = render_mod.Renderer(cfg, None, slam)
+    cap = {}
+
+    class Net:
+        bound = torch.tensor([[-2.0, 2.0], [-2.0, 2.0], [-2.0, 2.0]])
+
+        def __call__(self, ro, rd, zv, dst, render_params=None):
+            cap["z"], cap["d"] = zv, dst
+            return {"z": zv}
+    from goslam_b200 import synthetic
+    ro, rd, _, _ = synthetic.make_rays(32, S=72, seed=5)
+    depth = 0.5 + 2.0 * torch.rand(32, generator=torch.Generator().manual_seed(5))
+    depth[::7] = 0.0
+    torch.manual_seed(1234)
+    r.render_batch_ray(ro, rd, Net(), None, device="cpu", gt_depth=depth)
+    np.savez_compressed(os.path.join(HERE, "render_z.npz"), rays_o=ro.numpy(), rays_d=rd.numpy(), gt_depth=depth.numpy(),
+                        z_vals=cap["z"].numpy(), dists=cap["d"].numpy(), torch_seed=1234)
+
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF):
+        raise SystemExit("needs /root/reference (build container only)")
+    install_stubs()
+    which = sys.argv[1:] or ["corr_block", "reproject", "ba_torch", "neus", "render_z"]
+    for name in which:
+        globals()["gen_" + name]()
+        print("wrote", name)

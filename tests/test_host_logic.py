@@ -1,0 +1,125 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels are launched)."""
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geom_oracle
+
+
+def test_install_registers_reference_module_names():
+    import goslam_b200
+    saved = {k: sys.modules.get(k) for k in ("droid_backends", "lietorch")}
+    try:
+        db, lt = goslam_b200.install()
+        import droid_backends
+        import lietorch
+        assert droid_backends is db and lietorch is lt
+        # the nine functions of src/lib/droid.cpp:237-250
+        for fn in ("ba", "frame_distance", "projmap", "depth_filter", "iproj", "altcorr_forward",
+                   "altcorr_backward", "corr_index_forward", "corr_index_backward"):
+            assert callable(getattr(droid_backends, fn)), fn
+        assert hasattr(lietorch, "SE3") and hasattr(lietorch, "Sim3") and hasattr(lietorch, "cat")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_contiguity_and_device_errors_mirror_the_reference():
+    from goslam_b200 import droid_backends as db
+    vol = torch.zeros(1, 4, 4, 4, 4)
+    coords = torch.zeros(1, 2, 4, 4)
+    with pytest.raises(RuntimeError, match="must be contiguous"):
+        db.corr_index_forward(vol.transpose(1, 2), coords, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        db.corr_index_forward(vol, coords, 3)             # CPU tensors: no fallback
+    with pytest.raises(RuntimeError, match="training-only"):
+        db.corr_index_backward(vol, coords, vol, 3)
+    with pytest.raises(RuntimeError, match="training-only"):
+        db.altcorr_backward(vol, vol, coords, vol, 3)
+    poses = torch.zeros(4, 7)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        db.frame_distance(poses, torch.ones(4, 4, 4), torch.ones(4), torch.zeros(2).long(), torch.ones(2).long(), 0.3)
+
+
+def test_no_cpu_fallback_in_mirror_classes():
+    from goslam_b200.modules import CorrBlock
+    from goslam_b200 import neus, synthetic
+    f = torch.zeros(1, 1, 128, 16, 16).half()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CorrBlock(f, f)
+    net = neus.InstantNeuS(synthetic.NEUS_CFG, [[-1.0, 1.0]] * 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(2, 3), torch.ones(2, 3), torch.ones(2, 8), torch.ones(2, 8))
+
+
+def test_product_never_imports_oracle():
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "go-slam_b200")
+    for dp, _, fns in os.walk(root):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src, os.path.join(dp, fn)
+
+
+def _rand_se3(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(n, 4, generator=g)
+    q = q / q.norm(dim=-1, keepdim=True)
+    return torch.cat([torch.randn(n, 3, generator=g), q], dim=-1)
+
+
+def test_lietorch_shim_group_axioms_and_oracle_agreement():
+    from goslam_b200.lietorch import SE3
+    A, B = SE3(_rand_se3(5, 0)), SE3(_rand_se3(5, 1))
+    I = (A * A.inv()).data
+    assert torch.allclose(I[:, :3], torch.zeros(5, 3), atol=1e-5) and torch.allclose(I[:, 3:].abs(), torch.tensor([0, 0, 0, 1.0]).expand(5, 4), atol=1e-5)
+    X = torch.randn(5, 4)
+    # (A*B)*X == A*(B*X)
+    assert torch.allclose((A * B) * X, A * (B * X), atol=1e-5)
+    # relative pose == the CUDA twin relSE3 (src/lib/droid_kernels.cu:96-107)
+    rel = (B * A.inv()).data.numpy()
+    t, q = geom_oracle.rel_se3(A.data[:, :3].numpy(), A.data[:, 3:].numpy(), B.data[:, :3].numpy(), B.data[:, 3:].numpy())
+    assert np.allclose(rel[:, :3], t, atol=1e-5) and np.allclose(rel[:, 3:], q, atol=1e-5)
+    # act / adjT == actSE3 / adjSE3
+    Y = (A * X).numpy()
+    assert np.allclose(Y, geom_oracle.act_se3(A.data[:, :3].numpy(), A.data[:, 3:].numpy(), X.numpy()), atol=1e-5)
+    J = torch.randn(5, 6)
+    assert np.allclose(A.adjT(J).numpy(), geom_oracle.adj_se3(A.data[:, :3].numpy(), A.data[:, 3:].numpy(), J.numpy()), atol=1e-5)
+    # matrix() is the homogeneous form of act
+    M = A.matrix()
+    P = torch.randn(5, 3)
+    assert torch.allclose((M[:, :3, :3] @ P[..., None])[..., 0] + M[:, :3, 3], A * P, atol=1e-5)
+    # retraction == retrSE3 (left multiplication by exp)
+    xi = 0.1 * torch.randn(5, 6)
+    r = A.retr(xi).data.numpy()
+    t1, q1 = geom_oracle.retr_se3(xi.numpy(), A.data[:, :3].numpy(), A.data[:, 3:].numpy())
+    assert np.allclose(r[:, :3], t1, atol=1e-5) and np.allclose(r[:, 3:], q1, atol=1e-5)
+    assert np.allclose(SE3.exp(torch.zeros(2, 6)).data.numpy(), [[0, 0, 0, 0, 0, 0, 1]] * 2)
+
+
+def test_lietorch_shim_indexing_like_the_reference_call_sites():
+    from goslam_b200.lietorch import SE3, cat
+    G = SE3(_rand_se3(6, 2)[None])                 # [1, 6, 7] like DepthVideo.reproject
+    jj = torch.tensor([1, 2, 5])
+    assert G[:, jj].data.shape == (1, 3, 7)
+    assert G[:, :, None, None].data.shape == (1, 6, 1, 1, 7)
+    assert cat([G, G], 1).data.shape == (1, 12, 7)
+    assert SE3.Identity(1).data.tolist() == [[0, 0, 0, 0, 0, 0, 1]]
+    assert G.to(torch.float64).data.dtype == torch.float64
+
+
+def test_synthetic_graph_matches_reference_neighbourhood_rule():
+    from goslam_b200 import synthetic
+    ii, jj = synthetic.neighborhood_edges(0, 8, 3)
+    assert ii.numel() == 36
+    assert ((ii - jj).abs() <= 3).all() and (ii != jj).all()
+    sc, _ = synthetic.make_scene(8, 40, 80, with_fmaps=False)
+    sc2, _ = synthetic.make_scene(8, 40, 80, with_fmaps=False)
+    assert torch.equal(sc["poses"], sc2["poses"]) and torch.equal(sc["disps"], sc2["disps"])   # deterministic
+    assert abs(float(sc["poses"][:, 3:].norm(dim=-1).mean()) - 1.0) < 1e-5
