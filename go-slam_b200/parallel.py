@@ -1,0 +1,114 @@
+"""One factor graph sharded over the GPUs of a box — host-side logic.
+
+Edges are partitioned BY SOURCE KEYFRAME `ii` (all outgoing edges of a frame live on one rank),
+which keeps every per-pixel depth quantity (C, w, Q, the Schur products of a depth frame) local.
+Per Gauss-Newton iteration the only exchange is ONE all-reduce(sum) of the reduced camera system
+[(6P)^2 + 6P] float64 (0.57 MB at P = 63, latency bound on NVLink/NVSwitch); every rank then solves
+the identical system redundantly, retracts all poses, back-substitutes the depth of the frames it
+owns, and the updated disparity rows are re-replicated.
+
+The kernels are reached through a small backend object so the same driver runs
+  * on GPUs   : CudaBackend  -> goslam_ba_phase1 / goslam_ba_phase2 over NCCL,
+  * in tests  : any object with the same two methods over gloo (tests/test_sharded_ba_gloo.py).
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+
+def shard_frames_by_edges(ii, num_frames, world):
+    """Contiguous frame ranges [lo, hi) per rank, balanced by outgoing-edge count.
+    Deterministic and identical on every rank (pure function of ii)."""
+    counts = torch.bincount(ii.cpu().long(), minlength=num_frames).tolist()
+    total = sum(counts)
+    bounds, acc, lo = [], 0, 0
+    for r in range(world):
+        target = total * (r + 1) / world
+        hi = lo
+        while hi < num_frames and (acc + counts[hi] <= target or hi == lo and r < world - 1 and acc < target):
+            acc += counts[hi]
+            hi += 1
+        if r == world - 1:
+            hi = num_frames
+        bounds.append((lo, hi))
+        lo = hi
+    return bounds
+
+
+def local_edges(ii, lo, hi):
+    return ((ii >= lo) & (ii < hi)).nonzero(as_tuple=False).reshape(-1)
+
+
+class CudaBackend:
+    """goslam_ba_phase1 / goslam_ba_phase2 on the current CUDA device."""
+
+    def __init__(self, poses, disps, intrinsics, disps_sens, t0, t1):
+        from . import _lib
+        from .droid_backends import _workspace
+        self._lib, self._workspace = _lib, _workspace
+        self.poses, self.disps, self.intr, self.sens = poses, disps, intrinsics, disps_sens
+        self.t0, self.t1 = int(t0), int(t1)
+        self.num, self.ht, self.wd = disps.shape
+
+    def _ws(self, N):
+        lib = self._lib.load()
+        n = lib.goslam_ba_workspace_bytes(N, self.num, self.ht, self.wd, self.t0, self.t1)
+        return self._workspace(n, self.poses.device)
+
+    def phase1(self, targets, weights, eta_by_frame, ii, jj, motion_only):
+        lib = self._lib.load()
+        self.N = int(ii.shape[0])
+        ws = self._ws(self.N)
+        n_sys = lib.goslam_ba_system_doubles(self.t0, self.t1)
+        system = torch.empty(n_sys, dtype=torch.float64, device=self.poses.device)
+        # eta rows must follow this rank's own slot order (unique([t0,t1) U local ii))
+        kx = torch.unique(torch.cat([torch.arange(self.t0, self.t1, device=ii.device), ii]))
+        eta = eta_by_frame.view(self.num, -1)[kx].contiguous()
+        rc = lib.goslam_ba_phase1(
+            self._lib.ptr(self.poses), self._lib.ptr(self.disps), self._lib.ptr(self.intr), self._lib.ptr(self.sens),
+            self._lib.ptr(targets), self._lib.ptr(weights), self._lib.ptr(eta), int(eta.shape[0]),
+            self._lib.ptr(ii), self._lib.ptr(jj), self.N, self.num, self.ht, self.wd, self.t0, self.t1,
+            int(bool(motion_only)), self._lib.ptr(system), self._lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+            self._lib.stream_ptr())
+        self._lib.check(rc, "ba_phase1")
+        return system
+
+    def phase2(self, system, lm, ep, motion_only, owner_lo, owner_hi):
+        lib = self._lib.load()
+        ws = self._ws(self.N)
+        dx = torch.empty((self.t1 - self.t0, 6), dtype=torch.float32, device=self.poses.device)
+        rc = lib.goslam_ba_phase2(
+            self._lib.ptr(self.poses), self._lib.ptr(self.disps), self._lib.ptr(system), self.N, self.num,
+            self.ht, self.wd, self.t0, self.t1, float(lm), float(ep), int(bool(motion_only)),
+            int(owner_lo), int(owner_hi), self._lib.ptr(dx), None, None,
+            self._lib.ptr(ws), ctypes.c_size_t(ws.numel()), self._lib.stream_ptr())
+        self._lib.check(rc, "ba_phase2")
+        return dx
+
+
+def sharded_ba(backend, disps, targets, weights, eta_by_frame, ii, jj, iterations, lm, ep,
+               motion_only=False, group=None):
+    """Run `iterations` Gauss-Newton steps of ONE graph whose edges are sharded by source frame.
+
+    `targets` / `weights` / `ii` / `jj` are the FULL (replicated) edge list; each rank picks its
+    shard.  `disps` is the replicated [num, ht, wd] tensor the backend mutates; `eta_by_frame` is
+    [num, ht, wd] (frame-indexed damping).  Returns the last dx."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    num = disps.shape[0]
+    bounds = shard_frames_by_edges(ii, num, world)
+    lo, hi = bounds[rank]
+    sel = local_edges(ii, lo, hi)
+    tl, wl = targets[sel].contiguous(), weights[sel].contiguous()
+    il, jl = ii[sel].contiguous(), jj[sel].contiguous()
+    dx = None
+    for _ in range(iterations):
+        system = backend.phase1(tl, wl, eta_by_frame, il, jl, motion_only)
+        dist.all_reduce(system, op=dist.ReduceOp.SUM, group=group)        # the single exchange step
+        dx = backend.phase2(system, lm, ep, motion_only, lo, hi)
+        if not motion_only:
+            for r, (a, b) in enumerate(bounds):                           # re-replicate owned rows
+                if b > a:
+                    dist.broadcast(disps[a:b], src=dist.get_global_rank(group, r) if group else r, group=group)
+    return dx

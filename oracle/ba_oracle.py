@@ -101,118 +101,143 @@ def _adj_se3_any(t, q, X):
     return np.concatenate([_act_so3_any(qi, a), _act_so3_any(qi, b) + _act_so3_any(qi, u)], axis=-1)
 
 
+def phase1(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, motion_only,
+           dtype=np.float32):
+    """Linearise the given (local) edges and build their contribution to the reduced camera
+    system (A - S | b - v) in float64, plus what the back-substitution needs."""
+    T = dtype
+    ii = np.asarray(ii, np.int64)
+    jj = np.asarray(jj, np.int64)
+    N = len(ii)
+    num, ht, wd = np.asarray(disps).shape
+    hw = ht * wd
+    P = t1 - t0
+    n = 6 * P
+    ts = np.arange(t0, t1)
+    ii_exp = np.concatenate([ts, ii])
+    jj_exp = np.concatenate([ts, jj])
+    kx, kk_exp = np.unique(ii_exp, return_inverse=True)
+    M = len(kx)
+    lin = linearize(poses, disps, intrinsics, targets, weights, ii, jj, dtype=T) if N > 0 else None
+    # ---- pose x pose block A (float64, like the Eigen triplets)
+    A = np.zeros((n, n), np.float64)
+    b = np.zeros(n, np.float64)
+    for kblk, (ri, ci) in enumerate([(ii, ii), (ii, jj), (jj, ii), (jj, jj)]):
+        for e in range(N):
+            r, c = ri[e] - t0, ci[e] - t0
+            if r >= 0 and c >= 0 and r < P and c < P:
+                A[6 * r:6 * r + 6, 6 * c:6 * c + 6] += lin["Hs"][kblk, e].astype(np.float32).astype(np.float64)
+    for kblk, ri in enumerate((ii, jj)):
+        for e in range(N):
+            r = ri[e] - t0
+            if 0 <= r < P:
+                b[6 * r:6 * r + 6] += lin["vs"][kblk, e].astype(np.float32).astype(np.float64)
+    st = dict(A=A, kx=kx, kk_exp=kk_exp, jj_exp=jj_exp, P=P, N=N, lin=lin)
+    if motion_only:
+        st.update(Hred=A, bred=b)
+        return st
+    disps = np.asarray(disps, np.float32)
+    disps_sens = np.asarray(disps_sens, np.float32)
+    alpha = T(0.05)
+    m = (disps_sens[kx].reshape(M, hw) > 0).astype(T)
+    eta_a = np.asarray(eta, np.float32).reshape(-1, hw).astype(T)
+    if eta_a.shape[0] == num:          # frame-indexed eta (sharded callers): pick the rows of kx
+        eta_a = eta_a[kx]
+    eta_m = np.broadcast_to(eta_a, (M, hw))
+    C = np.zeros((M, hw), T)
+    w = np.zeros((M, hw), T)
+    for e in range(N):
+        k = kk_exp[P + e]
+        C[k] += lin["Cii"][e]
+        w[k] += lin["bz"][e]
+    C = C + m * alpha + (1 - m) * eta_m
+    w = w - m * alpha * (disps[kx].reshape(M, hw).astype(T) - disps_sens[kx].reshape(M, hw).astype(T))
+    Q = (T(1.0) / C).astype(T)
+    Ei = np.zeros((P, 6, hw), T)
+    for e in range(N):
+        p = ii[e] - t0
+        if 0 <= p < P:
+            Ei[p] += lin["Eii"][e]
+    E = np.concatenate([Ei, lin["Eij"].astype(T)], axis=0) if N > 0 else Ei     # [P+N,6,hw]
+    # ---- Schur complement (schur_block): entries n with t0 <= jj_exp[n] < t1
+    S = np.zeros((n, n), np.float64)
+    v = np.zeros(n, np.float64)
+    for k in range(M):
+        ent = [a for a in range(P + N) if kk_exp[a] == k and t0 <= jj_exp[a] < t1]
+        for a in ent:
+            pa = jj_exp[a] - t0
+            EaQ = E[a] * Q[k][None]
+            v[6 * pa:6 * pa + 6] += (EaQ * w[k][None]).sum(-1).astype(np.float32).astype(np.float64)
+            for bb in ent:
+                pb = jj_exp[bb] - t0
+                S[6 * pa:6 * pa + 6, 6 * pb:6 * pb + 6] += (EaQ @ E[bb].T).astype(np.float32).astype(np.float64)
+    st.update(Hred=A - S, bred=b - v, E=E, Q=Q, w=w, C=C)
+    return st
+
+
+def solve(Hred, bred, A, lm, ep, damping="reduced"):
+    """diag += ep + lm*diag, float64 LLT, failure => zero step (:1192-1213)."""
+    n = Hred.shape[0]
+    L = Hred.copy()
+    dg = np.diag(L).copy() if damping == "reduced" else np.diag(A).copy()
+    L[np.diag_indices(n)] = np.diag(L) + np.float64(np.float32(ep)) + np.float64(np.float32(lm)) * dg
+    try:
+        c = np.linalg.cholesky(L)
+        x = np.linalg.solve(c.T, np.linalg.solve(c, bred))
+        ok = bool(np.all(np.isfinite(x)))
+    except np.linalg.LinAlgError:
+        ok = False
+    P = n // 6
+    return (x.reshape(P, 6).astype(np.float32) if ok else np.zeros((P, 6), np.float32)), (0 if ok else 1)
+
+
+def phase2(st, dx, poses, disps, t0, t1, motion_only, owner_lo=0, owner_hi=None):
+    """Back-substitute dz for the frames in [owner_lo, owner_hi) and retract.  In place on copies
+    the caller owns; returns dz indexed by frame."""
+    num, ht, wd = disps.shape
+    hw = ht * wd
+    owner_hi = num if owner_hi is None else owner_hi
+    P, N, kx, kk_exp, jj_exp = st["P"], st["N"], st["kx"], st["kk_exp"], st["jj_exp"]
+    dz_frames = np.zeros((num, hw), np.float32)
+    if not motion_only:
+        E, Q, w = st["E"], st["Q"], st["w"]
+        T = E.dtype.type
+        ix = jj_exp - t0
+        acc = np.zeros_like(Q)
+        for a in range(P + N):
+            if 0 < ix[a] < P:                     # EvT6x1 skips pose index <= 0 (:1105)
+                acc[kk_exp[a]] += (E[a] * dx[ix[a]].astype(T)[:, None]).sum(0)
+        dz = (Q * (w - acc)).astype(np.float32)
+        own = (kx >= owner_lo) & (kx < owner_hi)
+        d = disps.reshape(num, hw)
+        d[kx[own]] = d[kx[own]] + dz[own]
+        dz_frames[kx[own]] = dz[own]
+    tn, qn = G.retr_se3(dx, poses[t0:t1, :3], poses[t0:t1, 3:])
+    poses[t0:t1, :3] = tn
+    poses[t0:t1, 3:] = qn
+    return dz_frames
+
+
 def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iterations,
        lm, ep, motion_only, dtype=np.float32, return_debug=False, damping="reduced"):
     """In-place-free restatement of droid_backends.ba: returns (poses, disps, dx, dz_by_frame, status).
     damping="reduced" is the CUDA path (diag(A-S) += ep + lm*diag(A-S), :1196-1197);
     damping="pose_block" is the convention of the reference's pure-torch BA (src/geom/chol.py:56-57:
     damp H before subtracting E Q E^T) and exists only to cross-check against that code."""
-    T = dtype
     poses = np.array(poses, np.float32, copy=True)
     disps = np.array(disps, np.float32, copy=True)
-    disps_sens = np.asarray(disps_sens, np.float32)
-    ii = np.asarray(ii, np.int64)
-    jj = np.asarray(jj, np.int64)
-    N = len(ii)
     num, ht, wd = disps.shape
-    hw = ht * wd
     P = t1 - t0
-    ts = np.arange(t0, t1)
-    ii_exp = np.concatenate([ts, ii])
-    jj_exp = np.concatenate([ts, jj])
-    kx, kk_exp = np.unique(ii_exp, return_inverse=True)
-    M = len(kx)
-    n = 6 * P
     dx = np.zeros((P, 6), np.float32)
-    dz_frames = np.zeros((num, hw), np.float32)
-    status = []
-    debug = {}
+    dz_frames = np.zeros((num, ht * wd), np.float32)
+    status, debug = [], {}
     for _ in range(iterations):
-        lin = linearize(poses, disps, intrinsics, targets, weights, ii, jj, dtype=T)
-        # ---- pose x pose block A (float64, like the Eigen triplets)
-        A = np.zeros((n, n), np.float64)
-        b = np.zeros(n, np.float64)
-        blocks = [(ii, ii), (ii, jj), (jj, ii), (jj, jj)]
-        for kblk, (ri, ci) in enumerate(blocks):
-            for e in range(N):
-                r, c = ri[e] - t0, ci[e] - t0
-                if r >= 0 and c >= 0 and r < P and c < P:
-                    A[6 * r:6 * r + 6, 6 * c:6 * c + 6] += lin["Hs"][kblk, e].astype(np.float32).astype(np.float64)
-        for kblk, ri in enumerate((ii, jj)):
-            for e in range(N):
-                r = ri[e] - t0
-                if 0 <= r < P:
-                    b[6 * r:6 * r + 6] += lin["vs"][kblk, e].astype(np.float32).astype(np.float64)
-        if motion_only:
-            Hred, bred = A, b
-        else:
-            alpha = T(0.05)
-            m = (disps_sens[kx].reshape(M, hw) > 0).astype(T)
-            eta_m = np.broadcast_to(np.asarray(eta, np.float32).reshape(-1, hw).astype(T), (M, hw))
-            C = np.zeros((M, hw), T)
-            w = np.zeros((M, hw), T)
-            for e in range(N):
-                k = kk_exp[P + e]
-                C[k] += lin["Cii"][e]
-                w[k] += lin["bz"][e]
-            C = C + m * alpha + (1 - m) * eta_m
-            w = w - m * alpha * (disps[kx].reshape(M, hw).astype(T) - disps_sens[kx].reshape(M, hw).astype(T))
-            Q = (T(1.0) / C).astype(T)
-            Ei = np.zeros((P, 6, hw), T)
-            for e in range(N):
-                p = ii[e] - t0
-                if 0 <= p < P:
-                    Ei[p] += lin["Eii"][e]
-            E = np.concatenate([Ei, lin["Eij"].astype(T)], axis=0)           # [P+N,6,hw]
-            # ---- Schur complement (schur_block): entries n with t0 <= jj_exp[n] < t1
-            S = np.zeros((n, n), np.float64)
-            v = np.zeros(n, np.float64)
-            for k in range(M):
-                ent = [a for a in range(P + N) if kk_exp[a] == k and t0 <= jj_exp[a] < t1]
-                for a in ent:
-                    pa = jj_exp[a] - t0
-                    EaQ = E[a] * Q[k][None]
-                    v[6 * pa:6 * pa + 6] += (EaQ * w[k][None]).sum(-1).astype(np.float32).astype(np.float64)
-                    for bb in ent:
-                        pb = jj_exp[bb] - t0
-                        S[6 * pa:6 * pa + 6, 6 * pb:6 * pb + 6] += (EaQ @ E[bb].T).astype(np.float32).astype(np.float64)
-            Hred, bred = A - S, b - v
-        # ---- damped float64 LLT
-        L = Hred.copy()
-        dg = np.diag(L).copy() if damping == "reduced" else np.diag(A).copy()
-        L[np.diag_indices(n)] = np.diag(L) + np.float64(np.float32(ep)) + np.float64(np.float32(lm)) * dg
-        ok = True
-        try:
-            c = np.linalg.cholesky(L)
-            x = np.linalg.solve(c.T, np.linalg.solve(c, bred))
-            ok = bool(np.all(np.isfinite(x)))
-        except np.linalg.LinAlgError:
-            ok = False
-        dx = x.reshape(P, 6).astype(np.float32) if ok else np.zeros((P, 6), np.float32)
-        status.append(0 if ok else 1)
+        st = phase1(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, motion_only, dtype)
+        dx, fail = solve(st["Hred"], st["bred"], st["A"], lm, ep, damping)
+        status.append(fail)
         if return_debug:
-            debug = dict(Hred=Hred, bred=bred, lin=lin)
-        if not motion_only:
-            ix = jj_exp - t0
-            dw = np.zeros((P + N, hw), T)
-            for a in range(P + N):
-                if 0 < ix[a] < P:
-                    dw[a] = (E[a] * dx[ix[a]].astype(T)[:, None]).sum(0)
-            acc = np.zeros((M, hw), T)
-            for a in range(P + N):
-                acc[kk_exp[a]] += dw[a]
-            dz = (Q * (w - acc)).astype(np.float32)
-            if return_debug:
-                debug.update(Q=Q, w=w, C=C, E=E)
-        # ---- retraction
-        tn, qn = G.retr_se3(dx, poses[t0:t1, :3], poses[t0:t1, 3:])
-        poses[t0:t1, :3] = tn
-        poses[t0:t1, 3:] = qn
-        if not motion_only:
-            d = disps.reshape(num, hw)
-            d[kx] = d[kx] + dz
-            dz_frames[:] = 0
-            dz_frames[kx] = dz
+            debug = {k: st[k] for k in ("Hred", "bred", "lin", "E", "Q", "w", "C") if k in st}
+        dz_frames = phase2(st, dx, poses, disps, t0, t1, motion_only)
     out = (poses, disps, dx, dz_frames, np.asarray(status, np.int32))
     return out + (debug,) if return_debug else out
 
