@@ -4,7 +4,7 @@
 // Reference: CorrBlock.__init__ / CorrBlock.corr (src/modules/corr.py:25-41,67-76) —
 // torch.matmul (cuBLAS) writes level 0, then three F.avg_pool2d passes re-read the volume.
 //
-// Design (one CTA per SM, persistent, warp-specialised, 192 threads):
+// Design (one CTA per SM, persistent, warp-specialised, 320 threads):
 //   warp 0      TMA producer: A tile = 128 source pixels x 128 channels (2 boxes of 64 ch,
 //               128B-swizzled, K-major) once per work item; B tile = an 8x16 patch of TARGET
 //               pixels x 128 channels (4-D tensor map (ch, x, y, edge) -> rows ordered
@@ -12,7 +12,7 @@
 //   warp 1      MMA issuer: 8 x tcgen05.mma (M128,N128,K16, fp16 in / fp32 accumulate in
 //               TMEM) per tile, 2 accumulator stages (256 TMEM columns), tcgen05.commit
 //               releases smem stages / publishes accumulators through mbarriers.
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns) -> x 1/16 -> fp16 -> level 0
+//   warps 2-9   epilogue (two groups of 4, one per TMEM stage): tcgen05.ld (32 lanes x 32 columns) -> x 1/16 -> fp16 -> level 0
 //               rows (32 B per (source pixel, target row)); because one thread holds the whole
 //               8x16 target patch of its source pixel, levels 1..3 (4x8, 2x4, 1x2) are pooled
 //               in registers from the ROUNDED finer level, exactly like avg_pool2d on fp16,
@@ -37,7 +37,8 @@ constexpr int kKBox = 64;               // channels per TMA box (128 B)
 constexpr int kTileBytes = kBM * kD * 2;          // 32 KB (A or B tile)
 constexpr int kBoxBytes = kBM * kKBox * 2;        // 16 KB
 constexpr int kAStages = 2, kBStages = 3, kTStages = 2;
-constexpr int kThreadsTC = 192;
+constexpr int kEpiGroups = 2;               // one epilogue warp-group (4 warps) per TMEM stage
+constexpr int kThreadsTC = 64 + kEpiGroups * 128;
 constexpr int kSmemTC = 1024 + (kAStages + kBStages) * kTileBytes + 256;
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -146,6 +147,9 @@ struct TcParams {
   int num_levels, N, h, w, hw;
   int n_mt, n_yb, n_xb;       // m-tiles, y-blocks, x-blocks
   int n_items;                // N * n_mt * n_yb
+  // optional edge -> feature-map-slot indirection (video-level K-major feature maps):
+  // slot1 = rig*ii[e], slot2 = rig*jj[e] + (ii[e]==jj[e])   (src/factor_graph.py:108-113,290)
+  const int64_t* ii; const int64_t* jj; int rig;
 };
 
 // ---- packed fp16 rows live in registers as uint32 pairs (lo = even column) ----
@@ -172,6 +176,12 @@ template <int NW>
 __device__ __forceinline__ void store_row(__half* dst, const uint32_t (&r)[NW], int nvalid) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
   if (nvalid >= 2 * NW) {
+    if (NW == 8 && (a & 31) == 0) {     // one full 32-byte sector per lane (STG.256)
+      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(r[0]),
+                   "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                   : "memory");
+      return;
+    }
     if (NW >= 4 && (a & 15) == 0) {
 #pragma unroll
       for (int i = 0; i < NW; i += 4)
@@ -235,17 +245,23 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
         const int yb = item % p.n_yb;
         const int mt = (item / p.n_yb) % p.n_mt;
         const int n = item / (p.n_yb * p.n_mt);
+        int n1 = n, n2 = n;
+        if (p.ii != nullptr) {
+          const int fi = (int)p.ii[n], fj = (int)p.jj[n];
+          n1 = p.rig * fi;
+          n2 = p.rig * fj + (fi == fj ? 1 : 0) * (p.rig > 1 ? 1 : 0);
+        }
         mbar_wait(&empty_a[as], aph ^ 1);
         mbar_expect_tx(&full_a[as], kTileBytes);
-        tma_load_3d(&mapA, &full_a[as], smA + as * kTileBytes, 0, mt * kBM, n);
-        tma_load_3d(&mapA, &full_a[as], smA + as * kTileBytes + kBoxBytes, kKBox, mt * kBM, n);
+        tma_load_3d(&mapA, &full_a[as], smA + as * kTileBytes, 0, mt * kBM, n1);
+        tma_load_3d(&mapA, &full_a[as], smA + as * kTileBytes + kBoxBytes, kKBox, mt * kBM, n1);
         if (++as == kAStages) { as = 0; aph ^= 1; }
         for (int xb = 0; xb < p.n_xb; ++xb) {
           mbar_wait(&empty_b[bs], bph ^ 1);
           mbar_expect_tx(&full_b[bs], kTileBytes);
-          tma_load_4d(&mapB, &full_b[bs], smB + bs * kTileBytes, 0, xb * kPX, yb * kPY, n);
+          tma_load_4d(&mapB, &full_b[bs], smB + bs * kTileBytes, 0, xb * kPX, yb * kPY, n2);
           tma_load_4d(&mapB, &full_b[bs], smB + bs * kTileBytes + kBoxBytes, kKBox, xb * kPX,
-                      yb * kPY, n);
+                      yb * kPY, n2);
           if (++bs == kBStages) { bs = 0; bph ^= 1; }
         }
       }
@@ -282,10 +298,13 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9: two groups of 4) =====================
+    // group g drains TMEM stage g only, so two tiles are in flight in the store path.
+    const int group = (warp - 2) >> 2;
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;             // row of the 128-row tile
-    int ts = 0, tph = 0;
+    const int ts = group;
+    int tph = 0, tile = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int yb = item % p.n_yb;
       const int mt = (item / p.n_yb) % p.n_mt;
@@ -294,7 +313,8 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
       const bool src_ok = src < p.hw;
       const long long plane_id = (long long)n * p.hw + src;
       const int y0 = yb * kPY;
-      for (int xb = 0; xb < p.n_xb; ++xb) {
+      for (int xb = 0; xb < p.n_xb; ++xb, ++tile) {
+        if ((tile & (kTStages - 1)) != ts) continue;
         const int x0 = xb * kPX;
         mbar_wait(&tm_full[ts], tph);
         tc_fence_after();
@@ -352,7 +372,7 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
           const int y = y0 >> 3, x = x0 >> 3;
           if (y < h3 && x < w3) store_row<1>(p.lvl[3] + (plane_id * h3 + y) * w3 + x, l3, w3 - x);
         }
-        if (++ts == kTStages) { ts = 0; tph ^= 1; }
+        tph ^= 1;
       }
     }
   }
@@ -401,38 +421,30 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int build_tc(const __half* f1, const __half* f2, __half* const* levels, int num_levels, int N,
-             int h, int w, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+// launch the tensor-core kernel on K-major operands: f1t/f2t = [F1|F2, hw, 128]
+int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_t* ii,
+              const int64_t* jj, int rig, __half* const* levels, int num_levels, int N, int h, int w,
+              cudaStream_t st) {
   const int hw = h * w;
-  const size_t per = (size_t)N * hw * kD * sizeof(__half);
-  if (workspace == nullptr || workspace_bytes < 2 * gs_align(per)) return GOSLAM_EWORKSPACE;
-  __half* f1t = reinterpret_cast<__half*>(workspace);
-  __half* f2t = reinterpret_cast<__half*>(reinterpret_cast<char*>(workspace) + gs_align(per));
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return GOSLAM_ELAUNCH;
-
-  dim3 tg(gs_cdiv(hw, 64), N);
-  to_kmajor_kernel<<<tg, 256, 0, st>>>(f1, f1t, hw);
-  to_kmajor_kernel<<<tg, 256, 0, st>>>(f2, f2t, hw);
-  GS_CHECK_LAUNCH();
-
   CUtensorMap mapA, mapB;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)hw, (cuuint64_t)N};
+    cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)hw, (cuuint64_t)F1};
     cuuint64_t strides[2] = {(cuuint64_t)kD * 2, (cuuint64_t)hw * kD * 2};
     cuuint32_t box[3] = {(cuuint32_t)kKBox, (cuuint32_t)kBM, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    if (enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, f1t, dims, strides, box, es,
+    if (enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(f1t), dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return GOSLAM_ELAUNCH;
   }
   {
-    cuuint64_t dims[4] = {(cuuint64_t)kD, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)N};
+    cuuint64_t dims[4] = {(cuuint64_t)kD, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)F2};
     cuuint64_t strides[3] = {(cuuint64_t)kD * 2, (cuuint64_t)w * kD * 2, (cuuint64_t)hw * kD * 2};
     cuuint32_t box[4] = {(cuuint32_t)kKBox, (cuuint32_t)kPX, (cuuint32_t)kPY, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    if (enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, f2t, dims, strides, box, es,
+    if (enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(f2t), dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return GOSLAM_ELAUNCH;
@@ -442,6 +454,7 @@ int build_tc(const __half* f1, const __half* f2, __half* const* levels, int num_
   p.num_levels = num_levels; p.N = N; p.h = h; p.w = w; p.hw = hw;
   p.n_mt = gs_cdiv(hw, kBM); p.n_yb = gs_cdiv(h, kPY); p.n_xb = gs_cdiv(w, kPX);
   p.n_items = N * p.n_mt * p.n_yb;
+  p.ii = ii; p.jj = jj; p.rig = rig;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(corr_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -461,6 +474,20 @@ int build_tc(const __half* f1, const __half* f2, __half* const* levels, int num_
   return GOSLAM_OK;
 }
 
+int build_tc(const __half* f1, const __half* f2, __half* const* levels, int num_levels, int N,
+             int h, int w, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int hw = h * w;
+  const size_t per = (size_t)N * hw * kD * sizeof(__half);
+  if (workspace == nullptr || workspace_bytes < 2 * gs_align(per)) return GOSLAM_EWORKSPACE;
+  __half* f1t = reinterpret_cast<__half*>(workspace);
+  __half* f2t = reinterpret_cast<__half*>(reinterpret_cast<char*>(workspace) + gs_align(per));
+  dim3 tg(gs_cdiv(hw, 64), N);
+  to_kmajor_kernel<<<tg, 256, 0, st>>>(f1, f1t, hw);
+  to_kmajor_kernel<<<tg, 256, 0, st>>>(f2, f2t, hw);
+  GS_CHECK_LAUNCH();
+  return launch_tc(f1t, N, f2t, N, nullptr, nullptr, 1, levels, num_levels, N, h, w, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -468,6 +495,28 @@ extern "C" {
 size_t goslam_corr_build_workspace_bytes(int N, int D, int h, int w) {
   if (N <= 0 || D != kD) return 256;
   return 2 * gs_align((size_t)N * h * w * kD * sizeof(__half)) + 256;
+}
+
+int goslam_fmaps_to_kmajor(const void* fmaps, void* out, int F, int D, int h, int w, void* stream) {
+  if (F < 0 || D != kD || h <= 0 || w <= 0) return GOSLAM_EINVAL;
+  if (F == 0) return GOSLAM_OK;
+  dim3 tg(gs_cdiv(h * w, 64), F);
+  to_kmajor_kernel<<<tg, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(fmaps),
+                                                         reinterpret_cast<__half*>(out), h * w);
+  GS_CHECK_LAUNCH();
+  return GOSLAM_OK;
+}
+
+int goslam_corr_build_indexed(const void* fmaps_kmajor, int F, int rig, const int64_t* ii,
+                              const int64_t* jj, void* const* levels, int num_levels, int N, int D,
+                              int h, int w, void* stream) {
+  if (N < 0 || F <= 0 || rig < 1 || D != kD || h <= 0 || w <= 0 || num_levels < 1 || num_levels > 4)
+    return GOSLAM_EINVAL;
+  if ((h >> (num_levels - 1)) <= 0 || (w >> (num_levels - 1)) <= 0) return GOSLAM_EINVAL;
+  if (N == 0) return GOSLAM_OK;
+  const __half* f = reinterpret_cast<const __half*>(fmaps_kmajor);
+  return launch_tc(f, F, f, F, ii, jj, rig, reinterpret_cast<__half* const*>(levels), num_levels, N, h,
+                   w, (cudaStream_t)stream);
 }
 
 int goslam_corr_build(const void* fmap1, const void* fmap2, void* const* levels, int num_levels,

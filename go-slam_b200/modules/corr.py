@@ -56,6 +56,25 @@ class CorrBlock:
             _lib.check(rc, "corr_build_f32")
         self.corr_pyramid = levels
 
+    @classmethod
+    def from_video(cls, fmaps_kmajor, ii, jj, ht, wd, rig=1, num_levels=4, radius=3):
+        """FactorGraph.add_factors' volume for edges (ii, jj) straight from video-level K-major
+        feature maps [buffer*rig, ht*wd, 128] (see `fmaps_to_kmajor`): no gathered copies."""
+        self = cls.__new__(cls)
+        self.num_levels, self.radius, self.ht, self.wd = num_levels, radius, ht, wd
+        dev = fmaps_kmajor.device
+        N = int(ii.shape[0])
+        F = int(fmaps_kmajor.shape[0])
+        levels = [torch.empty((N, ht, wd, ht >> i, wd >> i), dtype=torch.float16, device=dev)
+                  for i in range(num_levels)]
+        with torch.cuda.device(dev):
+            rc = _lib.load().goslam_corr_build_indexed(
+                _lib.ptr(fmaps_kmajor), F, int(rig), _lib.ptr(ii), _lib.ptr(jj), _ptr_array(levels),
+                num_levels, N, 128, ht, wd, _lib.stream_ptr())
+        _lib.check(rc, "corr_build_indexed")
+        self.corr_pyramid = levels
+        return self
+
     def __call__(self, coords):
         batch, num, ht, wd, _ = coords.shape
         N = batch * num
@@ -89,6 +108,22 @@ class CorrBlock:
         blk = CorrBlock(fmap1, fmap2, num_levels=1)
         batch, num, _, ht, wd = fmap1.shape
         return blk.corr_pyramid[0].view(batch, num, ht, wd, ht, wd)
+
+
+def fmaps_to_kmajor(fmaps, out=None):
+    """DepthVideo.fmaps [buffer, rig, 128, h, w] f16 -> K-major [buffer*rig, h*w, 128] (done once
+    per inserted keyframe; `out` lets the caller convert just the new rows in place)."""
+    if not fmaps.is_cuda or fmaps.dtype != torch.float16:
+        raise RuntimeError("fmaps_to_kmajor: CUDA float16 tensor required")
+    f = fmaps.contiguous()
+    h, w = f.shape[-2], f.shape[-1]
+    F = f.numel() // (128 * h * w)
+    if out is None:
+        out = torch.empty((F, h * w, 128), dtype=torch.float16, device=f.device)
+    with torch.cuda.device(f.device):
+        rc = _lib.load().goslam_fmaps_to_kmajor(_lib.ptr(f), _lib.ptr(out), F, 128, h, w, _lib.stream_ptr())
+    _lib.check(rc, "fmaps_to_kmajor")
+    return out
 
 
 class AltCorrBlock:

