@@ -215,7 +215,11 @@ ba_linearize_kernel(const float* __restrict__ poses, const float* __restrict__ d
     gs_act4(G, Xi, Xj);
     const float x = Xj[0], y = Xj[1], h = Xj[3];
     const bool behind = Xj[2] < GS_MIN_DEPTH;
-    const float dd = behind ? 0.0f : (float)(1.0 / (double)Xj[2]);
+    // reference: d = 1.0 / Xj[2] in double, then narrowed to float.  RN_f32(RN_f64(1/Z)) equals the
+    // correctly rounded float reciprocal unless the double quotient lands within 2^-53 of a float
+    // rounding midpoint (impossible exactly, since 1/Z has no finite midpoint expansion) — so the
+    // single-instruction float reciprocal is used instead of an fp64 divide.
+    const float dd = behind ? 0.0f : __frcp_rn(Xj[2]);
     const float d2 = dd * dd;
     float tu = 0.f, tv = 0.f, qu = 0.f, qv = 0.f;
     if (act) {
@@ -312,7 +316,9 @@ ba_system_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ii
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = ws.counts[0];
   const int npairs = motion_only ? 0 : ws.counts[2];
-  const int nitems = d.N + npairs;
+  constexpr int kChunk = 1024;                       // pixels per Schur work unit
+  const int nchunk = (d.hw + kChunk - 1) / kChunk;
+  const int nitems = d.N + npairs * nchunk;
   double* H = ws.sys;
   double* bvec = ws.sys + (size_t)d.n * d.n;
 
@@ -382,7 +388,9 @@ ba_system_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ii
       __syncthreads();
     } else {
       // ---------------- one Schur pair ----------------
-      const int p = item - d.N;
+      const int p = (item - d.N) / nchunk;
+      const int px0 = ((item - d.N) % nchunk) * kChunk;
+      const int px1 = min(d.hw, px0 + kChunk);
       // slot k with pair_ptr[k] <= p < pair_ptr[k+1]
       int lo = 0, hi = M;
       while (hi - lo > 1) {
@@ -407,7 +415,7 @@ ba_system_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ii
       float acc[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-      for (int px = tid; px < d.hw; px += 256) {
+      for (int px = px0 + tid; px < px1; px += 256) {
         const float qv = Qk[px];
         float ea[6], eb[6];
 #pragma unroll
@@ -452,6 +460,87 @@ ba_system_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ii
 // Damp + Cholesky (float64) + solve + pose retraction.  One block.
 // A lives in shared memory when it fits, else in the global scratch.
 // ------------------------------------------------------------------------------------
+// finish: write dx / status and retract the poses  (:898-931)
+__device__ __forceinline__ void solve_finish(float* poses, const BaDims& d, const BaWs& ws,
+                                             const double* x, int fail, float* dx_out,
+                                             int* status_out, int tid, int nt) {
+  for (int i = tid; i < d.n; i += nt) {
+    const float val = fail ? 0.0f : (float)x[i];
+    ws.dx[i] = val;
+    if (dx_out) dx_out[i] = val;
+  }
+  if (tid == 0 && status_out) *status_out = fail;
+}
+
+__device__ __forceinline__ void retract_poses(float* poses, const BaDims& d, const BaWs& ws, int tid,
+                                              int nt) {
+  for (int k = tid; k < d.P; k += nt) {
+    float* p = poses + 7 * (size_t)(d.t0 + k);
+    float t1[3], q1[4];
+    gs_retr(ws.dx + 6 * k, p, p + 3, t1, q1);
+    p[0] = t1[0]; p[1] = t1[1]; p[2] = t1[2];
+    p[3] = q1[0]; p[4] = q1[1]; p[5] = q1[2]; p[6] = q1[3];
+  }
+}
+
+// Small systems (6P <= kWarpSolveMaxN): ONE warp, matrix in shared memory, no block barriers,
+// one rsqrt per column and no divisions (the diagonal stores 1/l_jj).  A local window of 8
+// keyframes is a 42x42 system: latency, not throughput, is what matters.
+__global__ void __launch_bounds__(32)
+ba_solve_warp_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __restrict__ sys_in,
+                     float lm, float ep, float* __restrict__ dx_out, int* __restrict__ status_out) {
+  extern __shared__ double smd[];
+  const int n = d.n, lane = threadIdx.x;
+  double* A = smd;
+  double* y = smd + (size_t)n * n;
+  for (int idx = lane; idx < n * n; idx += 32) {
+    const int r = idx / n, c = idx - r * n;
+    double val = sys_in[idx];
+    if (r == c) val += (double)ep + (double)lm * val;
+    A[idx] = val;
+  }
+  for (int i = lane; i < n; i += 32) y[i] = sys_in[(size_t)n * n + i];
+  __syncwarp();
+  int fail = 0;
+  for (int j = 0; j < n; ++j) {
+    const double ajj = A[j * n + j];
+    if (!(ajj > 0.0)) { fail = 1; break; }             // warp-uniform
+    const double inv = rsqrt(ajj);
+    __syncwarp();
+    for (int i = j + 1 + lane; i < n; i += 32) A[i * n + j] *= inv;
+    if (lane == 0) A[j * n + j] = inv;
+    __syncwarp();
+    for (int i = j + 1 + lane; i < n; i += 32) {
+      const double lij = A[i * n + j];
+      for (int c = j + 1; c <= i; ++c) A[i * n + c] -= lij * A[c * n + j];
+    }
+    __syncwarp();
+  }
+  if (!fail) {
+    for (int j = 0; j < n; ++j) {                       // L z = b
+      const double zj = y[j] * A[j * n + j];
+      __syncwarp();
+      if (lane == 0) y[j] = zj;
+      for (int i = j + 1 + lane; i < n; i += 32) y[i] -= A[i * n + j] * zj;
+      __syncwarp();
+    }
+    for (int j = n - 1; j >= 0; --j) {                  // L^T x = z
+      const double xj = y[j] * A[j * n + j];
+      __syncwarp();
+      if (lane == 0) y[j] = xj;
+      for (int i = lane; i < j; i += 32) y[i] -= A[j * n + i] * xj;
+      __syncwarp();
+    }
+    int bad = 0;
+    for (int i = lane; i < n; i += 32) bad |= !isfinite(y[i]);
+    fail = __any_sync(0xffffffffu, bad) ? 1 : 0;
+  }
+  solve_finish(poses, d, ws, y, fail, dx_out, status_out, lane, 32);
+  __syncwarp();
+  retract_poses(poses, d, ws, lane, 32);
+}
+
+// General case: one block; A in shared memory when it fits, else in the global scratch.
 __global__ void __launch_bounds__(1024)
 ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __restrict__ sys_in,
                 float lm, float ep, int use_smem, float* __restrict__ dx_out,
@@ -471,17 +560,16 @@ ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __re
   for (int i = tid; i < n; i += nt) b[i] = sys_in[(size_t)n * n + i];
   __syncthreads();
 
-  // right-looking Cholesky on the lower triangle
+  // right-looking Cholesky on the lower triangle; the diagonal keeps 1/l_jj
   for (int j = 0; j < n; ++j) {
     const double ajj = A[(size_t)j * n + j];
     if (!(ajj > 0.0)) { if (tid == 0) fail = 1; }
     __syncthreads();
     if (fail) break;
-    const double ljj = sqrt(ajj);
-    for (int i = j + 1 + tid; i < n; i += nt) A[(size_t)i * n + j] /= ljj;
-    if (tid == 0) A[(size_t)j * n + j] = ljj;
+    const double inv = rsqrt(ajj);
+    for (int i = j + 1 + tid; i < n; i += nt) A[(size_t)i * n + j] *= inv;
+    if (tid == 0) A[(size_t)j * n + j] = inv;
     __syncthreads();
-    // trailing update: A[i][c] -= L[i][j] * L[c][j], j < c <= i < n
     const int m = n - j - 1;
     const int tot = m * m;                       // n <= 6*4096 => fits in int
     for (int idx = tid; idx < tot; idx += nt) {
@@ -493,43 +581,28 @@ ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __re
   }
 
   if (!fail) {
-    // forward substitution L y = b (column sweep), then L^T x = y
     for (int j = 0; j < n; ++j) {
-      if (tid == 0) b[j] /= A[(size_t)j * n + j];
+      const double zj = b[j] * A[(size_t)j * n + j];
       __syncthreads();
-      const double yj = b[j];
-      for (int i = j + 1 + tid; i < n; i += nt) b[i] -= A[(size_t)i * n + j] * yj;
+      if (tid == 0) b[j] = zj;
+      for (int i = j + 1 + tid; i < n; i += nt) b[i] -= A[(size_t)i * n + j] * zj;
       __syncthreads();
     }
     for (int j = n - 1; j >= 0; --j) {
-      if (tid == 0) b[j] /= A[(size_t)j * n + j];
+      const double xj = b[j] * A[(size_t)j * n + j];
       __syncthreads();
-      const double xj = b[j];
+      if (tid == 0) b[j] = xj;
       for (int i = tid; i < j; i += nt) b[i] -= A[(size_t)j * n + i] * xj;
       __syncthreads();
     }
-    // all entries must be finite, else treat as a failed solve
     int bad = 0;
     for (int i = tid; i < n; i += nt) bad |= !isfinite(b[i]);
     if (bad) fail = 1;
     __syncthreads();
   }
-
-  for (int i = tid; i < n; i += nt) {
-    const float val = fail ? 0.0f : (float)b[i];
-    ws.dx[i] = val;
-    if (dx_out) dx_out[i] = val;
-  }
-  if (tid == 0 && status_out) *status_out = fail;
+  solve_finish(poses, d, ws, b, fail, dx_out, status_out, tid, nt);
   __syncthreads();
-  // retraction  poses[k] <- exp(dx[k-t0]) * poses[k]   (:898-931)
-  for (int k = tid; k < d.P; k += nt) {
-    float* p = poses + 7 * (size_t)(d.t0 + k);
-    float t1[3], q1[4];
-    gs_retr(ws.dx + 6 * k, p, p + 3, t1, q1);
-    p[0] = t1[0]; p[1] = t1[1]; p[2] = t1[2];
-    p[3] = q1[0]; p[4] = q1[1]; p[5] = q1[2]; p[6] = q1[3];
-  }
+  retract_poses(poses, d, ws, tid, nt);
 }
 
 // ------------------------------------------------------------------------------------
@@ -580,6 +653,7 @@ bool make_dims(int N, int num, int ht, int wd, int t0, int t1, BaDims* d) {
 }
 
 constexpr int kSmemSolveMaxN = 160;   // (160*160 + 160) * 8 B = 206 KB of the 227 KB
+constexpr int kWarpSolveMaxN = 96;    // single-warp solve up to 16 poses
 
 int launch_phase1(const float* poses, const float* disps, const float* intr,
                   const float* disps_sens, const float* targets, const float* weights,
@@ -610,18 +684,24 @@ int launch_phase2(float* poses, float* disps, const double* sys_in,
                   const BaDims& d, const BaWs& ws, float lm, float ep, int motion_only,
                   int owner_lo, int owner_hi, float* dx_out, float* dz_out, int* status_out,
                   cudaStream_t st) {
-  const int use_smem = d.n <= kSmemSolveMaxN;
-  const size_t smem = use_smem ? ((size_t)d.n * d.n + d.n) * sizeof(double) : 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(((size_t)kSmemSolveMaxN * kSmemSolveMaxN + kSmemSolveMaxN) * 8));
+    cudaFuncSetAttribute(ba_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(((size_t)kWarpSolveMaxN * kWarpSolveMaxN + kWarpSolveMaxN) * 8));
     attr_set = true;
   }
-  // barrier cost dominates small systems: use only as many warps as the trailing update can feed
-  const int threads = d.n <= 48 ? 64 : d.n <= 96 ? 128 : d.n <= kSmemSolveMaxN ? 256 : 1024;
-  ba_solve_kernel<<<1, threads, smem, st>>>(poses, d, ws, sys_in, lm, ep, use_smem, dx_out,
-                                            status_out);
+  if (d.n <= kWarpSolveMaxN) {
+    const size_t smem = ((size_t)d.n * d.n + d.n) * sizeof(double);
+    ba_solve_warp_kernel<<<1, 32, smem, st>>>(poses, d, ws, sys_in, lm, ep, dx_out, status_out);
+  } else {
+    const int use_smem = d.n <= kSmemSolveMaxN;
+    const size_t smem = use_smem ? ((size_t)d.n * d.n + d.n) * sizeof(double) : 0;
+    const int threads = d.n <= kSmemSolveMaxN ? 256 : 1024;
+    ba_solve_kernel<<<1, threads, smem, st>>>(poses, d, ws, sys_in, lm, ep, use_smem, dx_out,
+                                              status_out);
+  }
   GS_CHECK_LAUNCH();
   if (!motion_only) {
     dim3 grid(ws.ntiles, d.num);
