@@ -22,13 +22,14 @@
 // weights resident in shared memory, phase 3 composites each ray with a warp scan.
 #include "common.cuh"
 #include <math.h>
+#include <algorithm>
 
 namespace {
 
 constexpr int kLevels = 16;
-constexpr int kThreadsN = 256;
+constexpr int kThreadsN = 384;
 constexpr int kWarpsN = kThreadsN / 32;
-constexpr int kRaysPerGroup = 8;
+constexpr int kDenseLevels = 5;     // levels whose res^3 fits the table (16,24,34,49,71)
 constexpr int kIn = 80, kInPad = 88;     // MLP input width / padded smem row (halves)
 constexpr int kHid = 64, kHidPad = 72;
 constexpr int kOutW = 16;
@@ -59,7 +60,6 @@ GridMeta make_grid_meta(int64_t* total_entries) {
   return g;
 }
 
-__constant__ GridMeta c_grid;
 
 struct NeusArgs {
   goslam_neus_params p;
@@ -70,19 +70,8 @@ struct NeusArgs {
   unsigned* blk_count;    // [grid] in-bound sample counts
   int* flag;              // [1] written by the finalize kernel: 1 = nothing in bound
   int mode;               // 0 main pass, 1 fix-up pass (mask[:100] = True)
+  int rays_per_group;     // rays one warp composites together (rays_per_group * S <= kMaxGroup)
 };
-
-__device__ __forceinline__ unsigned grid_index(int l, unsigned x, unsigned y, unsigned z) {
-  const unsigned res = (unsigned)c_grid.res[l];
-  const unsigned size = c_grid.size[l];
-  unsigned stride = 1, index = 0;
-  // mirrors tcnn grid_index: dense strides while they fit the table, else the hash
-  index += x * stride; stride *= res;
-  if (stride <= size) { index += y * stride; stride *= res; }
-  if (stride <= size) { index += z * stride; stride *= res; }
-  if (size < stride) index = (x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u);
-  return index % size;
-}
 
 __device__ __forceinline__ void ldmatrix_x4(unsigned (&r)[4], const void* p) {
   const unsigned a = (unsigned)__cvta_generic_to_shared(p);
@@ -148,24 +137,112 @@ __device__ __forceinline__ void store_relu_half(const float (&acc)[2][NT][4], __
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Shared memory: network weights once per (persistent) block + a private slab per warp.
+// ---------------------------------------------------------------------------------------
+constexpr int kEncPad = 40;            // enc row stride (halves): 80 B, conflict-free ldmatrix
+constexpr int kMaxGroup = 320;         // samples per warp work item (rays_per_group * S, padded)
+
+struct WarpSlab {
+  alignas(16) __half actA[32 * kInPad];    // MLP input rows / hidden 2; also the fp32 SDF-head tile
+  alignas(16) __half actB[32 * kHidPad];   // enc rows (stride kEncPad) then hidden 1, rgb scratch
+  float w[kMaxGroup];                      // compositing weights of the open group
+  float z[kMaxGroup];                      // mid-point depths
+};
+
 struct Smem {
   alignas(16) __half W1[kHid * kInPad];
   alignas(16) __half W2[kHid * kHidPad];
   alignas(16) __half W3[kOutW * kHidPad];
-  alignas(16) float sdfWT[35 * 32];          // transposed Linear weight: [k][out]
+  alignas(16) __half sdfWhi[32 * kEncPad];   // Linear(35,32) weight, enc part, fp16 hi/lo split:
+  alignas(16) __half sdfWlo[32 * kEncPad];   //   W = hi + lo to 2^-22 relative, products exact
+  float sdfWxyz[3 * 32];                     // xyz part [k][out], fp32
   float sdfB[32];
+  float gy[32];                              // dL/dy of the normal: W[0,3:] rounded to half
   float colB[3 * 33];
-  alignas(16) __half actA[kWarpsN][32 * kInPad];
-  alignas(16) __half actB[kWarpsN][32 * kHidPad];
-  // per-sample results of the current ray group
-  float alpha[kRaysPerGroup * 128];
-  float zmid[kRaysPerGroup * 128];
-  float grad[3][kRaysPerGroup * 128];
-  float rgb[3][kRaysPerGroup * 128];
-  float maskf[kRaysPerGroup * 128];
+  WarpSlab slab[kWarpsN];
   float red_g[kWarpsN];
   unsigned red_c[kWarpsN];
 };
+
+static_assert(32 * 33 * 4 <= 32 * kInPad * 2, "fp32 SDF-head tile must fit in actA");
+
+struct LevelConst {
+  float scale;
+  unsigned res, res2, offset;
+};
+__constant__ LevelConst c_lvl[kLevels];
+
+// sin(x) for |x| up to a few hundred: 2-term Cody-Waite reduction by 2*pi, then the SFU.
+__device__ __forceinline__ float fast_sin(float x) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.28125f, x);
+  r = fmaf(-k, 1.9353071795864769e-3f, r);
+  return __sinf(r);
+}
+
+template <bool HASHED>
+__device__ __forceinline__ void encode_level(int l, const __half2* __restrict__ table,
+                                             const float (&x01)[3], const float* gyv,
+                                             __half2& enc, float (&genc)[3]) {
+  const LevelConst L = c_lvl[l];
+  float fr[3];
+  unsigned pg[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float pos = fmaf(L.scale, x01[c], 0.5f);
+    const float fl = floorf(pos);
+    pg[c] = (unsigned)(int)fl;
+    fr[c] = pos - fl;
+  }
+  unsigned idx[8];
+  if (HASHED) {
+    const unsigned hx0 = pg[0], hx1 = pg[0] + 1u;
+    const unsigned hy0 = pg[1] * 2654435761u, hy1 = hy0 + 2654435761u;
+    const unsigned hz0 = pg[2] * 805459861u, hz1 = hz0 + 805459861u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      idx[q] = (((q & 1) ? hx1 : hx0) ^ ((q & 2) ? hy1 : hy0) ^ ((q & 4) ? hz1 : hz0)) & 0x7FFFFu;
+  } else {
+    // dense level: index < res^3 <= table size by construction, no modulo needed
+    const unsigned base = pg[0] + pg[1] * L.res + pg[2] * L.res2;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      idx[q] = base + ((q & 1) ? 1u : 0u) + ((q & 2) ? L.res : 0u) + ((q & 4) ? L.res2 : 0u);
+  }
+  const __half2* lvl = table + L.offset;
+  __half2 v[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = __ldg(lvl + idx[q]);
+
+  const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
+  __half2 r = __float2half2_rn(0.f);
+  float2 vf[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    vf[q] = __half22float2(v[q]);
+    const float w = (wx[q & 1] * wy[(q >> 1) & 1]) * wz[(q >> 2) & 1];
+    r = __hadd2_rn(r, __floats2half2_rn(w * vf[q].x, w * vf[q].y));      // half accumulation (tcnn)
+  }
+  enc = r;
+  const float gy0 = gyv[2 * l], gy1 = gyv[2 * l + 1];
+#pragma unroll
+  for (int gd = 0; gd < 3; ++gd) {
+    const int d1 = (gd + 1) % 3, d2 = (gd + 2) % 3;
+    float gsum = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int b1 = q & 1, b2 = (q >> 1) & 1;
+      const float w1 = (d1 == 0 ? wx[b1] : d1 == 1 ? wy[b1] : wz[b1]);
+      const float w2 = (d2 == 0 ? wx[b2] : d2 == 1 ? wy[b2] : wz[b2]);
+      const float w = L.scale * w1 * w2;
+      const int il = (b1 << d1) | (b2 << d2);
+      const int ir = il | (1 << gd);
+      gsum += w * ((vf[ir].x - vf[il].x) * gy0 + (vf[ir].y - vf[il].y) * gy1);
+    }
+    genc[gd] += gsum;
+  }
+}
 
 __global__ void __launch_bounds__(kThreadsN, 1)
 neus_forward_kernel(const NeusArgs a) {
@@ -173,13 +250,15 @@ neus_forward_kernel(const NeusArgs a) {
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.S;
+  const int G = a.rays_per_group;                 // rays per warp work item
+  const int gs = G * S;                           // real samples per item (<= kMaxGroup)
+  const int ntiles = gs_cdiv_dev(gs, 32);
 
-  int num_groups = gs_cdiv_dev(a.R, kRaysPerGroup);
+  int num_groups = gs_cdiv_dev(a.R, G);
   if (a.mode == 1) {
-    if (*a.flag == 0) return;                    // something was in bound: no fix-up needed
-    num_groups = gs_cdiv_dev(gs_cdiv_dev(100, S), kRaysPerGroup);
-    const int rg = gs_cdiv_dev(a.R, kRaysPerGroup);
-    if (num_groups > rg) num_groups = rg;
+    if (*a.flag == 0) return;                     // something was in bound: no fix-up needed
+    const int need = gs_cdiv_dev(gs_cdiv_dev(100, S), G);
+    if (num_groups > need) num_groups = need;
   }
 
   // ---- stage the network weights once per block (persistent) ----
@@ -190,33 +269,56 @@ neus_forward_kernel(const NeusArgs a) {
       sm.W2[(i / kHid) * kHidPad + i % kHid] = w[kHid * kIn + i];
     for (int i = tid; i < kOutW * kHid; i += kThreadsN)
       sm.W3[(i / kHid) * kHidPad + i % kHid] = w[kHid * kIn + kHid * kHid + i];
-    for (int i = tid; i < 32 * 35; i += kThreadsN) sm.sdfWT[(i % 35) * 32 + i / 35] = a.p.sdf_w[i];
+    for (int i = tid; i < 32 * 35; i += kThreadsN) {
+      const int o = i / 35, k = i % 35;
+      const float wv = a.p.sdf_w[i];
+      if (k < 3) {
+        sm.sdfWxyz[k * 32 + o] = wv;
+      } else {
+        const __half hi = __float2half_rn(wv);
+        sm.sdfWhi[o * kEncPad + (k - 3)] = hi;
+        sm.sdfWlo[o * kEncPad + (k - 3)] = __float2half_rn(wv - __half2float(hi));
+        if (o == 0) sm.gy[k - 3] = __half2float(hi);
+      }
+    }
+    for (int i = tid; i < 32 * (kEncPad - 32); i += kThreadsN) {   // zero the row padding
+      const int o = i / (kEncPad - 32), k = 32 + i % (kEncPad - 32);
+      sm.sdfWhi[o * kEncPad + k] = __float2half_rn(0.f);
+      sm.sdfWlo[o * kEncPad + k] = __float2half_rn(0.f);
+    }
     for (int i = tid; i < 32; i += kThreadsN) sm.sdfB[i] = a.p.sdf_b[i];
     for (int i = tid; i < 99; i += kThreadsN) sm.colB[i] = a.p.color_B[i];
   }
   __syncthreads();
 
+  WarpSlab& sl = sm.slab[warp];
   const __half2* table = reinterpret_cast<const __half2*>(a.p.grid);
   float gerr_local = 0.f;
   unsigned count_local = 0;
+  const int warps_total = gridDim.x * kWarpsN;
 
-  for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
-    const int ray0 = group * kRaysPerGroup;
-    const int nrays = min(kRaysPerGroup, a.R - ray0);
+  for (int group = blockIdx.x * kWarpsN + warp; group < num_groups; group += warps_total) {
+    const int ray0 = group * G;
+    const int nrays = min(G, a.R - ray0);
     const int nsamp = nrays * S;
-    const int ntiles = gs_cdiv_dev(nsamp, 32);
 
-    for (int tile = warp; tile < ntiles; tile += kWarpsN) {
-      const int ls = tile * 32 + lane;           // local sample index in the group
+    // compositing state of the ray that is still open (lane-replicated)
+    int open_ray = -1;
+    float carry_T = 1.f;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // ws, dep, r, g, b, nx, ny, nz
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+      if (tile * 32 >= nsamp) break;               // warp-uniform
+      const int ls = tile * 32 + lane;             // local sample index in the group
       const bool valid = ls < nsamp;
-      const int lr = valid ? ls / S : 0;
-      const int sidx = valid ? ls % S : 0;
-      const int ray = ray0 + lr;
+      const int lr = valid ? ls / S : -2;          // local ray
+      const int sidx = valid ? ls - lr * S : 0;
+      const int ray = ray0 + (valid ? lr : 0);
       const size_t gidx = (size_t)ray * S + sidx;
-      __half* rowA = sm.actA[warp] + lane * kInPad;
 
       float zm = 0.f, dist = 0.f, alpha = 0.f, sdf = 100.f;
       float g3[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f}, pt[3] = {0.f, 0.f, 0.f};
+      float xn[3] = {0.f, 0.f, 0.f}, dscale[3] = {0.f, 0.f, 0.f};
       bool inb = false;
       if (valid) {
         dist = a.dists[gidx];
@@ -234,13 +336,11 @@ neus_forward_kernel(const NeusArgs a) {
         if (a.mode == 1 && gidx < 100) inb = true;
       }
 
-      float feat[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) feat[i] = 0.f;
-
+      // ---- phase 1a: hash-grid encoding (thread per sample) -> enc row in actB ----
+      float genc[3] = {0.f, 0.f, 0.f};
+      __half2* encrow = reinterpret_cast<__half2*>(sl.actB + lane * kEncPad);
       if (inb) {
-        // normalised coordinate, clamp, unit cube
-        float xn[3], x01[3], dscale[3];
+        float x01[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float b0 = a.p.bound[2 * c], b1 = a.p.bound[2 * c + 1];
@@ -249,74 +349,81 @@ neus_forward_kernel(const NeusArgs a) {
           dscale[c] = (raw >= -1.0f && raw <= 1.0f) ? 2.0f / (b1 - b0) : 0.0f;
           x01[c] = __fdiv_rn(__fadd_rn(xn[c], 1.0f), 2.0f);
         }
-        // SDF head accumulators start from bias + xyz part
-        float out[32];
-#pragma unroll
-        for (int o = 0; o < 32; ++o)
-          out[o] = sm.sdfB[o] + sm.sdfWT[0 * 32 + o] * xn[0] + sm.sdfWT[1 * 32 + o] * xn[1] +
-                   sm.sdfWT[2 * 32 + o] * xn[2];
-        float genc[3] = {0.f, 0.f, 0.f};
-#pragma unroll 2
-        for (int l = 0; l < kLevels; ++l) {
-          const float scale = c_grid.scale[l];
-          float fr[3]; unsigned pg[3];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float pos = fmaf(scale, x01[c], 0.5f);
-            const float fl = floorf(pos);
-            pg[c] = (unsigned)(int)fl;
-            fr[c] = pos - fl;
-          }
-          const __half2* lvl = table + c_grid.offset[l];
-          __half2 v[8];
-#pragma unroll
-          for (int idx = 0; idx < 8; ++idx) {
-            const unsigned cx = pg[0] + (idx & 1), cy = pg[1] + ((idx >> 1) & 1),
-                           cz = pg[2] + ((idx >> 2) & 1);
-            v[idx] = __ldg(lvl + grid_index(l, cx, cy, cz));
-          }
-          __half r0 = __float2half_rn(0.f), r1 = r0;
-#pragma unroll
-          for (int idx = 0; idx < 8; ++idx) {
-            float w = 1.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) w *= ((idx >> c) & 1) ? fr[c] : 1.f - fr[c];
-            r0 = __hadd_rn(r0, __float2half_rn(w * __low2float(v[idx])));
-            r1 = __hadd_rn(r1, __float2half_rn(w * __high2float(v[idx])));
-          }
-          const float e0 = __half2float(r0), e1 = __half2float(r1);
-          // dL/dy for the normal: sdf row of the Linear weight, rounded to half (tcnn bwd)
-          const float gy0 = __half2float(__float2half_rn(sm.sdfWT[(3 + 2 * l) * 32]));
-          const float gy1 = __half2float(__float2half_rn(sm.sdfWT[(4 + 2 * l) * 32]));
-#pragma unroll
-          for (int gd = 0; gd < 3; ++gd) {
-            const int d1 = (gd + 1) % 3, d2 = (gd + 2) % 3;
-            float gsum = 0.f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int b1 = q & 1, b2 = (q >> 1) & 1;
-              const float w = scale * (b1 ? fr[d1] : 1.f - fr[d1]) * (b2 ? fr[d2] : 1.f - fr[d2]);
-              const int il = (b1 << d1) | (b2 << d2);
-              const int ir = il | (1 << gd);
-              gsum += w * ((__low2float(v[ir]) - __low2float(v[il])) * gy0 +
-                           (__high2float(v[ir]) - __high2float(v[il])) * gy1);
-            }
-            genc[gd] += gsum;
-          }
-#pragma unroll
-          for (int o = 0; o < 32; ++o)
-            out[o] += sm.sdfWT[(3 + 2 * l) * 32 + o] * e0 + sm.sdfWT[(4 + 2 * l) * 32 + o] * e1;
+#pragma unroll 1
+        for (int l = 0; l < kDenseLevels; ++l) {
+          __half2 e;
+          encode_level<false>(l, table, x01, sm.gy, e, genc);
+          encrow[l] = e;
         }
+#pragma unroll 2
+        for (int l = kDenseLevels; l < kLevels; ++l) {
+          __half2 e;
+          encode_level<true>(l, table, x01, sm.gy, e, genc);
+          encrow[l] = e;
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < kLevels; ++l) encrow[l] = __float2half2_rn(0.f);
+      }
+      __syncwarp();
+
+      // ---- phase 1b: SDF head  out[32 x 32] = enc (W_hi + W_lo)^T  on tensor cores ----
+      float* outf = reinterpret_cast<float*>(sl.actA);     // [32][33] fp32 tile
+      {
+        float acc4[2][4][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc4[mt][nt][q] = 0.f;
+        const int lrr = lane & 15, lcc = (lane >> 4) * 8;
+        const int br = lane & 7, bc = ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          unsigned af[2][4];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+            ldmatrix_x4(af[mt], sl.actB + (mt * 16 + lrr) * kEncPad + kt * 16 + lcc);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            unsigned bh[2], bl[2];
+            ldmatrix_x2(bh, sm.sdfWhi + (nt * 8 + br) * kEncPad + kt * 16 + bc);
+            ldmatrix_x2(bl, sm.sdfWlo + (nt * 8 + br) * kEncPad + kt * 16 + bc);
+            mma16816(acc4[0][nt], af[0], bl);
+            mma16816(acc4[1][nt], af[1], bl);
+            mma16816(acc4[0][nt], af[0], bh);
+            mma16816(acc4[1][nt], af[1], bh);
+          }
+        }
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const int col = nt * 8 + 2 * t;
+            outf[(mt * 16 + g) * 33 + col] = acc4[mt][nt][0];
+            outf[(mt * 16 + g) * 33 + col + 1] = acc4[mt][nt][1];
+            outf[(mt * 16 + g + 8) * 33 + col] = acc4[mt][nt][2];
+            outf[(mt * 16 + g + 8) * 33 + col + 1] = acc4[mt][nt][3];
+          }
+      }
+      __syncwarp();
+      float out[32];
+#pragma unroll
+      for (int o = 0; o < 32; ++o)
+        out[o] = outf[lane * 33 + o] + (sm.sdfB[o] + sm.sdfWxyz[o] * xn[0] + sm.sdfWxyz[32 + o] * xn[1] +
+                                        sm.sdfWxyz[64 + o] * xn[2]);
+      __syncwarp();                                  // everyone has read outf before actA is reused
+
+      if (inb) {
         sdf = out[0];
 #pragma unroll
-        for (int i = 0; i < 31; ++i) feat[i] = out[1 + i];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          g3[c] = (sm.sdfWT[c * 32] + 0.5f * genc[c]) * dscale[c];
+        for (int c = 0; c < 3; ++c) g3[c] = (sm.sdfWxyz[c * 32] + 0.5f * genc[c]) * dscale[c];
       }
 
+      // ---- NeuS alpha (get_alpha, src/InstantNeuS.py:276-293) ----
       if (valid) {
-        // NeuS alpha (get_alpha, src/InstantNeuS.py:276-293)
         const float true_cos = dir[0] * g3[0] + dir[1] * g3[1] + dir[2] * g3[2];
         const float car = a.p.cos_anneal_ratio;
         const float iter_cos = -(fmaxf(-true_cos * 0.5f + 0.5f, 0.f) * (1.0f - car) +
@@ -334,23 +441,20 @@ neus_forward_kernel(const NeusArgs a) {
           gerr_local += gn * gn;
           ++count_local;
         }
-        sm.alpha[ls] = alpha;
-        sm.zmid[ls] = zm;
-        sm.grad[0][ls] = g3[0]; sm.grad[1][ls] = g3[1]; sm.grad[2][ls] = g3[2];
-        sm.maskf[ls] = inb ? 1.f : 0.f;
       }
 
       // ---- MLP input row: [sin(p B)(33) | normal(3) | feat(31) | 1-padding(13)] ----
       {
+        __half* rowA = sl.actA + lane * kInPad;
 #pragma unroll
         for (int j = 0; j < 33; ++j) {
           const float arg = pt[0] * sm.colB[j] + pt[1] * sm.colB[33 + j] + pt[2] * sm.colB[66 + j];
-          rowA[j] = __float2half_rn(sinf(arg));
+          rowA[j] = __float2half_rn(fast_sin(arg));
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) rowA[33 + c] = __float2half_rn(g3[c]);
 #pragma unroll
-        for (int i = 0; i < 31; ++i) rowA[36 + i] = __float2half_rn(feat[i]);
+        for (int i = 0; i < 31; ++i) rowA[36 + i] = __float2half_rn(inb ? out[1 + i] : 0.f);
 #pragma unroll
         for (int i = 67; i < kIn; ++i) rowA[i] = __float2half_rn(1.0f);
       }
@@ -359,20 +463,18 @@ neus_forward_kernel(const NeusArgs a) {
       // ---- warp-wide MLP on tensor cores ----
       float rgbv[3] = {0.f, 0.f, 0.f};
       {
-        float acc[2][8][4];
-        warp_layer<8, kIn / 16, kInPad, kInPad>(sm.actA[warp], sm.W1, acc, lane);
-        store_relu_half<8, kHidPad>(acc, sm.actB[warp], lane);
+        float accm[2][8][4];
+        warp_layer<8, kIn / 16, kInPad, kInPad>(sl.actA, sm.W1, accm, lane);
+        store_relu_half<8, kHidPad>(accm, sl.actB, lane);
         __syncwarp();
-        warp_layer<8, kHid / 16, kHidPad, kHidPad>(sm.actB[warp], sm.W2, acc, lane);
+        warp_layer<8, kHid / 16, kHidPad, kHidPad>(sl.actB, sm.W2, accm, lane);
         __syncwarp();
-        // hidden 2 goes back into actA (row stride kInPad; only the first 64 columns used)
-        store_relu_half<8, kInPad>(acc, sm.actA[warp], lane);
+        store_relu_half<8, kInPad>(accm, sl.actA, lane);
         __syncwarp();
         float acc3[2][2][4];
-        warp_layer<2, kHid / 16, kInPad, kHidPad>(sm.actA[warp], sm.W3, acc3, lane);
+        warp_layer<2, kHid / 16, kInPad, kHidPad>(sl.actA, sm.W3, acc3, lane);
         __syncwarp();
-        // scatter the 32x16 result so each lane can pick up its own sample's rgb
-        float* scratch = reinterpret_cast<float*>(sm.actB[warp]);   // 32 x 4 floats
+        float* scratch = reinterpret_cast<float*>(sl.actB);   // 32 x 4 floats
         const int g = lane >> 2, t = lane & 3;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
@@ -386,70 +488,77 @@ neus_forward_kernel(const NeusArgs a) {
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float x = __half2float(__float2half_rn(scratch[lane * 4 + c]));  // tcnn output is half
+          const float x = __half2float(__float2half_rn(scratch[lane * 4 + c]));   // tcnn output is half
           const float sg = 1.0f / (1.0f + expf(-x));
-          rgbv[c] = __half2float(__float2half_rn(sg));                           // torch.sigmoid(half)
+          rgbv[c] = inb ? __half2float(__float2half_rn(sg)) : 0.f;                // torch.sigmoid(half)
         }
         __syncwarp();
       }
-      if (valid) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sm.rgb[c][ls] = inb ? rgbv[c] : 0.f;
-      }
-    }
-    __syncthreads();
 
-    // ---- compositing: one warp per ray, exclusive product scan of (1 - alpha + 1e-7) ----
-    for (int lr = warp; lr < nrays; lr += kWarpsN) {
-      const int ray = ray0 + lr;
-      float carry = 1.0f;
-      float wsum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
-      // pass 1: weights; keep them in the alpha slot
-      for (int s0 = 0; s0 < S; s0 += 32) {
-        const int s = s0 + lane;
-        const int ls = lr * S + s;
-        const float al = (s < S) ? sm.alpha[ls] : 0.f;
-        float fct = (s < S) ? (1.0f - al + 1e-7f) : 1.0f;
-        // inclusive product scan
+      // ---- incremental front-to-back compositing (segmented scan over the rays in this tile) ----
+      {
+        const float fct = valid ? (1.0f - alpha + 1e-7f) : 1.0f;
         float inc = fct;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
           const float nb = __shfl_up_sync(0xffffffffu, inc, off);
-          if (lane >= off) inc *= nb;
+          const int nr = __shfl_up_sync(0xffffffffu, lr, off);
+          if (lane >= off && nr == lr) inc *= nb;
         }
         float exc = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) exc = 1.0f;
-        const float T = carry * exc;
-        const float wgt = al * T;
-        carry *= __shfl_sync(0xffffffffu, inc, 31);
-        if (s < S) {
-          sm.alpha[ls] = wgt;
-          const float z = sm.zmid[ls];
-          const float m = sm.maskf[ls];
-          wsum += wgt; dep += z * wgt;
-          cr += sm.rgb[0][ls] * wgt; cg += sm.rgb[1][ls] * wgt; cb += sm.rgb[2][ls] * wgt;
-          nx += sm.grad[0][ls] * wgt * m; ny += sm.grad[1][ls] * wgt * m; nz += sm.grad[2][ls] * wgt * m;
+        const int prev_lr = __shfl_up_sync(0xffffffffu, lr, 1);
+        if (lane == 0 || prev_lr != lr) exc = 1.0f;
+        const float T = (lr == open_ray ? carry_T : 1.0f) * exc;
+        const float wgt = alpha * T;
+        if (valid) { sl.w[ls] = wgt; sl.z[ls] = zm; }
+        const int first_ray = (tile * 32) / S;
+        const int last_ray = min((tile * 32 + 31) / S, nrays - 1);
+        // carry for the ray that stays open after this tile
+        const int last_lane = min(31, nsamp - 1 - tile * 32);
+        const float inc_last = __shfl_sync(0xffffffffu, inc, last_lane);
+        const float carry_next = (last_ray == open_ray ? carry_T : 1.0f) * inc_last;
+        for (int q = first_ray; q <= last_ray; ++q) {
+          const bool mine = valid && lr == q;
+          float v8[8];
+          v8[0] = mine ? wgt : 0.f;
+          v8[1] = mine ? zm * wgt : 0.f;
+          v8[2] = mine ? rgbv[0] * wgt : 0.f;
+          v8[3] = mine ? rgbv[1] * wgt : 0.f;
+          v8[4] = mine ? rgbv[2] * wgt : 0.f;
+          const float m = inb ? 1.f : 0.f;
+          v8[5] = mine ? g3[0] * wgt * m : 0.f;
+          v8[6] = mine ? g3[1] * wgt * m : 0.f;
+          v8[7] = mine ? g3[2] * wgt * m : 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v8[i] = gs_warp_sum(v8[i]) + (q == open_ray ? acc[i] : 0.f);
+          const bool done = (q + 1) * S <= tile * 32 + 32;      // last sample of ray q is in this tile
+          if (done) {
+            const float dep = v8[1];
+            float var = 0.f;
+            __syncwarp();
+            for (int s = lane; s < S; s += 32) {
+              const float dz = sl.z[q * S + s] - dep;
+              var += dz * dz * sl.w[q * S + s];
+            }
+            var = gs_warp_sum(var);
+            if (lane == 0) {
+              const int rg = ray0 + q;
+              a.o.weight_sum[rg] = v8[0]; a.o.depth[rg] = dep; a.o.depth_variance[rg] = var;
+              a.o.color[(size_t)rg * 3 + 0] = v8[2]; a.o.color[(size_t)rg * 3 + 1] = v8[3];
+              a.o.color[(size_t)rg * 3 + 2] = v8[4];
+              a.o.normal[(size_t)rg * 3 + 0] = v8[5]; a.o.normal[(size_t)rg * 3 + 1] = v8[6];
+              a.o.normal[(size_t)rg * 3 + 2] = v8[7];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = v8[i];
+          }
         }
-      }
-      wsum = gs_warp_sum(wsum); dep = gs_warp_sum(dep);
-      cr = gs_warp_sum(cr); cg = gs_warp_sum(cg); cb = gs_warp_sum(cb);
-      nx = gs_warp_sum(nx); ny = gs_warp_sum(ny); nz = gs_warp_sum(nz);
-      float var = 0.f;
-      for (int s = lane; s < S; s += 32) {
-        const int ls = lr * S + s;
-        const float dz = sm.zmid[ls] - dep;
-        var += dz * dz * sm.alpha[ls];
-      }
-      var = gs_warp_sum(var);
-      if (lane == 0) {
-        a.o.color[(size_t)ray * 3 + 0] = cr; a.o.color[(size_t)ray * 3 + 1] = cg;
-        a.o.color[(size_t)ray * 3 + 2] = cb;
-        a.o.depth[ray] = dep; a.o.depth_variance[ray] = var; a.o.weight_sum[ray] = wsum;
-        a.o.normal[(size_t)ray * 3 + 0] = nx; a.o.normal[(size_t)ray * 3 + 1] = ny;
-        a.o.normal[(size_t)ray * 3 + 2] = nz;
+        open_ray = last_ray;
+        carry_T = carry_next;
+        __syncwarp();
       }
     }
-    __syncthreads();
   }
 
   // ---- per-block partials of the eikonal term / in-bound count (deterministic order) ----
@@ -503,7 +612,7 @@ int goslam_neus_forward(const goslam_neus_params* params, const float* rays_o, c
                         const float* z_vals, const float* dists, int R, int S,
                         const goslam_neus_out* out, void* workspace, size_t workspace_bytes,
                         void* stream) {
-  if (!params || !out || R < 0 || S <= 0 || S > 128) return GOSLAM_EINVAL;
+  if (!params || !out || R < 0 || S <= 0 || S > kMaxGroup) return GOSLAM_EINVAL;
   if (R == 0) return GOSLAM_OK;
   if (workspace == nullptr || workspace_bytes < goslam_neus_workspace_bytes(R, S))
     return GOSLAM_EWORKSPACE;
@@ -511,7 +620,17 @@ int goslam_neus_forward(const goslam_neus_params* params, const float* rays_o, c
   static bool init = false;
   if (!init) {
     GridMeta g = make_grid_meta(nullptr);
-    if (cudaMemcpyToSymbol(c_grid, &g, sizeof(g)) != cudaSuccess) return GOSLAM_ELAUNCH;
+    LevelConst lc[kLevels];
+    for (int l = 0; l < kLevels; ++l) {
+      lc[l].scale = g.scale[l];
+      lc[l].res = (unsigned)g.res[l];
+      lc[l].res2 = (unsigned)g.res[l] * (unsigned)g.res[l];
+      lc[l].offset = g.offset[l];
+      const unsigned long long dense = (unsigned long long)g.res[l] * g.res[l] * g.res[l];
+      const bool hashed = dense > g.size[l];
+      if (hashed != (l >= kDenseLevels) || (hashed && g.size[l] != (1u << 19))) return GOSLAM_EINVAL;
+    }
+    if (cudaMemcpyToSymbol(c_lvl, lc, sizeof(lc)) != cudaSuccess) return GOSLAM_ELAUNCH;
     if (cudaFuncSetAttribute(neus_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(Smem)) != cudaSuccess) return GOSLAM_ELAUNCH;
     init = true;
@@ -525,8 +644,13 @@ int goslam_neus_forward(const goslam_neus_params* params, const float* rays_o, c
   a.blk_gerr = ar.take<float>(148 * 4);
   a.blk_count = ar.take<unsigned>(148 * 4);
   a.flag = reinterpret_cast<int*>(ar.take<int>(1));
-  const int groups = gs_cdiv(R, kRaysPerGroup);
-  const int nblk = groups < grid ? groups : grid;
+  // rays per warp work item: make G*S a multiple of 32 when that fits the slab, else pad
+  int G = 32 / std::__gcd(S, 32);
+  if (G * S > kMaxGroup) G = kMaxGroup / S;
+  if (G < 1) return GOSLAM_EINVAL;
+  a.rays_per_group = G;
+  const int groups = gs_cdiv(R, G);
+  const int nblk = gs_cdiv(groups, kWarpsN) < grid ? gs_cdiv(groups, kWarpsN) : grid;
   for (int mode = 0; mode < 2; ++mode) {
     a.mode = mode;
     neus_forward_kernel<<<nblk, kThreadsN, sizeof(Smem), st>>>(a);
