@@ -486,33 +486,49 @@ __device__ __forceinline__ void retract_poses(float* poses, const BaDims& d, con
 // Small systems (6P <= kWarpSolveMaxN): ONE warp, matrix in shared memory, no block barriers,
 // one rsqrt per column and no divisions (the diagonal stores 1/l_jj).  A local window of 8
 // keyframes is a 42x42 system: latency, not throughput, is what matters.
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 ba_solve_warp_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __restrict__ sys_in,
                      float lm, float ep, float* __restrict__ dx_out, int* __restrict__ status_out) {
   extern __shared__ double smd[];
-  const int n = d.n, lane = threadIdx.x;
-  double* A = smd;
-  double* y = smd + (size_t)n * n;
-  for (int idx = lane; idx < n * n; idx += 32) {
-    const int r = idx / n, c = idx - r * n;
-    double val = sys_in[idx];
-    if (r == c) val += (double)ep + (double)lm * val;
-    A[idx] = val;
-  }
-  for (int i = lane; i < n; i += 32) y[i] = sys_in[(size_t)n * n + i];
-  __syncwarp();
+  const int n = d.n, tid = threadIdx.x, lane = tid & 31;
+  double* __restrict__ A = smd;
+  double* __restrict__ y = smd + (size_t)n * n;
+  double* __restrict__ colj = y + n;
+  // all 4 warps stage the damped system (coalesced rows), then warp 0 works alone
+  for (int r = tid >> 5; r < n; r += 4)
+    for (int c = lane; c < n; c += 32) {
+      double val = sys_in[(size_t)r * n + c];
+      if (r == c) val += (double)ep + (double)lm * val;
+      A[r * n + c] = val;
+    }
+  for (int i = tid; i < n; i += 128) y[i] = sys_in[(size_t)n * n + i];
+  __syncthreads();
+  if (tid >= 32) return;
+
   int fail = 0;
   for (int j = 0; j < n; ++j) {
     const double ajj = A[j * n + j];
     if (!(ajj > 0.0)) { fail = 1; break; }             // warp-uniform
     const double inv = rsqrt(ajj);
     __syncwarp();
-    for (int i = j + 1 + lane; i < n; i += 32) A[i * n + j] *= inv;
+    for (int i = j + 1 + lane; i < n; i += 32) {
+      const double l = A[i * n + j] * inv;
+      A[i * n + j] = l;
+      colj[i] = l;                                      // column j, contiguous, for the update below
+    }
     if (lane == 0) A[j * n + j] = inv;
     __syncwarp();
     for (int i = j + 1 + lane; i < n; i += 32) {
-      const double lij = A[i * n + j];
-      for (int c = j + 1; c <= i; ++c) A[i * n + c] -= lij * A[c * n + j];
+      const double lij = colj[i];
+      double* __restrict__ row = A + i * n;
+      int c = j + 1;
+      for (; c + 3 <= i; c += 4) {                      // loads first, then FMAs, then stores
+        const double a0 = row[c], a1 = row[c + 1], a2 = row[c + 2], a3 = row[c + 3];
+        const double b0 = colj[c], b1 = colj[c + 1], b2 = colj[c + 2], b3 = colj[c + 3];
+        row[c] = a0 - lij * b0; row[c + 1] = a1 - lij * b1;
+        row[c + 2] = a2 - lij * b2; row[c + 3] = a3 - lij * b3;
+      }
+      for (; c <= i; ++c) row[c] -= lij * colj[c];
     }
     __syncwarp();
   }
@@ -689,12 +705,12 @@ int launch_phase2(float* poses, float* disps, const double* sys_in,
     cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(((size_t)kSmemSolveMaxN * kSmemSolveMaxN + kSmemSolveMaxN) * 8));
     cudaFuncSetAttribute(ba_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(((size_t)kWarpSolveMaxN * kWarpSolveMaxN + kWarpSolveMaxN) * 8));
+                         (int)(((size_t)kWarpSolveMaxN * kWarpSolveMaxN + 2 * kWarpSolveMaxN) * 8));
     attr_set = true;
   }
   if (d.n <= kWarpSolveMaxN) {
-    const size_t smem = ((size_t)d.n * d.n + d.n) * sizeof(double);
-    ba_solve_warp_kernel<<<1, 32, smem, st>>>(poses, d, ws, sys_in, lm, ep, dx_out, status_out);
+    const size_t smem = ((size_t)d.n * d.n + 2 * d.n) * sizeof(double);
+    ba_solve_warp_kernel<<<1, 128, smem, st>>>(poses, d, ws, sys_in, lm, ep, dx_out, status_out);
   } else {
     const int use_smem = d.n <= kSmemSolveMaxN;
     const size_t smem = use_smem ? ((size_t)d.n * d.n + d.n) * sizeof(double) : 0;

@@ -169,7 +169,7 @@ static_assert(32 * 33 * 4 <= 32 * kInPad * 2, "fp32 SDF-head tile must fit in ac
 
 struct LevelConst {
   float scale;
-  unsigned res, res2, offset;
+  unsigned res, res2, offset, size;
 };
 __constant__ LevelConst c_lvl[kLevels];
 
@@ -204,11 +204,15 @@ __device__ __forceinline__ void encode_level(int l, const __half2* __restrict__ 
     for (int q = 0; q < 8; ++q)
       idx[q] = (((q & 1) ? hx1 : hx0) ^ ((q & 2) ? hy1 : hy0) ^ ((q & 4) ? hz1 : hz0)) & 0x7FFFFu;
   } else {
-    // dense level: index < res^3 <= table size by construction, no modulo needed
+    // dense level: tcnn's `index % size`.  pos = x*scale + 0.5 reaches res-1+0.5, so the +1
+    // corner can index one past the last row/plane and wraps; index < 2*size always, so the
+    // modulo is one conditional subtract.
     const unsigned base = pg[0] + pg[1] * L.res + pg[2] * L.res2;
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      idx[q] = base + ((q & 1) ? 1u : 0u) + ((q & 2) ? L.res : 0u) + ((q & 4) ? L.res2 : 0u);
+    for (int q = 0; q < 8; ++q) {
+      const unsigned i = base + ((q & 1) ? 1u : 0u) + ((q & 2) ? L.res : 0u) + ((q & 4) ? L.res2 : 0u);
+      idx[q] = i >= L.size ? i - L.size : i;
+    }
   }
   const __half2* lvl = table + L.offset;
   __half2 v[8];
@@ -626,6 +630,7 @@ int goslam_neus_forward(const goslam_neus_params* params, const float* rays_o, c
       lc[l].res = (unsigned)g.res[l];
       lc[l].res2 = (unsigned)g.res[l] * (unsigned)g.res[l];
       lc[l].offset = g.offset[l];
+      lc[l].size = g.size[l];
       const unsigned long long dense = (unsigned long long)g.res[l] * g.res[l] * g.res[l];
       const bool hashed = dense > g.size[l];
       if (hashed != (l >= kDenseLevels) || (hashed && g.size[l] != (1u << 19))) return GOSLAM_EINVAL;
