@@ -483,18 +483,21 @@ __device__ __forceinline__ void retract_poses(float* poses, const BaDims& d, con
   }
 }
 
-// Small systems (6P <= kWarpSolveMaxN): ONE warp, matrix in shared memory, no block barriers,
-// one rsqrt per column and no divisions (the diagonal stores 1/l_jj).  A local window of 8
-// keyframes is a 42x42 system: latency, not throughput, is what matters.
+// Small systems (6P <= kWarpSolveMaxN): blocked right-looking Cholesky with the natural 6x6
+// pose blocks, matrix in shared memory, 128 threads, 3 barriers per block column (a local
+// window of 8 keyframes is 7 block columns).  The 6x6 diagonal factor is computed redundantly in
+// registers; one rsqrt per column and no divisions.  Blocked forward/backward substitution.
 __global__ void __launch_bounds__(128)
 ba_solve_warp_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __restrict__ sys_in,
                      float lm, float ep, float* __restrict__ dx_out, int* __restrict__ status_out) {
   extern __shared__ double smd[];
-  const int n = d.n, tid = threadIdx.x, lane = tid & 31;
-  double* __restrict__ A = smd;
+  __shared__ double Ld[6][6];       // factor of the current diagonal block (diag = 1/l_kk)
+  __shared__ double xs[6];
+  __shared__ int failed;
+  const int n = d.n, P = d.P, tid = threadIdx.x, lane = tid & 31;
+  double* __restrict__ A = smd;                       // lower triangle is used
   double* __restrict__ y = smd + (size_t)n * n;
-  double* __restrict__ colj = y + n;
-  // all 4 warps stage the damped system (coalesced rows), then warp 0 works alone
+  double* __restrict__ invd = y + n;                  // 1/l_jj
   for (int r = tid >> 5; r < n; r += 4)
     for (int c = lane; c < n; c += 32) {
       double val = sys_in[(size_t)r * n + c];
@@ -502,58 +505,133 @@ ba_solve_warp_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double*
       A[r * n + c] = val;
     }
   for (int i = tid; i < n; i += 128) y[i] = sys_in[(size_t)n * n + i];
+  if (tid == 0) failed = 0;
   __syncthreads();
-  if (tid >= 32) return;
 
-  int fail = 0;
-  for (int j = 0; j < n; ++j) {
-    const double ajj = A[j * n + j];
-    if (!(ajj > 0.0)) { fail = 1; break; }             // warp-uniform
-    const double inv = rsqrt(ajj);
-    __syncwarp();
-    for (int i = j + 1 + lane; i < n; i += 32) {
-      const double l = A[i * n + j] * inv;
-      A[i * n + j] = l;
-      colj[i] = l;                                      // column j, contiguous, for the update below
-    }
-    if (lane == 0) A[j * n + j] = inv;
-    __syncwarp();
-    for (int i = j + 1 + lane; i < n; i += 32) {
-      const double lij = colj[i];
-      double* __restrict__ row = A + i * n;
-      int c = j + 1;
-      for (; c + 3 <= i; c += 4) {                      // loads first, then FMAs, then stores
-        const double a0 = row[c], a1 = row[c + 1], a2 = row[c + 2], a3 = row[c + 3];
-        const double b0 = colj[c], b1 = colj[c + 1], b2 = colj[c + 2], b3 = colj[c + 3];
-        row[c] = a0 - lij * b0; row[c + 1] = a1 - lij * b1;
-        row[c + 2] = a2 - lij * b2; row[c + 3] = a3 - lij * b3;
+  for (int jb = 0; jb < P; ++jb) {
+    const int j0 = 6 * jb;
+    // (a) 6x6 diagonal block, left-looking, every thread of warp 0 redundantly (registers)
+    if (tid < 32) {
+      double l[6][6];
+      bool bad = false;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double dkk = A[(j0 + k) * n + j0 + k];
+#pragma unroll
+        for (int m = 0; m < k; ++m) dkk -= l[k][m] * l[k][m];
+        if (!(dkk > 0.0)) bad = true;
+        const double inv = rsqrt(dkk);
+        l[k][k] = inv;
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r) {
+          double v = A[(j0 + r) * n + j0 + k];
+#pragma unroll
+          for (int m = 0; m < k; ++m) v -= l[r][m] * l[k][m];
+          l[r][k] = v * inv;
+        }
       }
-      for (; c <= i; ++c) row[c] -= lij * colj[c];
+      if (lane == 0) {
+        if (bad) failed = 1;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+          for (int c = 0; c <= r; ++c) {
+            Ld[r][c] = l[r][c];
+            if (c < r) A[(j0 + r) * n + j0 + c] = l[r][c];   // L below the diagonal; 1/l_rr in invd
+          }
+          invd[j0 + r] = l[r][r];
+        }
+      }
     }
-    __syncwarp();
+    __syncthreads();
+    if (failed) break;
+    // (b) panel: rows below the block, x L_d^T = a_row
+    for (int i = j0 + 6 + tid; i < n; i += 128) {
+      double x[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double v = A[i * n + j0 + k];
+#pragma unroll
+        for (int m = 0; m < k; ++m) v -= x[m] * Ld[k][m];
+        x[k] = v * Ld[k][k];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) A[i * n + j0 + k] = x[k];
+    }
+    __syncthreads();
+    // (c) rank-6 update of the trailing lower triangle
+    const int m = n - j0 - 6;
+    for (int idx = tid; idx < m * m; idx += 128) {
+      const int q = idx / m;
+      const int i = j0 + 6 + q, c = j0 + 6 + (idx - q * m);
+      if (c > i) continue;
+      double acc = A[i * n + c];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc -= A[i * n + j0 + k] * A[c * n + j0 + k];
+      A[i * n + c] = acc;
+    }
+    __syncthreads();
   }
+
+  int fail = failed;
   if (!fail) {
-    for (int j = 0; j < n; ++j) {                       // L z = b
-      const double zj = y[j] * A[j * n + j];
-      __syncwarp();
-      if (lane == 0) y[j] = zj;
-      for (int i = j + 1 + lane; i < n; i += 32) y[i] -= A[i * n + j] * zj;
-      __syncwarp();
+    // forward: L z = b, block by block
+    for (int jb = 0; jb < P; ++jb) {
+      const int j0 = 6 * jb;
+      if (tid == 0) {
+        double z[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double v = y[j0 + k];
+#pragma unroll
+          for (int mm = 0; mm < k; ++mm) v -= A[(j0 + k) * n + j0 + mm] * z[mm];
+          z[k] = v * invd[j0 + k];
+          xs[k] = z[k];
+          y[j0 + k] = z[k];
+        }
+      }
+      __syncthreads();
+      for (int i = j0 + 6 + tid; i < n; i += 128) {
+        double v = y[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v -= A[i * n + j0 + k] * xs[k];
+        y[i] = v;
+      }
+      __syncthreads();
     }
-    for (int j = n - 1; j >= 0; --j) {                  // L^T x = z
-      const double xj = y[j] * A[j * n + j];
-      __syncwarp();
-      if (lane == 0) y[j] = xj;
-      for (int i = lane; i < j; i += 32) y[i] -= A[j * n + i] * xj;
-      __syncwarp();
+    // backward: L^T x = z
+    for (int jb = P - 1; jb >= 0; --jb) {
+      const int j0 = 6 * jb;
+      if (tid < 6) {                                   // s_k = sum_{i below} L[i][j0+k] x[i]
+        double sacc = 0.0;
+        for (int i = j0 + 6; i < n; ++i) sacc += A[i * n + j0 + tid] * y[i];
+        xs[tid] = y[j0 + tid] - sacc;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double x[6];
+#pragma unroll
+        for (int k = 5; k >= 0; --k) {
+          double v = xs[k];
+#pragma unroll
+          for (int mm = k + 1; mm < 6; ++mm) v -= A[(j0 + mm) * n + j0 + k] * x[mm];
+          x[k] = v * invd[j0 + k];
+          y[j0 + k] = x[k];
+        }
+      }
+      __syncthreads();
     }
-    int bad = 0;
-    for (int i = lane; i < n; i += 32) bad |= !isfinite(y[i]);
-    fail = __any_sync(0xffffffffu, bad) ? 1 : 0;
+    if (tid < 32) {
+      int bad = 0;
+      for (int i = lane; i < n; i += 32) bad |= !isfinite(y[i]);
+      if (__any_sync(0xffffffffu, bad) && lane == 0) failed = 1;
+    }
+    __syncthreads();
+    fail = failed;
   }
-  solve_finish(poses, d, ws, y, fail, dx_out, status_out, lane, 32);
-  __syncwarp();
-  retract_poses(poses, d, ws, lane, 32);
+  solve_finish(poses, d, ws, y, fail, dx_out, status_out, tid, 128);
+  __syncthreads();
+  retract_poses(poses, d, ws, tid, 128);
 }
 
 // General case: one block; A in shared memory when it fits, else in the global scratch.

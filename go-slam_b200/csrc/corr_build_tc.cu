@@ -23,12 +23,15 @@
 // operands use the canonical K-major SWIZZLE_128B UMMA layout.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
+#include <cstring>
 
 int gs_corr_build_simt_f16(const __half* f1, const __half* f2, __half* const* levels,
                            int num_levels, int N, int D, int h, int w, cudaStream_t st);
 
 namespace {
 
+constexpr int kEpiGroupsC = 2;
 constexpr int kD = 128;                 // channels (K)
 constexpr int kBM = 128;                // source pixels per tile
 constexpr int kPY = 8, kPX = 16;        // target patch
@@ -36,10 +39,13 @@ constexpr int kBN = kPY * kPX;          // 128
 constexpr int kKBox = 64;               // channels per TMA box (128 B)
 constexpr int kTileBytes = kBM * kD * 2;          // 32 KB (A or B tile)
 constexpr int kBoxBytes = kBM * kKBox * 2;        // 16 KB
-constexpr int kAStages = 2, kBStages = 3, kTStages = 2;
+constexpr int kAStages = 2, kBStages = 2, kTStages = 2;
 constexpr int kEpiGroups = 2;               // one epilogue warp-group (4 warps) per TMEM stage
 constexpr int kThreadsTC = 64 + kEpiGroups * 128;
-constexpr int kSmemTC = 1024 + (kAStages + kBStages) * kTileBytes + 256;
+constexpr int kStageL0 = kPY * kBM * kPX * 2;              // [8][128][16] halves = 32 KB
+constexpr int kStageL1 = (kPY / 2) * kBM * (kPX / 2) * 2;  // [4][128][8]  halves =  8 KB
+constexpr int kStageBytes = kStageL0 + kStageL1;           // per epilogue group
+constexpr int kSmemTC = 1024 + (kAStages + kBStages) * kTileBytes + kEpiGroupsC * kStageBytes + 256;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -90,6 +96,23 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)), "l"((uint64_t)map),
       "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          (uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void group_bar(int id) {
+  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -150,6 +173,7 @@ struct TcParams {
   // optional edge -> feature-map-slot indirection (video-level K-major feature maps):
   // slot1 = rig*ii[e], slot2 = rig*jj[e] + (ii[e]==jj[e])   (src/factor_graph.py:108-113,290)
   const int64_t* ii; const int64_t* jj; int rig;
+  int tma_l0, tma_l1;         // level 0 / 1 leave through TMA tensor stores (else direct STG)
 };
 
 // ---- packed fp16 rows live in registers as uint32 pairs (lo = even column) ----
@@ -207,14 +231,17 @@ __device__ __forceinline__ void store_row(__half* dst, const uint32_t (&r)[NW], 
 
 __global__ void __launch_bounds__(kThreadsTC, 1)
 corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                     const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+                     const __grid_constant__ CUtensorMap mapB,
+                     const __grid_constant__ CUtensorMap mapL0,
+                     const __grid_constant__ CUtensorMap mapL1, const TcParams p) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   unsigned char* base =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* smA = base;
   unsigned char* smB = base + kAStages * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (kAStages + kBStages) * kTileBytes);
+  unsigned char* smStage = base + (kAStages + kBStages) * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smStage + kEpiGroupsC * kStageBytes);
   uint64_t* full_a = bars;                       // [kAStages]
   uint64_t* empty_a = full_a + kAStages;
   uint64_t* full_b = empty_a + kAStages;         // [kBStages]
@@ -304,6 +331,10 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;             // row of the 128-row tile
     const int ts = group;
+    const bool use_tma = (p.tma_l0 | p.tma_l1) != 0;
+    const bool elected = (warp == 2 + 4 * group) && lane == 0;
+    unsigned char* stg0 = smStage + group * kStageBytes;      // [8][128][16] halves
+    unsigned char* stg1 = stg0 + kStageL0;                    // [4][128][8]  halves
     int tph = 0, tile = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int yb = item % p.n_yb;
@@ -318,6 +349,11 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
         const int x0 = xb * kPX;
         mbar_wait(&tm_full[ts], tph);
         tc_fence_after();
+        if (use_tma) {
+          // the previous tensor store issued from this group's staging buffer must have been read
+          if (elected) bulk_wait_read0();
+          group_bar(1 + group);
+        }
         const uint32_t taddr = tmem_base + ts * kBN + ((uint32_t)(quad * 32) << 16);
         uint32_t l1[4][4];     // level-1 rows (8 halves each) of this patch
         uint32_t l2[2][2];     // level-2 rows (4 halves each)
@@ -336,14 +372,26 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
               const int y = y0 + 2 * c + r;
+              if (p.tma_l0) continue;
               if (y < p.h) store_row<8>(p.lvl[0] + (plane_id * p.h + y) * p.w + x0, h0[r], p.w - x0);
+            }
+          }
+          if (p.tma_l0) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              uint4* dst = reinterpret_cast<uint4*>(stg0 + ((2 * c + r) * kBM + row) * (kPX * 2));
+              dst[0] = make_uint4(h0[r][0], h0[r][1], h0[r][2], h0[r][3]);
+              dst[1] = make_uint4(h0[r][4], h0[r][5], h0[r][6], h0[r][7]);
             }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             l1[c][j] = pack2(pool_pair(h0[0][2 * j], h0[1][2 * j]),
                              pool_pair(h0[0][2 * j + 1], h0[1][2 * j + 1]));
-          if (src_ok && p.num_levels > 1) {
+          if (p.tma_l1) {
+            *reinterpret_cast<uint4*>(stg1 + (c * kBM + row) * (kPX)) =
+                make_uint4(l1[c][0], l1[c][1], l1[c][2], l1[c][3]);
+          } else if (src_ok && p.num_levels > 1) {
             const int h1 = p.h >> 1, w1 = p.w >> 1;
             const int y = (y0 >> 1) + c, x = x0 >> 1;
             if (y < h1 && x < w1) store_row<4>(p.lvl[1] + (plane_id * h1 + y) * w1 + x, l1[c], w1 - x);
@@ -365,6 +413,15 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tm_empty[ts]);
+        if (use_tma) {
+          fence_async_smem();                      // generic-proxy smem writes -> async proxy
+          group_bar(1 + group);
+          if (elected) {
+            if (p.tma_l0) tma_store_4d(&mapL0, stg0, x0, mt * kBM, y0, n);
+            if (p.tma_l1) tma_store_4d(&mapL1, stg1, x0 >> 1, mt * kBM, y0 >> 1, n);
+            bulk_commit();
+          }
+        }
         if (src_ok && p.num_levels > 3) {
           uint32_t l3[1];
           l3[0] = pack2(pool_pair(l2[0][0], l2[1][0]), pool_pair(l2[0][1], l2[1][1]));
@@ -375,6 +432,7 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
         tph ^= 1;
       }
     }
+    if (use_tma && elected) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -403,6 +461,9 @@ to_kmajor_kernel(const __half* __restrict__ in, __half* __restrict__ out, int hw
     }
   }
 }
+
+// GOSLAM_TC_DIRECT_STORE=1 forces the direct-STG epilogue (A/B switch for profiling)
+static const bool g_tma_store = [] { const char* e = getenv("GOSLAM_TC_DIRECT_STORE"); return !(e && e[0] == '1'); }();
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -451,6 +512,22 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
   }
   TcParams p{};
   for (int i = 0; i < 4; ++i) p.lvl[i] = i < num_levels ? levels[i] : nullptr;
+  // output tensor maps (x, source pixel, y, edge): the epilogue stages [y][src][x] tiles in
+  // shared memory and the TMA engine streams the 32-byte rows out, clipping ragged edges
+  CUtensorMap mapL0, mapL1;
+  memset(&mapL0, 0, sizeof(mapL0)); memset(&mapL1, 0, sizeof(mapL1));
+  auto make_out_map = [&](CUtensorMap* m, __half* ptr, int hl, int wl, int bx, int by) -> bool {
+    if (ptr == nullptr || (wl * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)wl, (cuuint64_t)hw, (cuuint64_t)hl, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)hl * wl * 2, (cuuint64_t)wl * 2, (cuuint64_t)hw * hl * wl * 2};
+    cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)kBM, (cuuint32_t)by, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ptr, dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  p.tma_l0 = (g_tma_store && make_out_map(&mapL0, levels[0], h, w, kPX, kPY)) ? 1 : 0;
+  p.tma_l1 = (g_tma_store && num_levels > 1 && make_out_map(&mapL1, levels[1], h >> 1, w >> 1, kPX / 2, kPY / 2)) ? 1 : 0;
   p.num_levels = num_levels; p.N = N; p.h = h; p.w = w; p.hw = hw;
   p.n_mt = gs_cdiv(hw, kBM); p.n_yb = gs_cdiv(h, kPY); p.n_xb = gs_cdiv(w, kPX);
   p.n_items = N * p.n_mt * p.n_yb;
@@ -469,7 +546,7 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = p.n_items < sms ? p.n_items : sms;
-  corr_build_tc_kernel<<<grid, kThreadsTC, kSmemTC, st>>>(mapA, mapB, p);
+  corr_build_tc_kernel<<<grid, kThreadsTC, kSmemTC, st>>>(mapA, mapB, mapL0, mapL1, p);
   GS_CHECK_LAUNCH();
   return GOSLAM_OK;
 }
