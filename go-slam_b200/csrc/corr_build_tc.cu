@@ -45,6 +45,17 @@ constexpr int kThreadsTC = 64 + kEpiGroups * 128;
 constexpr int kStageL0 = kPY * kBM * kPX * 2;              // [8][128][16] halves = 32 KB
 constexpr int kStageL1 = (kPY / 2) * kBM * (kPX / 2) * 2;  // [4][128][8]  halves =  8 KB
 constexpr int kStageBytes = kStageL0 + kStageL1;           // per epilogue group
+// pooled-level staging of one work item (all x-tiles of an 8-row band), so that levels 1-3 leave
+// the SM as long contiguous runs of complete 32-byte sectors (partial-sector writes cost an ECC
+// read-modify-write in L2 and were measured to cost more than all of level 0):
+constexpr int kMaxXB = 5;                                  // x-tiles per band supported by the stage (w <= 80)
+constexpr int kP1Row = kMaxXB * 8 * 2;                     // 80 B  : one level-1 row of the band
+constexpr int kP1Src = 4 * kP1Row + 16;                    // 336 B : 4 rows + pad (bank-conflict-free)
+constexpr int kP2Row = kMaxXB * 4 * 2;                     // 40 B
+constexpr int kP2Src = 2 * kP2Row + 8;                     // 88 B
+constexpr int kP3Src = kMaxXB * 2 * 2 + 4;                 // 24 B
+constexpr int kPoolBytes = kBM * (kP1Src + kP2Src + kP3Src);   // 57,344 B
+static_assert(kPoolBytes <= kEpiGroupsC * kStageBytes, "pooled staging aliases the TMA-store staging");
 constexpr int kSmemTC = 1024 + (kAStages + kBStages) * kTileBytes + kEpiGroupsC * kStageBytes + 256;
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -174,6 +185,8 @@ struct TcParams {
   // slot1 = rig*ii[e], slot2 = rig*jj[e] + (ii[e]==jj[e])   (src/factor_graph.py:108-113,290)
   const int64_t* ii; const int64_t* jj; int rig;
   int tma_l0, tma_l1;         // level 0 / 1 leave through TMA tensor stores (else direct STG)
+  int experiment;             // profiling only: 1 = no output writes, 2 = no TMEM reads
+  int pool_stage;             // levels 1-3 staged per band in smem and written as contiguous runs
 };
 
 // ---- packed fp16 rows live in registers as uint32 pairs (lo = even column) ----
@@ -330,22 +343,31 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
     const int group = (warp - 2) >> 2;
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;             // row of the 128-row tile
-    const int ts = group;
-    const bool use_tma = (p.tma_l0 | p.tma_l1) != 0;
+    int ts = group;
+    const bool single = p.experiment == 5;        // profiling: one epilogue group drains both stages
+    const bool use_tma = (p.tma_l0 | p.tma_l1) != 0 && p.experiment != 1;
     const bool elected = (warp == 2 + 4 * group) && lane == 0;
     unsigned char* stg0 = smStage + group * kStageBytes;      // [8][128][16] halves
     unsigned char* stg1 = stg0 + kStageL0;                    // [4][128][8]  halves
+    unsigned char* pool1 = smStage;                            // [128][kP1Src]
+    unsigned char* pool2 = pool1 + kBM * kP1Src;               // [128][kP2Src]
+    unsigned char* pool3 = pool2 + kBM * kP2Src;               // [128][kP3Src]
+    const int etid = threadIdx.x - 64;                         // 0..255 within the epilogue warps
     int tph = 0, tile = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int yb = item % p.n_yb;
       const int mt = (item / p.n_yb) % p.n_mt;
       const int n = item / (p.n_yb * p.n_mt);
       const int src = mt * kBM + row;
-      const bool src_ok = src < p.hw;
+      const bool src_ok = src < p.hw && p.experiment != 1;
       const long long plane_id = (long long)n * p.hw + src;
       const int y0 = yb * kPY;
       for (int xb = 0; xb < p.n_xb; ++xb, ++tile) {
-        if ((tile & (kTStages - 1)) != ts) continue;
+        if (single) {
+          if (group != 0) continue;
+          ts = tile & (kTStages - 1);
+          tph = (tile >> 1) & 1;
+        } else if ((tile & (kTStages - 1)) != ts) continue;
         const int x0 = xb * kPX;
         mbar_wait(&tm_full[ts], tph);
         tc_fence_after();
@@ -360,7 +382,11 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
+          if (p.experiment != 2) tmem_ld32(taddr + c * 32, v);
+          else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = 0x3f800000u + q;
+          }
           uint32_t h0[2][8];
 #pragma unroll
           for (int r = 0; r < 2; ++r)
@@ -388,7 +414,10 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
           for (int j = 0; j < 4; ++j)
             l1[c][j] = pack2(pool_pair(h0[0][2 * j], h0[1][2 * j]),
                              pool_pair(h0[0][2 * j + 1], h0[1][2 * j + 1]));
-          if (p.tma_l1) {
+          if (p.pool_stage) {
+            *reinterpret_cast<uint4*>(pool1 + row * kP1Src + c * kP1Row + xb * 16) =
+                make_uint4(l1[c][0], l1[c][1], l1[c][2], l1[c][3]);
+          } else if (p.tma_l1) {
             *reinterpret_cast<uint4*>(stg1 + (c * kBM + row) * (kPX)) =
                 make_uint4(l1[c][0], l1[c][1], l1[c][2], l1[c][3]);
           } else if (src_ok && p.num_levels > 1) {
@@ -402,7 +431,9 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
             for (int j = 0; j < 2; ++j)
               l2[q][j] = pack2(pool_pair(l1[c - 1][2 * j], l1[c][2 * j]),
                                pool_pair(l1[c - 1][2 * j + 1], l1[c][2 * j + 1]));
-            if (src_ok && p.num_levels > 2) {
+            if (p.pool_stage) {
+              *reinterpret_cast<uint2*>(pool2 + row * kP2Src + q * kP2Row + xb * 8) = make_uint2(l2[q][0], l2[q][1]);
+            } else if (src_ok && p.num_levels > 2) {
               const int h2 = p.h >> 2, w2 = p.w >> 2;
               const int y = (y0 >> 2) + q, x = x0 >> 2;
               if (y < h2 && x < w2) store_row<2>(p.lvl[2] + (plane_id * h2 + y) * w2 + x, l2[q], w2 - x);
@@ -422,7 +453,10 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
             bulk_commit();
           }
         }
-        if (src_ok && p.num_levels > 3) {
+        if (p.pool_stage) {
+          *reinterpret_cast<uint32_t*>(pool3 + row * kP3Src + xb * 4) =
+              pack2(pool_pair(l2[0][0], l2[1][0]), pool_pair(l2[0][1], l2[1][1]));
+        } else if (src_ok && p.num_levels > 3) {
           uint32_t l3[1];
           l3[0] = pack2(pool_pair(l2[0][0], l2[1][0]), pool_pair(l2[0][1], l2[1][1]));
           const int h3 = p.h >> 3, w3 = p.w >> 3;
@@ -430,6 +464,56 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
           if (y < h3 && x < w3) store_row<1>(p.lvl[3] + (plane_id * h3 + y) * w3 + x, l3, w3 - x);
         }
         tph ^= 1;
+      }
+      if (p.pool_stage) {
+        // ---- band write-out: both epilogue groups have staged all x-tiles of this 8-row band ----
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        const int s_loc = etid >> 1, part = etid & 1;          // two threads per source pixel
+        const int s_glb = mt * kBM + s_loc;
+        if (s_glb < p.hw) {
+          const long long pl = (long long)n * p.hw + s_glb;
+          // level 1: 4 full rows = 4*w1 halves contiguous (w1 == n_xb*8), 32-byte aligned
+          {
+            const int w1b = p.n_xb * 16;                        // bytes per level-1 row
+            unsigned char* g = reinterpret_cast<unsigned char*>(p.lvl[1]) + (pl * (p.h >> 1) + (y0 >> 1)) * w1b;
+            const unsigned char* sp = pool1 + s_loc * kP1Src;
+            const int total = 4 * w1b;                          // bytes, multiple of 64
+            for (int off = part * 32; off < total; off += 64) {
+              // staging rows are kP1Row apart, global rows w1b apart
+              uint32_t rr[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int o = off + 4 * k;
+                rr[k] = *reinterpret_cast<const uint32_t*>(sp + (o / w1b) * kP1Row + (o % w1b));
+              }
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(g + off), "r"(rr[0]),
+                           "r"(rr[1]), "r"(rr[2]), "r"(rr[3]), "r"(rr[4]), "r"(rr[5]), "r"(rr[6]), "r"(rr[7])
+                           : "memory");
+            }
+          }
+          if (part == 0 && p.num_levels > 2) {                  // level 2: 2 rows of w2 halves
+            const int w2b = p.n_xb * 8;
+            unsigned char* g = reinterpret_cast<unsigned char*>(p.lvl[2]) + (pl * (p.h >> 2) + (y0 >> 2)) * w2b;
+            const unsigned char* sp = pool2 + s_loc * kP2Src;
+            for (int off = 0; off < 2 * w2b; off += 16) {       // 2*w2b = n_xb*16: whole 16-byte chunks
+              uint32_t rr[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int o = off + 4 * k;
+                rr[k] = *reinterpret_cast<const uint32_t*>(sp + (o / w2b) * kP2Row + (o % w2b));
+              }
+              *reinterpret_cast<uint4*>(g + off) = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+            }
+          }
+          if (part == 1 && p.num_levels > 3) {                  // level 3: 1 row of w3 halves
+            const int w3b = p.n_xb * 4;
+            unsigned char* g = reinterpret_cast<unsigned char*>(p.lvl[3]) + (pl * (p.h >> 3) + (y0 >> 3)) * w3b;
+            const unsigned char* sp = pool3 + s_loc * kP3Src;
+            for (int off = 0; off < w3b; off += 4)
+              *reinterpret_cast<uint32_t*>(g + off) = *reinterpret_cast<const uint32_t*>(sp + off);
+          }
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
       }
     }
     if (use_tma && elected) bulk_wait_all();
@@ -512,6 +596,8 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
   }
   TcParams p{};
   for (int i = 0; i < 4; ++i) p.lvl[i] = i < num_levels ? levels[i] : nullptr;
+  const char* exp_env = getenv("GOSLAM_TC_EXPERIMENT");
+  const int exp_id = exp_env ? atoi(exp_env) : 0;
   // output tensor maps (x, source pixel, y, edge): the epilogue stages [y][src][x] tiles in
   // shared memory and the TMA engine streams the 32-byte rows out, clipping ragged edges
   CUtensorMap mapL0, mapL1;
@@ -532,6 +618,14 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
   p.n_mt = gs_cdiv(hw, kBM); p.n_yb = gs_cdiv(h, kPY); p.n_xb = gs_cdiv(w, kPX);
   p.n_items = N * p.n_mt * p.n_yb;
   p.ii = ii; p.jj = jj; p.rig = rig;
+  p.experiment = exp_id;
+  // band staging of the pooled levels needs whole tiles and sector-aligned level-1 bands
+  static const bool no_pool_stage = [] { const char* e = getenv("GOSLAM_TC_NO_POOL_STAGE"); return e && e[0] == '1'; }();
+  p.pool_stage = (!no_pool_stage && num_levels == 4 && w % 16 == 0 && h % 8 == 0 && p.n_xb <= kMaxXB &&
+                  exp_id != 1 && exp_id != 3) ? 1 : 0;
+  if (p.pool_stage) { p.tma_l0 = 0; p.tma_l1 = 0; }       // level 0 leaves as full-sector STG.256
+  if (exp_id == 1) { p.tma_l0 = 0; p.tma_l1 = 0; }
+  if (exp_id == 3) { p.num_levels = 1; p.tma_l1 = 0; }   // level 0 only
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(corr_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
