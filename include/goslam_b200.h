@@ -70,8 +70,9 @@ int goslam_corr_build(const void* fmap1, const void* fmap2, void* const* levels,
                       int num_levels, int N, int D, int h, int w, int impl,
                       void* workspace, size_t workspace_bytes, void* stream);
 /* Video-level form of FactorGraph.add_factors' correlation build (src/factor_graph.py:106-114):
- * the per-frame feature maps are kept K-major ([F = buffer*rig, h*w, D] f16, converted ONCE when a
- * keyframe is inserted by goslam_fmaps_to_kmajor from DepthVideo.fmaps' [F, D, h, w]) and the
+ * the per-frame feature maps are kept K-major AND PRE-SCALED BY 1/4 in half — the reference's
+ * `fmap / 4.0` (src/modules/corr.py:71-72) — as [F = buffer*rig, h*w, D] f16, converted ONCE when a
+ * keyframe is inserted by goslam_fmaps_to_kmajor from DepthVideo.fmaps' [F, D, h, w], and the
  * kernel indexes them per edge on the device: slot1 = rig*ii[e], slot2 = rig*jj[e] + (ii[e]==jj[e])
  * — no gathered [N,D,h,w] copies, no per-edge re-layout.  Tensor-core kernel only (D == 128). */
 int goslam_fmaps_to_kmajor(const void* fmaps, void* out, int F, int D, int h, int w, void* stream);
