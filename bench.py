@@ -291,8 +291,13 @@ def main():
     build_bytes = N * (2 * 128 * hw * 2 + hw * lvl * 2)
     build_flops = N * 2.0 * 128 * hw * hw
     ach = build_bytes / (ms_build * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):      # dram__bytes_read+write of one `ncu --set full` capture of this kernel/workload
+        traffic = json.load(open(tp)).get("corr_build_tc_kernel", {}).get("dram_bytes_per_launch")
     roof = {"kernel": "corr_build_tc_kernel", "bound": "hbm", "achieved": ach,
-            "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+            "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic,
+            "algorithmic_bytes": build_bytes,
             "peak_source": pk["src"] + " (burst copy bandwidth)", "ms_per_launch": ms_build,
             "share_of_step": ms_build / ms_step,
             "tensor_tflops": build_flops / (ms_build * 1e-3) / 1e12,
