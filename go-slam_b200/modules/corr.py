@@ -156,11 +156,32 @@ class AltCorrBlock:
         return torch.cat(corr_list, dim=2)
 
     def __call__(self, coords, ii, jj):
-        squeeze_output = False
-        if len(coords.shape) == 5:
+        if len(coords.shape) == 5 and coords.is_cuda and self.pyramid[0].dtype == torch.float16:
+            return self._fused(coords, ii, jj)
+        squeeze_output = len(coords.shape) == 5
+        if squeeze_output:
             coords = coords.unsqueeze(dim=-2)
-            squeeze_output = True
         corr = self.corr_fn(coords, ii, jj)
         if squeeze_output:
             corr = corr.squeeze(dim=-1)
         return corr.contiguous()
+
+    def _fused(self, coords, ii, jj):
+        """one launch for all levels, feature maps indexed per edge on the device."""
+        B, N, H, W, _ = coords.shape
+        if B != 1:
+            raise RuntimeError("AltCorrBlock fused path expects batch 1 (as GO-SLAM uses it)")
+        C = self.pyramid[0].shape[-1]
+        dev = coords.device
+        rd = 2 * self.radius + 1
+        out = torch.empty((1, N, self.num_levels * rd * rd, H, W), dtype=torch.float32, device=dev)
+        pyr = [p.contiguous() for p in self.pyramid]
+        ii = torch.as_tensor(ii, device=dev).long().contiguous()
+        jj = torch.as_tensor(jj, device=dev).long().contiguous()
+        c = coords.reshape(N, H, W, 2).float().contiguous()
+        with torch.cuda.device(dev):
+            rc = _lib.load().goslam_altcorr_pyramid(_ptr_array(pyr), self.num_levels, _lib.ptr(c), _lib.ptr(ii),
+                                                    _lib.ptr(jj), _lib.ptr(out), N, H, W, C, int(self.radius),
+                                                    _lib.stream_ptr())
+        _lib.check(rc, "altcorr_pyramid")
+        return out

@@ -93,6 +93,15 @@ int goslam_altcorr_forward(const float* fmap1, const float* fmap2, const float* 
                            float* corr, int B, int S, int H, int W, int H2, int W2,
                            int C, int radius, void* stream);
 
+/* AltCorrBlock.__call__ in one launch (src/modules/corr.py:97-145, one coordinate set per edge):
+ *   pyramid[l] = [F, H>>l, W>>l, C] f16 NHWC, the reference's AltCorrBlock.pyramid (fmaps/4,
+ *   avg-pooled), shared by all edges; ii, jj [N] int64 index F (the reference passes rig*ii and
+ *   rig*jj + (ii==jj)); coords [N,H,W,2] f32 at level-0 resolution (scaled by 2^-l inside);
+ *   out [N, L*(2r+1)^2, H, W] f32, level-major, x-offset-major inside a level. */
+int goslam_altcorr_pyramid(const void* const* pyramid, int num_levels, const float* coords,
+                           const int64_t* ii, const int64_t* jj, float* out, int N, int H, int W,
+                           int C, int radius, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Geometry kernels of droid_backends (src/lib/droid.cpp:120-160,220-225).
  *   poses [num,7] f32 (tx,ty,tz,qx,qy,qz,qw); disps [num,ht,wd] f32; intrinsics [4]

@@ -155,6 +155,28 @@ def test_altcorr_forward():
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=1e-4)
 
 
+def test_altcorr_block_fused_matches_per_level_path():
+    """AltCorrBlock(fmaps)(coords, ii, jj): fused indexed half-precision launch == the reference-shaped
+    per-level path (gather + .float() + altcorr_forward) == the oracle."""
+    from goslam_b200.modules import AltCorrBlock
+    g = torch.Generator().manual_seed(8)
+    F, H, W, N = 6, 30, 40, 9
+    fm = torch.randn(1, F, 128, H, W, generator=g).half().to(dev())
+    blk = AltCorrBlock(fm)
+    ii = torch.randint(0, F, (N,), generator=g).to(dev())
+    jj = torch.randint(0, F, (N,), generator=g).to(dev())
+    base = torch.stack(torch.meshgrid(torch.arange(W).float(), torch.arange(H).float(), indexing="xy"), -1)
+    coords = (base[None, None].repeat(1, N, 1, 1, 1) + 3 * torch.randn(1, N, H, W, 2, generator=g)).to(dev())
+    fused = blk(coords, ii, jj)
+    slow = blk.corr_fn(coords.unsqueeze(-2), ii, jj).squeeze(-1).contiguous()
+    assert fused.shape == slow.shape == (1, N, 196, H, W)
+    assert (fused - slow).abs().max().item() < 1e-4 * max(1.0, slow.abs().max().item())
+    lvl = 2
+    ref = corr_oracle.altcorr_forward(blk.pyramid[0][0, ii].float().cpu().numpy(), blk.pyramid[lvl][0, jj].float().cpu().numpy(),
+                                      (coords[0] / 2 ** lvl).unsqueeze(1).cpu().numpy(), 3)
+    np.testing.assert_allclose(fused[0, :, 49 * lvl:49 * (lvl + 1)].cpu().numpy(), ref[:, 0], rtol=1e-4, atol=1e-4)
+
+
 # ------------------------------------------------------------------------------ geometry
 def _scene(num_kf=6, ht=12, wd=16, **kw):
     from goslam_b200 import synthetic
