@@ -46,14 +46,40 @@ def peaks():
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML (nvidia_ml_py) in a thread at
+    ~1 kHz (the timed region of the default run is ~10 ms), falling back to nvidia-smi polling."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.samples, self.stop = index, [], False
+        self.index, self.samples, self.stop, self.max_mhz = index, [], False, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        if self.nvml is not None:
+            nv = self.nvml
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self.stop:
+                try:
+                    mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    r = int(get_reasons(self.h))
+                    self.samples.append([mhz, self.max_mhz] + [("Active" if (r & m) else "Not Active") for m in bits.values()])
+                except Exception:
+                    pass
+                time.sleep(0.001)
+            return
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -63,7 +89,7 @@ class ClockSampler:
                     self.samples.append(f)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def __enter__(self):
         self.t.start()
@@ -78,9 +104,9 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(float(s[0]) for s in self.samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        reasons = [n for i, n in enumerate(names) if any(str(s[2 + i]).lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------ workload

@@ -10,6 +10,7 @@
 // feature vector is staged once per pixel in shared memory; a block covers 32 consecutive
 // pixels and writes the 49 channels with coalesced 128-byte rows.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -185,6 +186,148 @@ altcorr_pyramid_kernel(const AltPyrArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tensor-core AltCorrBlock: a WARP takes 16 consecutive source pixels and multiplies their
+// feature vectors (A, 16 x 128, registers) with every target pixel inside the bounding box of
+// their 8x8 windows (B, streamed straight from L2 as mma fragments), 8 targets per
+// mma.sync.m16n8k16 column tile.  For a smooth flow field the box is ~25 x 10 targets, i.e. ~3x
+// redundant MACs on the tensor pipe instead of 64 x 128 scalar FMAs per pixel, and each target
+// row is fetched once per 16 pixels instead of once per pixel.  Inputs are half (exact products),
+// accumulation is fp32: the same numbers as the fp32 kernel up to summation order.
+// The logical K order of the MMA is a fixed permutation of the channels (identical for A and
+// B) chosen so that every fragment load is one 128-bit vector.
+// ---------------------------------------------------------------------------------------
+constexpr int kTcWarps = 4;
+constexpr int kTcPix = 16 * kTcWarps;      // 64 source pixels per block
+
+__device__ __forceinline__ void mma16816_f32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2,
+                                             unsigned a3, unsigned b0, unsigned b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int R>
+__global__ void __launch_bounds__(kTcWarps * 32)
+altcorr_tc_kernel(const AltPyrArgs a) {
+  constexpr int RD = 2 * R + 1;
+  static_assert(RD == 7, "8x8 tap windows");
+  __shared__ float taps[kTcWarps][16 * 64];
+  __shared__ float frac[kTcWarps][16][2];
+  __shared__ float stage[RD * RD][kTcPix + 1];
+  const int e = blockIdx.y, lvl = blockIdx.z;
+  const int k0 = blockIdx.x * kTcPix;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int HW = a.H * a.W;
+  const int H2 = a.Hl[lvl], W2 = a.Wl[lvl];
+  const __half* f1b = a.pyr[0] + (size_t)a.ii[e] * HW * 128;
+  const __half* f2b = a.pyr[lvl] + (size_t)a.jj[e] * H2 * W2 * 128;
+  const float sc = a.inv_scale[lvl];
+  const int kw = k0 + warp * 16;                   // first pixel of this warp
+
+  // ---- window origin of pixel (lane & 15) ----
+  const int pk = kw + (lane & 15);
+  const bool pvalid = pk < HW;
+  int fxi = 0, fyi = 0;
+  {
+    float cx = 0.f, cy = 0.f;
+    if (pvalid) {
+      const float2 xy = *reinterpret_cast<const float2*>(a.coords + ((size_t)e * HW + pk) * 2);
+      cx = xy.x * sc; cy = xy.y * sc;
+    }
+    const float fx0 = floorf(cx), fy0 = floorf(cy);
+    fxi = (int)fx0; fyi = (int)fy0;
+    if (lane < 16) { frac[warp][lane][0] = cx - fx0; frac[warp][lane][1] = cy - fy0; }
+  }
+  // bounding box of all taps of the valid pixels, clipped to the target image
+  const int big = 1 << 28;
+  // clamp far-out windows so the box arithmetic cannot overflow; they contribute nothing anyway
+  const int cfx = max(-big, min(big, fxi)), cfy = max(-big, min(big, fyi));
+  int bx0 = __reduce_min_sync(0xffffffffu, pvalid ? cfx - R : big);
+  int bx1 = __reduce_max_sync(0xffffffffu, pvalid ? cfx + R + 1 : -big);
+  int by0 = __reduce_min_sync(0xffffffffu, pvalid ? cfy - R : big);
+  int by1 = __reduce_max_sync(0xffffffffu, pvalid ? cfy + R + 1 : -big);
+  bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, W2 - 1); by1 = min(by1, H2 - 1);
+  const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
+  const int nt = (bw > 0 && bh > 0) ? bw * bh : 0;
+  // window origins of the two rows (pixels g and g+8) whose accumulators this lane holds
+  const int ox_lo = __shfl_sync(0xffffffffu, fxi, g) - R, oy_lo = __shfl_sync(0xffffffffu, fyi, g) - R;
+  const int ox_hi = __shfl_sync(0xffffffffu, fxi, g + 8) - R, oy_hi = __shfl_sync(0xffffffffu, fyi, g + 8) - R;
+  const bool v_lo = (kw + g) < HW, v_hi = (kw + g + 8) < HW;
+
+  for (int i = lane; i < 16 * 64; i += 32) taps[warp][i] = 0.f;
+
+  // ---- A fragments: pixels g and g+8, all 128 channels (4 k-pairs x one 128-bit vector each) ----
+  uint4 Alo[4], Ahi[4];
+#pragma unroll
+  for (int kp = 0; kp < 4; ++kp) {
+    Alo[kp] = v_lo ? __ldg(reinterpret_cast<const uint4*>(f1b + (size_t)(kw + g) * 128 + kp * 32 + t4 * 8))
+                   : make_uint4(0, 0, 0, 0);
+    Ahi[kp] = v_hi ? __ldg(reinterpret_cast<const uint4*>(f1b + (size_t)(kw + g + 8) * 128 + kp * 32 + t4 * 8))
+                   : make_uint4(0, 0, 0, 0);
+  }
+  __syncwarp();
+
+  // ---- stream the box, 8 targets per column tile ----
+  for (int c0 = 0; c0 < nt; c0 += 8) {
+    const int tb = c0 + g;                         // the target whose row this lane loads (B: n = g)
+    uint4 Bv[4];
+    if (tb < nt) {
+      const int ty = by0 + tb / bw, tx = bx0 + tb % bw;
+      const uint4* rowp = reinterpret_cast<const uint4*>(f2b + ((size_t)ty * W2 + tx) * 128 + t4 * 8);
+#pragma unroll
+      for (int kp = 0; kp < 4; ++kp) Bv[kp] = __ldg(rowp + kp * 4);
+    } else {
+#pragma unroll
+      for (int kp = 0; kp < 4; ++kp) Bv[kp] = make_uint4(0, 0, 0, 0);
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {
+      // k-step 2kp: halves 0..3 of each vector; k-step 2kp+1: halves 4..7
+      mma16816_f32(acc, Alo[kp].x, Ahi[kp].x, Alo[kp].y, Ahi[kp].y, Bv[kp].x, Bv[kp].y);
+      mma16816_f32(acc, Alo[kp].z, Ahi[kp].z, Alo[kp].w, Ahi[kp].w, Bv[kp].z, Bv[kp].w);
+    }
+    // scatter the 16x8 tile into the per-pixel 8x8 tap arrays
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int tc = c0 + 2 * t4 + j;
+      if (tc < nt) {
+        const int ty = by0 + tc / bw, tx = bx0 + tc % bw;
+        int iy = ty - oy_lo, ix = tx - ox_lo;
+        if (v_lo && (unsigned)iy < 8u && (unsigned)ix < 8u) taps[warp][g * 64 + iy * 8 + ix] = acc[j];
+        iy = ty - oy_hi; ix = tx - ox_hi;
+        if (v_hi && (unsigned)iy < 8u && (unsigned)ix < 8u) taps[warp][(g + 8) * 64 + iy * 8 + ix] = acc[2 + j];
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- bilinear blend of the tap arrays (x-offset-major channels) ----
+  for (int idx = lane; idx < 16 * RD * RD; idx += 32) {
+    const int p = idx / (RD * RD), o = idx % (RD * RD);
+    const int ox = o / RD, oy = o % RD;
+    const float dx = frac[warp][p][0], dy = frac[warp][p][1];
+    const float* tw = taps[warp] + p * 64;
+    float v = tw[oy * 8 + ox] * ((1 - dy) * (1 - dx));
+    v += tw[oy * 8 + ox + 1] * ((1 - dy) * dx);
+    v += tw[(oy + 1) * 8 + ox] * (dy * (1 - dx));
+    v += tw[(oy + 1) * 8 + ox + 1] * (dy * dx);
+    stage[o][warp * 16 + p] = v;
+  }
+  __syncthreads();
+  const int npx = min(kTcPix, HW - k0);
+  float* outp = a.out + (((size_t)e * a.L + lvl) * RD * RD) * HW + k0;
+  for (int idx = threadIdx.x; idx < RD * RD * kTcPix; idx += kTcWarps * 32) {
+    const int c = idx / kTcPix, p = idx % kTcPix;
+    if (p < npx) outp[(size_t)c * HW + p] = stage[c][p];
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -234,8 +377,14 @@ int goslam_altcorr_pyramid(const void* const* pyramid, int num_levels, const flo
     cudaFuncSetAttribute(altcorr_pyramid_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  dim3 grid(gs_cdiv(H * W, kPixPerBlock), N, num_levels);
-  altcorr_pyramid_kernel<3><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(a);
+  static const bool force_simt = [] { const char* e = getenv("GOSLAM_ALTCORR_SIMT"); return e && e[0] == '1'; }();
+  if (C == 128 && !force_simt) {                   // tensor-core path (the model's feature width)
+    dim3 grid(gs_cdiv(H * W, kTcPix), N, num_levels);
+    altcorr_tc_kernel<3><<<grid, kTcWarps * 32, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    dim3 grid(gs_cdiv(H * W, kPixPerBlock), N, num_levels);
+    altcorr_pyramid_kernel<3><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(a);
+  }
   GS_CHECK_LAUNCH();
   return GOSLAM_OK;
 }
