@@ -150,15 +150,45 @@ class Window:
         d["disps"].clamp_(min=0.001)            # src/depth_video.py:269
         return feat
 
+    E2E_KEYS = ("fmaps", "poses", "disps", "disps_sens", "intrinsics", "targets", "weights", "eta", "ii", "jj")
+
     def step_e2e(self, out_pinned):
-        h, d = self.host, self.d
-        for k in ("fmaps", "poses", "disps", "disps_sens", "intrinsics", "targets", "weights", "eta", "ii", "jj"):
-            d[k].copy_(h[k], non_blocking=True)
-        self.poses0.copy_(d["poses"])
-        self.disps0.copy_(d["disps"])
+        """one update through the public API from pinned HOST buffers: H2D of every input of the
+        step, the step, D2H of the updated state.  Copies run on a side stream into the other half
+        of a double buffer, so the transfer of update i+1 overlaps the kernels of update i (each
+        step still waits for ITS inputs and its result is read back)."""
+        if not hasattr(self, "_e2e"):
+            self._e2e = dict(copy=torch.cuda.Stream(self.dev), bufs=[None, None], ready=[None, None],
+                             done=[None, None], parity=0)
+            for b in range(2):
+                self._e2e["bufs"][b] = {k: torch.empty_like(self.d[k]) for k in self.E2E_KEYS}
+        st = self._e2e
+        cur = st["parity"]
+        main = torch.cuda.current_stream(self.dev)
+        if st["ready"][cur] is None:                      # first call: nothing prefetched yet
+            self._prefetch(cur)
+        main.wait_event(st["ready"][cur])
+        for k in self.E2E_KEYS:
+            self.d[k] = st["bufs"][cur][k]
+        self.poses0.copy_(self.d["poses"])
+        self.disps0.copy_(self.d["disps"])
+        self._prefetch(cur ^ 1)                           # next update's inputs, overlapped
         self.step()
-        out_pinned[0].copy_(d["poses"], non_blocking=True)
-        out_pinned[1].copy_(d["disps"], non_blocking=True)
+        out_pinned[0].copy_(self.d["poses"], non_blocking=True)
+        out_pinned[1].copy_(self.d["disps"], non_blocking=True)
+        st["done"][cur] = torch.cuda.Event()
+        st["done"][cur].record(main)
+        st["parity"] = cur ^ 1
+
+    def _prefetch(self, b):
+        st = self._e2e
+        with torch.cuda.stream(st["copy"]):
+            if st["done"][b] is not None:                 # buffer b must not be in use by an older step
+                st["copy"].wait_event(st["done"][b])
+            for k in self.E2E_KEYS:
+                st["bufs"][b][k].copy_(self.host[k], non_blocking=True)
+            st["ready"][b] = torch.cuda.Event()
+            st["ready"][b].record(st["copy"])
 
     def h2d_bytes(self):
         return sum(self.host[k].numel() * self.host[k].element_size() for k in

@@ -26,6 +26,7 @@
 // damping diag += ep + lm*diag (:1197); failed factorisation => dx = 0 (:1207-1210).
 #include "common.cuh"
 #include "se3.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -179,21 +180,26 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
 // ------------------------------------------------------------------------------------
 // Linearise: grid (ntiles, num); block = kTP pixels of slot blockIdx.y.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTP)
-ba_linearize_kernel(const float* __restrict__ poses, const float* __restrict__ disps,
-                    const float* __restrict__ intr, const float* __restrict__ disps_sens,
-                    const float* __restrict__ targets, const float* __restrict__ weights,
-                    const float* __restrict__ eta, int eta_rows,
-                    const int64_t* __restrict__ ii, const int64_t* __restrict__ jj,
-                    BaDims d, BaWs ws, int motion_only) {
-  const int k = blockIdx.y;
-  if (k >= ws.counts[0]) return;
+struct BaIn {
+  const float* poses; const float* disps; const float* intr; const float* disps_sens;
+  const float* targets; const float* weights; const float* eta; int eta_rows;
+  const int64_t* ii; const int64_t* jj;
+};
+
+// One (frame slot k, kTP-pixel tile) unit; blockDim.x == kTP.  poses / disps are deliberately
+// NOT __restrict__: the single-kernel path below rewrites them between iterations.
+__device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, const BaWs& ws,
+                                               int motion_only, int k, int tile,
+                                               float (*red)[32]) {
+  const float* poses = in.poses; const float* disps = in.disps;
+  const float* __restrict__ intr = in.intr; const float* __restrict__ disps_sens = in.disps_sens;
+  const float* __restrict__ targets = in.targets; const float* __restrict__ weights = in.weights;
+  const float* __restrict__ eta = in.eta; const int eta_rows = in.eta_rows;
+  const int64_t* __restrict__ jj = in.jj;
   const int f = ws.kx[k];
-  const int tile = blockIdx.x;
   const int px = tile * kTP + threadIdx.x;
   const bool act = px < d.hw;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __shared__ float red[kTP / 32][32];
 
   const float fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3];
   const float u = (float)(px % d.wd), v = (float)(px / d.wd);
@@ -301,6 +307,13 @@ ba_linearize_kernel(const float* __restrict__ poses, const float* __restrict__ d
   }
 }
 
+__global__ void __launch_bounds__(kTP)
+ba_linearize_kernel(BaIn in, BaDims d, BaWs ws, int motion_only) {
+  __shared__ float red[kTP / 32][32];
+  if ((int)blockIdx.y >= ws.counts[0]) return;
+  linearize_tile(in, d, ws, motion_only, blockIdx.y, blockIdx.x, red);
+}
+
 // ------------------------------------------------------------------------------------
 // Reduced camera system accumulation (persistent blocks):
 //   items [0, N)            pose blocks of edge e from its H_jj/v_j partials (A, :1376-1383)
@@ -308,11 +321,19 @@ ba_linearize_kernel(const float* __restrict__ poses, const float* __restrict__ d
 //                           and for a == b also v_a = sum_px E_a Q w   (:1001-1093,:1257-1311)
 // sys = (A - S | b_A - b_S) in float64.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-ba_system_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ii,
-                 const int64_t* __restrict__ jj, BaDims d, BaWs ws, int motion_only) {
-  __shared__ float red[8][64];
-  __shared__ double Hs[36], Ms[36], Ts[36], vs[6];
+struct SysSmem {
+  float red[8][64];
+  double Hs[36], Ms[36], Ts[36], vs[6];
+};
+
+// items first, first + stride, ... ; NT threads per block (poses not __restrict__, see above)
+template <int NT>
+__device__ __forceinline__ void system_items(const float* poses, const int64_t* __restrict__ ii,
+                                             const int64_t* __restrict__ jj, const BaDims& d,
+                                             const BaWs& ws, int motion_only, int first, int stride,
+                                             SysSmem& sm) {
+  float (*red)[64] = sm.red;
+  double* Hs = sm.Hs; double* Ms = sm.Ms; double* Ts = sm.Ts; double* vs = sm.vs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = ws.counts[0];
   const int npairs = motion_only ? 0 : ws.counts[2];
@@ -322,7 +343,7 @@ ba_system_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ii
   double* H = ws.sys;
   double* bvec = ws.sys + (size_t)d.n * d.n;
 
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+  for (int item = first; item < nitems; item += stride) {
     if (item < d.N) {
       // ---------------- pose blocks of one edge ----------------
       const int e = item;
@@ -415,7 +436,7 @@ ba_system_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ii
       float acc[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-      for (int px = px0 + tid; px < px1; px += 256) {
+      for (int px = px0 + tid; px < px1; px += NT) {
         const float qv = Qk[px];
         float ea[6], eb[6];
 #pragma unroll
@@ -442,7 +463,7 @@ ba_system_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ii
       if (tid < 42) {
         double s = 0.0;
 #pragma unroll
-        for (int wq = 0; wq < 8; ++wq) s += (double)red[wq][tid];
+        for (int wq = 0; wq < NT / 32; ++wq) s += (double)red[wq][tid];
         if (tid < 36) {
           const int r = tid / 6, c = tid % 6;
           atomicAdd(&H[(size_t)(6 * pa + r) * d.n + 6 * pb + c], -s);
@@ -454,6 +475,13 @@ ba_system_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ii
       __syncthreads();
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+ba_system_kernel(const float* poses, const int64_t* __restrict__ ii,
+                 const int64_t* __restrict__ jj, BaDims d, BaWs ws, int motion_only) {
+  __shared__ SysSmem sm;
+  system_items<256>(poses, ii, jj, d, ws, motion_only, blockIdx.x, gridDim.x, sm);
 }
 
 // ------------------------------------------------------------------------------------
@@ -487,13 +515,19 @@ __device__ __forceinline__ void retract_poses(float* poses, const BaDims& d, con
 // pose blocks, matrix in shared memory, 128 threads, 3 barriers per block column (a local
 // window of 8 keyframes is 7 block columns).  The 6x6 diagonal factor is computed redundantly in
 // registers; one rsqrt per column and no divisions.  Blocked forward/backward substitution.
-__global__ void __launch_bounds__(128)
-ba_solve_warp_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __restrict__ sys_in,
-                     float lm, float ep, float* __restrict__ dx_out, int* __restrict__ status_out) {
-  extern __shared__ double smd[];
-  __shared__ double Ld[6][6];       // factor of the current diagonal block (diag = 1/l_kk)
-  __shared__ double xs[6];
-  __shared__ int failed;
+struct SolveSmem {
+  double Ld[6][6];       // factor of the current diagonal block (diag = 1/l_kk)
+  double xs[6];
+  int failed;
+};
+
+// 128 threads; smd = (n*n + 2n) doubles of shared memory
+__device__ __forceinline__ void solve_small(float* poses, const BaDims& d, const BaWs& ws,
+                                            const double* sys_in, float lm, float ep, float* dx_out,
+                                            int* status_out, double* smd, SolveSmem& ss) {
+  double (*Ld)[6] = ss.Ld;
+  double* xs = ss.xs;
+  int& failed = ss.failed;
   const int n = d.n, P = d.P, tid = threadIdx.x, lane = tid & 31;
   double* __restrict__ A = smd;                       // lower triangle is used
   double* __restrict__ y = smd + (size_t)n * n;
@@ -599,25 +633,27 @@ ba_solve_warp_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double*
       }
       __syncthreads();
     }
-    // backward: L^T x = z
+    // backward: L^T x = z, right-looking (solved block is pushed into the rows above it)
     for (int jb = P - 1; jb >= 0; --jb) {
       const int j0 = 6 * jb;
-      if (tid < 6) {                                   // s_k = sum_{i below} L[i][j0+k] x[i]
-        double sacc = 0.0;
-        for (int i = j0 + 6; i < n; ++i) sacc += A[i * n + j0 + tid] * y[i];
-        xs[tid] = y[j0 + tid] - sacc;
-      }
-      __syncthreads();
       if (tid == 0) {
         double x[6];
 #pragma unroll
         for (int k = 5; k >= 0; --k) {
-          double v = xs[k];
+          double v = y[j0 + k];
 #pragma unroll
           for (int mm = k + 1; mm < 6; ++mm) v -= A[(j0 + mm) * n + j0 + k] * x[mm];
           x[k] = v * invd[j0 + k];
           y[j0 + k] = x[k];
+          xs[k] = x[k];
         }
+      }
+      __syncthreads();
+      for (int i = tid; i < j0; i += 128) {
+        double v = y[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v -= A[(j0 + k) * n + i] * xs[k];
+        y[i] = v;
       }
       __syncthreads();
     }
@@ -632,6 +668,14 @@ ba_solve_warp_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double*
   solve_finish(poses, d, ws, y, fail, dx_out, status_out, tid, 128);
   __syncthreads();
   retract_poses(poses, d, ws, tid, 128);
+}
+
+__global__ void __launch_bounds__(128)
+ba_solve_warp_kernel(float* poses, BaDims d, BaWs ws, const double* sys_in, float lm, float ep,
+                     float* dx_out, int* status_out) {
+  extern __shared__ double smd[];
+  __shared__ SolveSmem ss;
+  solve_small(poses, d, ws, sys_in, lm, ep, dx_out, status_out, smd, ss);
 }
 
 // General case: one block; A in shared memory when it fits, else in the global scratch.
@@ -703,14 +747,12 @@ ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __re
 // Depth back-substitution + retraction: dz = Q (w - sum_a E_a^T dx[pose_a]), disps += dz.
 // (EvT6x1 + accum + disp_retr, :1095-1115,:1417,:933-946)
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTP)
-ba_backsub_kernel(float* __restrict__ disps, BaDims d, BaWs ws,
-                  int owner_lo, int owner_hi, float* __restrict__ dz_out) {
-  const int k = blockIdx.y;
-  if (k >= ws.counts[0]) return;
+__device__ __forceinline__ void backsub_tile(float* disps, const BaDims& d, const BaWs& ws,
+                                             int owner_lo, int owner_hi, float* dz_out, int k,
+                                             int tile) {
   const int f = ws.kx[k];
   if (f < owner_lo || f >= owner_hi) return;
-  const int px = blockIdx.x * kTP + threadIdx.x;
+  const int px = tile * kTP + threadIdx.x;
   if (px >= d.hw) return;
   float acc = 0.f;
   // own pose entry E_i: pose index f - t0, skipped when <= 0 (reference quirk) or >= P
@@ -738,6 +780,70 @@ ba_backsub_kernel(float* __restrict__ disps, BaDims d, BaWs ws,
   if (dz_out) dz_out[(size_t)f * d.hw + px] = dz;
 }
 
+__global__ void __launch_bounds__(kTP)
+ba_backsub_kernel(float* disps, BaDims d, BaWs ws, int owner_lo, int owner_hi, float* dz_out) {
+  if ((int)blockIdx.y >= ws.counts[0]) return;
+  backsub_tile(disps, d, ws, owner_lo, owner_hi, dz_out, blockIdx.y, blockIdx.x);
+}
+
+// ------------------------------------------------------------------------------------
+// Small windows: ALL Gauss-Newton iterations of one call in ONE cooperative kernel.  The phases
+// are separated by grid barriers instead of kernel boundaries, and the depth back-substitution
+// of iteration i runs fused with the linearisation of iteration i+1 (same pixel, same thread).
+// 3 grid barriers per iteration replace 5 launches.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+  __syncthreads();
+  ++epoch;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned target = epoch * gridDim.x;
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTP)
+ba_persistent_kernel(float* poses, float* disps, BaIn in, BaDims d, BaWs ws, int iterations, float lm,
+                     float ep, int motion_only, float* dx_out, float* dz_out, int* status_out,
+                     unsigned* barrier) {
+  extern __shared__ double smd[];
+  __shared__ float red[kTP / 32][32];
+  __shared__ SysSmem sys_sm;
+  __shared__ SolveSmem solve_sm;
+  unsigned epoch = 0;
+  const int M = ws.counts[0];
+  const int units = M * ws.ntiles;
+  const size_t nsys = (size_t)d.n * d.n + d.n;
+  for (int it = 0; it < iterations; ++it) {
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int k = u / ws.ntiles, tile = u - k * ws.ntiles;
+      if (it > 0 && !motion_only) backsub_tile(disps, d, ws, 0, d.num, dz_out, k, tile);
+      linearize_tile(in, d, ws, motion_only, k, tile, red);
+    }
+    grid_barrier(barrier, epoch);
+    system_items<kTP>(poses, in.ii, in.jj, d, ws, motion_only, blockIdx.x, gridDim.x, sys_sm);
+    grid_barrier(barrier, epoch);
+    if (blockIdx.x == 0) {
+      solve_small(poses, d, ws, ws.sys, lm, ep, dx_out, status_out ? status_out + it : nullptr, smd,
+                  solve_sm);
+      __syncthreads();
+      for (size_t i = threadIdx.x; i < nsys; i += kTP) ws.sys[i] = 0.0;   // for the next iteration
+    }
+    grid_barrier(barrier, epoch);
+  }
+  if (!motion_only)
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int k = u / ws.ntiles, tile = u - k * ws.ntiles;
+      backsub_tile(disps, d, ws, 0, d.num, dz_out, k, tile);
+    }
+}
+
 bool make_dims(int N, int num, int ht, int wd, int t0, int t1, BaDims* d) {
   if (N < 0 || num <= 0 || num > 4096 || ht <= 0 || wd <= 0) return false;
   d->N = N; d->num = num; d->ht = ht; d->wd = wd; d->hw = ht * wd;
@@ -753,6 +859,7 @@ int launch_phase1(const float* poses, const float* disps, const float* intr,
                   const float* disps_sens, const float* targets, const float* weights,
                   const float* eta, int eta_rows, const int64_t* ii, const int64_t* jj,
                   const BaDims& d, const BaWs& ws, int motion_only, bool prep, cudaStream_t st) {
+  const BaIn in{poses, disps, intr, disps_sens, targets, weights, eta, eta_rows, ii, jj};
   if (prep) {
     ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws);
     GS_CHECK_LAUNCH();
@@ -760,13 +867,11 @@ int launch_phase1(const float* poses, const float* disps, const float* intr,
   cudaMemsetAsync(ws.sys, 0, ((size_t)d.n * d.n + d.n) * sizeof(double), st);
   if (d.N > 0) {
     dim3 grid(ws.ntiles, d.num);
-    ba_linearize_kernel<<<grid, kTP, 0, st>>>(poses, disps, intr, disps_sens, targets, weights,
-                                              eta, eta_rows, ii, jj, d, ws, motion_only);
+    ba_linearize_kernel<<<grid, kTP, 0, st>>>(in, d, ws, motion_only);
     GS_CHECK_LAUNCH();
   } else if (!motion_only) {
     dim3 grid(ws.ntiles, d.num);   // still need Q / w / Ei (= prior only) for every slot
-    ba_linearize_kernel<<<grid, kTP, 0, st>>>(poses, disps, intr, disps_sens, targets, weights,
-                                              eta, eta_rows, ii, jj, d, ws, motion_only);
+    ba_linearize_kernel<<<grid, kTP, 0, st>>>(in, d, ws, motion_only);
     GS_CHECK_LAUNCH();
   }
   ba_system_kernel<<<148 * 4, 256, 0, st>>>(poses, ii, jj, d, ws, motion_only);
@@ -835,6 +940,41 @@ int goslam_ba(float* poses, float* disps, const float* intrinsics, const float* 
   if (workspace == nullptr || need > workspace_bytes) return GOSLAM_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   if (dz_out) cudaMemsetAsync(dz_out, 0, (size_t)num * d.hw * sizeof(float), st);
+  static const bool multi_kernel = [] {
+    const char* e = getenv("GOSLAM_BA_MULTIKERNEL");
+    return e && e[0] == '1';
+  }();
+  if (d.n <= kWarpSolveMaxN && !multi_kernel) {
+    static int blocks_per_sm = -1, sms = 0;
+    const size_t smem = ((size_t)kWarpSolveMaxN * kWarpSolveMaxN + 2 * kWarpSolveMaxN) * sizeof(double);
+    if (blocks_per_sm < 0) {
+      int dev = 0, occ = 0, coop = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      cudaFuncSetAttribute(ba_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ba_persistent_kernel, kTP, smem);
+      int want = 2;
+      if (const char* e = getenv("GOSLAM_BA_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
+      blocks_per_sm = (!coop || occ < 1) ? 0 : (occ > want ? want : occ);
+    }
+    if (blocks_per_sm > 0) {
+      ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws);
+      GS_CHECK_LAUNCH();
+      unsigned* barrier = reinterpret_cast<unsigned*>(ws.counts + 3);
+      cudaMemsetAsync(barrier, 0, sizeof(unsigned), st);
+      cudaMemsetAsync(ws.sys, 0, ((size_t)d.n * d.n + d.n) * sizeof(double), st);
+      BaIn in{poses, disps, intrinsics, disps_sens, targets, weights, eta, eta_rows, ii, jj};
+      BaDims dd = d;
+      BaWs wsv = ws;
+      void* args[] = {&poses, &disps, &in, &dd, &wsv, &iterations, &lm, &ep, &motion_only,
+                      &dx_out, &dz_out, &status_out, &barrier};
+      if (cudaLaunchCooperativeKernel((const void*)ba_persistent_kernel, dim3(sms * blocks_per_sm),
+                                      dim3(kTP), args, smem, st) != cudaSuccess)
+        return GOSLAM_ELAUNCH;
+      return GOSLAM_OK;
+    }
+  }
   for (int it = 0; it < iterations; ++it) {
     int rc = launch_phase1(poses, disps, intrinsics, disps_sens, targets, weights, eta, eta_rows,
                            ii, jj, d, ws, motion_only, it == 0, st);
