@@ -159,6 +159,7 @@ struct TcParams {
   // optional edge -> feature-map-slot indirection (video-level K-major feature maps):
   // slot1 = rig*ii[e], slot2 = rig*jj[e] + (ii[e]==jj[e])   (src/factor_graph.py:108-113,290)
   const int64_t* ii; const int64_t* jj; int rig;
+  const int* out_slot;        // optional edge -> output slot of the level buffers (CorrPool)
   int aligned;                // w % 16 == 0 && h % 8 == 0: every store is a whole aligned sector run
   int experiment;             // profiling only: 1 = no output writes
 };
@@ -333,7 +334,8 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
       const int n = item / (p.n_yb * p.n_mt);
       const int src = mt * kBM + row;
       const bool src_ok = src < p.hw && wr;
-      const long long plane_id = (long long)n * p.hw + src;
+      const int n_out = p.out_slot ? __ldg(p.out_slot + n) : n;
+      const long long plane_id = (long long)n_out * p.hw + src;
       const int y0 = yb * kPY;
       for (int xb = 0; xb < p.n_xb; ++xb, ++tile) {
         if ((tile & (kTStages - 1)) != ts) continue;
@@ -385,7 +387,7 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
         const int s_loc = etid >> 2, part = etid & 3;          // four threads per source pixel
         const int s_glb = mt * kBM + s_loc;
         if (s_glb < p.hw) {
-          const long long pl = (long long)n * p.hw + s_glb;
+          const long long pl = (long long)n_out * p.hw + s_glb;
           const unsigned char* sp1 = pool1 + s_loc * p1src;
           const unsigned char* sp2 = pool2 + s_loc * p2src;
           if (p.aligned) {
@@ -500,8 +502,8 @@ EncodeTiledFn get_encode_fn() {
 
 // launch the tensor-core kernel on K-major (pre-scaled) operands: f1t/f2t = [F1|F2, hw, 128]
 int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_t* ii,
-              const int64_t* jj, int rig, __half* const* levels, int num_levels, int N, int h, int w,
-              cudaStream_t st) {
+              const int64_t* jj, int rig, const int* out_slot, __half* const* levels, int num_levels,
+              int N, int h, int w, cudaStream_t st) {
   const int hw = h * w;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return GOSLAM_ELAUNCH;
@@ -531,7 +533,7 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
   p.num_levels = num_levels; p.N = N; p.h = h; p.w = w; p.hw = hw;
   p.n_mt = gs_cdiv(hw, kBM); p.n_yb = gs_cdiv(h, kPY); p.n_xb = gs_cdiv(w, kPX);
   p.n_items = N * p.n_mt * p.n_yb;
-  p.ii = ii; p.jj = jj; p.rig = rig;
+  p.ii = ii; p.jj = jj; p.rig = rig; p.out_slot = out_slot;
   p.aligned = (w % 16 == 0 && h % 8 == 0) ? 1 : 0;
   { const char* e = getenv("GOSLAM_TC_EXPERIMENT"); p.experiment = e ? atoi(e) : 0; }
   static bool attr = false;
@@ -564,7 +566,7 @@ int build_tc(const __half* f1, const __half* f2, __half* const* levels, int num_
   to_kmajor_kernel<<<tg, 256, 0, st>>>(f1, f1t, hw);
   to_kmajor_kernel<<<tg, 256, 0, st>>>(f2, f2t, hw);
   GS_CHECK_LAUNCH();
-  return launch_tc(f1t, N, f2t, N, nullptr, nullptr, 1, levels, num_levels, N, h, w, st);
+  return launch_tc(f1t, N, f2t, N, nullptr, nullptr, 1, nullptr, levels, num_levels, N, h, w, st);
 }
 
 }  // namespace
@@ -589,14 +591,21 @@ int goslam_fmaps_to_kmajor(const void* fmaps, void* out, int F, int D, int h, in
 int goslam_corr_build_indexed(const void* fmaps_kmajor, int F, int rig, const int64_t* ii,
                               const int64_t* jj, void* const* levels, int num_levels, int N, int D,
                               int h, int w, void* stream) {
+  return goslam_corr_pool_build(fmaps_kmajor, F, rig, ii, jj, nullptr, levels, num_levels, N, D, h, w,
+                                stream);
+}
+
+int goslam_corr_pool_build(const void* fmaps_kmajor, int F, int rig, const int64_t* ii,
+                           const int64_t* jj, const int* slots, void* const* levels, int num_levels,
+                           int N, int D, int h, int w, void* stream) {
   if (N < 0 || F <= 0 || rig < 1 || D != kD || h <= 0 || w <= 0 || num_levels < 1 || num_levels > 4)
     return GOSLAM_EINVAL;
   if ((h >> (num_levels - 1)) <= 0 || (w >> (num_levels - 1)) <= 0) return GOSLAM_EINVAL;
   if (w > kMaxXB * kPX) return GOSLAM_EINVAL;
   if (N == 0) return GOSLAM_OK;
   const __half* f = reinterpret_cast<const __half*>(fmaps_kmajor);
-  return launch_tc(f, F, f, F, ii, jj, rig, reinterpret_cast<__half* const*>(levels), num_levels, N, h,
-                   w, (cudaStream_t)stream);
+  return launch_tc(f, F, f, F, ii, jj, rig, slots, reinterpret_cast<__half* const*>(levels), num_levels,
+                   N, h, w, (cudaStream_t)stream);
 }
 
 int goslam_corr_build(const void* fmap1, const void* fmap2, void* const* levels, int num_levels,

@@ -37,6 +37,8 @@ struct LookupArgs {
   int interleaved;
   void* out;             // [N, num_levels*rd*rd, h1*w1]
   int N, hw1, radius;
+  const int* slot;       // optional edge -> volume slot table (CorrPool); nullptr = identity
+  int cap;               // slots in the volume allocation (N when slot == nullptr)
 };
 
 // ---- row fetch: 8 consecutive elements starting at absolute element index e0 ----------
@@ -192,6 +194,7 @@ corr_lookup_kernel(const LookupArgs a) {
   __shared__ __align__(16) T stage[CH * LD];
 
   const int n = blockIdx.y;
+  const int nv = a.slot ? __ldg(a.slot + n) : n;      // where this edge's volume lives
   const int k0 = blockIdx.x * kTile;
   const int lane8 = threadIdx.x & 7;          // window row
   const int pslot = threadIdx.x >> 3;         // 0..31 pixel slot within a pass
@@ -218,13 +221,13 @@ corr_lookup_kernel(const LookupArgs a) {
   for (int lvl = 0; lvl < a.num_levels; ++lvl) {
     const int h2 = a.h2[lvl], w2 = a.w2[lvl];
     const long long plane = (long long)h2 * w2;
-    const long long total = (long long)a.N * a.hw1 * plane;
+    const long long total = (long long)a.cap * a.hw1 * plane;
     const T* vol = reinterpret_cast<const T*>(a.vol[lvl]);
     const float sc = a.inv_scale[lvl];
 #pragma unroll
     for (int ps = 0; ps < 2; ++ps) {
       const int k = k0 + ps * 32 + pslot;
-      const long long pbase = ((long long)n * a.hw1 + k) * plane;
+      const long long pbase = ((long long)nv * a.hw1 + k) * plane;
       if constexpr (sizeof(T) == 2) {
         lookup_pass_h<R>(reinterpret_cast<const __half*>(vol), total, pbase, h2, w2, cx[ps] * sc,
                          cy[ps] * sc, lane8, act[ps], reinterpret_cast<__half*>(stage), LD,
@@ -268,7 +271,7 @@ int goslam_corr_index_forward(const void* volume, int dtype, const float* coords
   LookupArgs a{};
   a.vol[0] = volume; a.h2[0] = h2; a.w2[0] = w2; a.inv_scale[0] = 1.0f;
   a.num_levels = 1; a.coords = coords; a.interleaved = 0; a.out = corr;
-  a.N = N; a.hw1 = h1 * w1; a.radius = radius;
+  a.N = N; a.hw1 = h1 * w1; a.radius = radius; a.slot = nullptr; a.cap = N;
   if (dtype == GOSLAM_F16) return launch_lookup<__half>(a, (cudaStream_t)stream);
   if (dtype == GOSLAM_F32) return launch_lookup<float>(a, (cudaStream_t)stream);
   return GOSLAM_EINVAL;
@@ -277,7 +280,14 @@ int goslam_corr_index_forward(const void* volume, int dtype, const float* coords
 int goslam_corr_pyramid_lookup(const void* const* pyramid, int dtype, int num_levels,
                                const float* coords_hw2, void* out, int N, int h1, int w1, int h2,
                                int w2, int radius, void* stream) {
-  if (N < 0 || h1 <= 0 || w1 <= 0 || num_levels < 1 || num_levels > kMaxLevels)
+  return goslam_corr_pool_lookup(pyramid, dtype, num_levels, nullptr, N, coords_hw2, out, N, h1, w1,
+                                 h2, w2, radius, stream);
+}
+
+int goslam_corr_pool_lookup(const void* const* pyramid, int dtype, int num_levels, const int* slots,
+                            int capacity, const float* coords_hw2, void* out, int N, int h1, int w1,
+                            int h2, int w2, int radius, void* stream) {
+  if (N < 0 || h1 <= 0 || w1 <= 0 || num_levels < 1 || num_levels > kMaxLevels || capacity < N)
     return GOSLAM_EINVAL;
   if (N == 0) return GOSLAM_OK;
   LookupArgs a{};
@@ -288,7 +298,7 @@ int goslam_corr_pyramid_lookup(const void* const* pyramid, int dtype, int num_le
     if (a.h2[i] <= 0 || a.w2[i] <= 0) return GOSLAM_EINVAL;
   }
   a.num_levels = num_levels; a.coords = coords_hw2; a.interleaved = 1; a.out = out;
-  a.N = N; a.hw1 = h1 * w1; a.radius = radius;
+  a.N = N; a.hw1 = h1 * w1; a.radius = radius; a.slot = slots; a.cap = capacity;
   if (dtype == GOSLAM_F16) return launch_lookup<__half>(a, (cudaStream_t)stream);
   if (dtype == GOSLAM_F32) return launch_lookup<float>(a, (cudaStream_t)stream);
   return GOSLAM_EINVAL;

@@ -23,7 +23,42 @@ def _ptr_array(tensors):
     return arr
 
 
+class CorrPool:
+    """Slot pool for the correlation pyramids of a factor graph.
+
+    The reference concatenates / boolean-masks the whole pyramid on every add_factors /
+    rm_factors (src/modules/corr.py:55-65 via src/factor_graph.py:114,149) — a copy of up to
+    N*hw*1.33*hw*2 bytes each time.  Here the graph owns `capacity` slots per level, allocated
+    once (FactorGraph.max_factors is the natural capacity); a CorrBlock built `from_video(...,
+    pool=pool)` holds only a table of slot ids, so cat() joins two tables and __getitem__ filters
+    one.  The build and lookup kernels follow the table on the device
+    (goslam_corr_pool_build / goslam_corr_pool_lookup)."""
+
+    def __init__(self, capacity, ht, wd, num_levels=4, device="cuda"):
+        self.capacity, self.ht, self.wd, self.num_levels = int(capacity), ht, wd, num_levels
+        self.levels = [torch.empty((capacity, ht, wd, ht >> i, wd >> i), dtype=torch.float16, device=device)
+                       for i in range(num_levels)]
+        self._free = list(range(self.capacity - 1, -1, -1))     # stack; slot 0 is handed out first
+
+    @property
+    def free_slots(self):
+        return len(self._free)
+
+    def alloc(self, n):
+        if n > len(self._free):
+            raise RuntimeError("CorrPool exhausted: %d slots requested, %d free of %d"
+                               % (n, len(self._free), self.capacity))
+        out = self._free[len(self._free) - n:][::-1]
+        del self._free[len(self._free) - n:]
+        return out
+
+    def release(self, slots):
+        self._free.extend(reversed(list(slots)))
+
+
 class CorrBlock:
+    pool = None          # set for slot-pool blocks (see CorrPool); then `slots`/`_slots_host` exist
+
     def __init__(self, fmap1, fmap2, num_levels=4, radius=3, impl=0):
         self.num_levels = num_levels
         self.radius = radius
@@ -57,14 +92,27 @@ class CorrBlock:
         self.corr_pyramid = levels
 
     @classmethod
-    def from_video(cls, fmaps_kmajor, ii, jj, ht, wd, rig=1, num_levels=4, radius=3):
+    def from_video(cls, fmaps_kmajor, ii, jj, ht, wd, rig=1, num_levels=4, radius=3, pool=None):
         """FactorGraph.add_factors' volume for edges (ii, jj) straight from video-level K-major
-        feature maps [buffer*rig, ht*wd, 128] (see `fmaps_to_kmajor`): no gathered copies."""
+        feature maps [buffer*rig, ht*wd, 128] (see `fmaps_to_kmajor`): no gathered copies.
+        With `pool` the volumes are written into free slots of that CorrPool."""
         self = cls.__new__(cls)
         self.num_levels, self.radius, self.ht, self.wd = num_levels, radius, ht, wd
         dev = fmaps_kmajor.device
         N = int(ii.shape[0])
         F = int(fmaps_kmajor.shape[0])
+        if pool is not None:
+            if (pool.ht, pool.wd, pool.num_levels) != (ht, wd, num_levels):
+                raise RuntimeError("CorrBlock.from_video: pool shape mismatch")
+            self.pool = pool
+            self._slots_host = pool.alloc(N)
+            self.slots = torch.tensor(self._slots_host, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                rc = _lib.load().goslam_corr_pool_build(
+                    _lib.ptr(fmaps_kmajor), F, int(rig), _lib.ptr(ii), _lib.ptr(jj), _lib.ptr(self.slots),
+                    _ptr_array(pool.levels), num_levels, N, 128, ht, wd, _lib.stream_ptr())
+            _lib.check(rc, "corr_pool_build")
+            return self
         levels = [torch.empty((N, ht, wd, ht >> i, wd >> i), dtype=torch.float16, device=dev)
                   for i in range(num_levels)]
         with torch.cuda.device(dev):
@@ -78,6 +126,8 @@ class CorrBlock:
     def __call__(self, coords):
         batch, num, ht, wd, _ = coords.shape
         N = batch * num
+        if self.pool is not None:
+            return self._call_pooled(coords, batch, num, ht, wd)
         vol0 = self.corr_pyramid[0]
         rd = 2 * self.radius + 1
         coords = coords.reshape(N, ht, wd, 2).contiguous().float()
@@ -92,15 +142,71 @@ class CorrBlock:
         _lib.check(rc, "corr_pyramid_lookup")
         return out
 
+    def _call_pooled(self, coords, batch, num, ht, wd):
+        N = batch * num
+        if N != len(self._slots_host):
+            raise RuntimeError("CorrBlock: %d coordinate maps for %d edges" % (N, len(self._slots_host)))
+        pool = self.pool
+        rd = 2 * self.radius + 1
+        dev = pool.levels[0].device
+        coords = coords.reshape(N, ht, wd, 2).contiguous().float()
+        out = torch.empty((batch, num, self.num_levels * rd * rd, ht, wd), dtype=torch.float16, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().goslam_corr_pool_lookup(
+                _ptr_array(pool.levels), 1, self.num_levels, _lib.ptr(self.slots), pool.capacity,
+                _lib.ptr(coords), _lib.ptr(out), N, ht, wd, pool.ht, pool.wd, int(self.radius),
+                _lib.stream_ptr())
+        _lib.check(rc, "corr_pool_lookup")
+        return out
+
     def cat(self, other):
+        if self.pool is not None:
+            # O(edges): join the slot tables; `other` gives up its slots
+            if other.pool is not self.pool:
+                raise RuntimeError("CorrBlock.cat: blocks live in different pools")
+            self._slots_host = self._slots_host + other._slots_host
+            self.slots = torch.cat([self.slots, other.slots])
+            other._slots_host, other.slots = [], other.slots[:0]
+            return self
         for i in range(self.num_levels):
             self.corr_pyramid[i] = torch.cat([self.corr_pyramid[i], other.corr_pyramid[i]], dim=0)
         return self
 
     def __getitem__(self, index):
+        if self.pool is not None:
+            # O(edges): keep the selected slot ids, hand the others back to the pool.  Any index
+            # form torch accepts on dim 0 works (FactorGraph passes boolean masks).
+            ids = torch.arange(len(self._slots_host))[index.cpu() if torch.is_tensor(index) else index]
+            keep = [int(i) for i in ids.reshape(-1).tolist()]
+            kept = set(keep)
+            if len(kept) != len(keep):
+                raise RuntimeError("CorrBlock[index]: a pooled block cannot hold one slot twice")
+            self.pool.release(s for i, s in enumerate(self._slots_host) if i not in kept)
+            self._slots_host = [self._slots_host[i] for i in keep]
+            self.slots = torch.tensor(self._slots_host, dtype=torch.int32, device=self.slots.device)
+            return self
         for i in range(self.num_levels):
             self.corr_pyramid[i] = self.corr_pyramid[i][index]
         return self
+
+    def free(self):
+        """return every slot to the pool (FactorGraph drops `self.corr` when it clears edges)."""
+        if self.pool is not None and self._slots_host:
+            self.pool.release(self._slots_host)
+            self._slots_host, self.slots = [], self.slots[:0]
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def gather_pyramid(self):
+        """materialise [N,h,w,h>>i,w>>i] per level (tests / code that reads .corr_pyramid)."""
+        if self.pool is None:
+            return self.corr_pyramid
+        idx = self.slots.long()
+        return [lvl[idx] for lvl in self.pool.levels]
 
     @staticmethod
     def corr(fmap1, fmap2):

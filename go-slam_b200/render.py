@@ -2,53 +2,54 @@
 AABB, stratified + surface-guided z sampling, then ONE call of the fused marcher for the whole
 ray batch (the reference splits into 10,000-ray chunks of ~60 eager kernels each, :53-59).
 
-The z-sampling is a handful of [R, S] elementwise torch ops + one sort over 72 columns; it is
-kept in torch so that, given the same torch RNG state, it reproduces the reference's samples
-bit for bit (shared `perturb_rand[N_samples]` for all rays included, src/render.py:159).
+The z-sampling is ONE kernel launch (goslam_sample_z, csrc/zsample.cu; the reference issues ~25
+eager [R,S] kernels and a torch.sort).  The two linspace tables and the shared
+`perturb_rand[N_samples]` (src/render.py:159) still come from torch, so the RNG stream advances
+exactly as in the reference and z_vals are bit-identical to it for the same RNG state.
 """
+import ctypes
+
 import torch
+
+from . import _lib
+from .droid_backends import _workspace
+
+_tables = {}
+
+
+def _linspace_tables(n_samples, n_surface, device):
+    key = (n_samples, n_surface, str(device))
+    if key not in _tables:
+        tv = torch.linspace(0, 1, steps=n_samples, device=device)                       # src/render.py:143
+        ts = torch.linspace(0, 1, steps=n_surface).float().to(device) if n_surface > 0 else None   # :134
+        _tables[key] = (tv, ts)
+    return _tables[key]
 
 
 def sample_z(rays_o, rays_d, bound, gt_depth, n_samples, n_surface, perturb=1.0, lindisp=False):
     """Returns z_vals [R, S], dists [R, S] with S = n_samples (+ n_surface when gt_depth is given)."""
     device = rays_o.device
-    n_rays = rays_o.shape[0]
+    if not rays_o.is_cuda:
+        raise RuntimeError("sample_z: CUDA tensors required (no CPU fallback)")
+    R = int(rays_o.shape[0])
     if gt_depth is None:
         n_surface = 0
-        near = 0.01
-    else:
-        gt_depth = gt_depth.reshape(-1, 1)
-        near = gt_depth.repeat(1, n_samples) * 0.01
-    with torch.no_grad():
-        t = (bound[None].to(device) - rays_o.detach()[:, :, None]) / rays_d.detach()[:, :, None]
-        far_bb = torch.min(torch.max(t, dim=2)[0], dim=1)[0][:, None] + 0.01
-    far = torch.clamp(far_bb, 0, (gt_depth * 1.2).max()) if gt_depth is not None else far_bb
-
-    z_surface = None
-    if n_surface > 0:
-        valid = gt_depth > 0
-        vdepth = (gt_depth * valid).repeat(1, n_surface)
-        ts = torch.linspace(0, 1, steps=n_surface).float().to(device)[None, :].repeat(n_rays, 1)
-        snr, sfar = (1 - 0.1) * vdepth, (1 + 0.1) * vdepth
-        z_valid = snr + (sfar - snr) * ts
-        z_invalid = 0.001 + (gt_depth.max() - 0.001) * ts
-        z_surface = z_valid * valid + z_invalid * (1 - valid.float())
-
-    tv = torch.linspace(0, 1, steps=n_samples, device=device)[None, :].repeat(n_rays, 1)
-    if not lindisp:
-        z_vals = near + (far - near) * tv
-        sample_dist = ((far - near) / n_samples).mean(dim=1, keepdim=True)
-    else:
-        z_vals = 1.0 / (1.0 / far + (1.0 / near - 1.0 / far) * tv)
-        sample_dist = 1.0 / ((1.0 / near - 1.0 / far) / n_samples).mean(dim=1, keepdim=True)
-    if perturb > 0:
-        mid = 0.5 * (z_vals[:, :-1] + z_vals[:, 1:])
-        upper = torch.cat([mid, z_vals[:, -1:]], dim=1)
-        lower = torch.cat([z_vals[:, :1], mid], dim=1)
-        z_vals = lower + (upper - lower) * torch.rand(n_samples, device=device)
-    if n_surface > 0:
-        z_vals, _ = torch.sort(torch.cat([z_vals, z_surface.float()], dim=1), dim=1)
-    dists = torch.cat([z_vals[..., 1:] - z_vals[..., :-1], sample_dist], dim=-1)
+    S = n_samples + n_surface
+    tv, ts = _linspace_tables(n_samples, n_surface, device)
+    rand = torch.rand(n_samples, device=device) if perturb > 0 else None                # src/render.py:159
+    ro = rays_o.detach().float().contiguous()
+    rd = rays_d.detach().float().contiguous()
+    bd = bound.to(device=device, dtype=torch.float32).contiguous()
+    gd = gt_depth.reshape(-1).float().contiguous() if gt_depth is not None else None
+    z_vals = torch.empty((R, S), dtype=torch.float32, device=device)
+    dists = torch.empty((R, S), dtype=torch.float32, device=device)
+    ws = _workspace(256, device)
+    with torch.cuda.device(device):
+        rc = _lib.load().goslam_sample_z(_lib.ptr(ro), _lib.ptr(rd), _lib.ptr(bd), _lib.ptr(gd), _lib.ptr(tv),
+                                         _lib.ptr(ts), _lib.ptr(rand), R, n_samples, n_surface, int(bool(lindisp)),
+                                         _lib.ptr(z_vals), _lib.ptr(dists), _lib.ptr(ws),
+                                         ctypes.c_size_t(ws.numel()), _lib.stream_ptr())
+    _lib.check(rc, "sample_z")
     return z_vals, dists
 
 

@@ -79,6 +79,19 @@ int goslam_fmaps_to_kmajor(const void* fmaps, void* out, int F, int D, int h, in
 int goslam_corr_build_indexed(const void* fmaps_kmajor, int F, int rig, const int64_t* ii,
                               const int64_t* jj, void* const* levels, int num_levels, int N, int D,
                               int h, int w, void* stream);
+
+/* Slot-pool variants: the edge dimension of the volume is a POOL of `capacity` slots that the
+ * factor graph allocates once; edge e of a block lives in slot slots[e] (int32, device).  Makes
+ * CorrBlock.cat / CorrBlock.__getitem__ (src/modules/corr.py:55-65, hit on every add_factors /
+ * rm_factors, src/factor_graph.py:114,149) an edit of the slot table instead of a copy of the
+ * whole pyramid.  slots == NULL means identity (slot e = edge e).
+ *   levels[L]: pool buffers, level i dims [capacity,h,w,h>>i,w>>i] f16. */
+int goslam_corr_pool_build(const void* fmaps_kmajor, int F, int rig, const int64_t* ii,
+                           const int64_t* jj, const int* slots, void* const* levels, int num_levels,
+                           int N, int D, int h, int w, void* stream);
+int goslam_corr_pool_lookup(const void* const* pyramid, int dtype, int num_levels, const int* slots,
+                            int capacity, const float* coords_hw2, void* out, int N, int h1, int w1,
+                            int h2, int w2, int radius, void* stream);
 /* fp32 variant used by the CPU-shaped config (fmaps f32, volume f32); SIMT only. */
 int goslam_corr_build_f32(const float* fmap1, const float* fmap2, float* const* levels,
                           int num_levels, int N, int D, int h, int w, void* stream);
@@ -207,6 +220,23 @@ int goslam_neus_forward(const goslam_neus_params* params, const float* rays_o,
 /* hash-grid geometry helper (host side, no GPU): fills offsets[17] (in PARAMS, i.e.
  * entries*2), resolutions[16], scales[16]; returns total number of f16 params. */
 int64_t goslam_hashgrid_layout(int64_t* offsets, int* resolutions, float* scales);
+
+/* ------------------------------------------------------------------------------------
+ * Per-ray depth sampling — the z-sampling half of Renderer.render_batch_ray
+ * (src/render.py:99-171: near/far from the scene AABB and the sensor depth, n_samples
+ * stratified samples with one shared jitter table, n_surface samples around the sensor
+ * depth, sorted union, successive distances).
+ *   rays_o, rays_d [R,3] f32; bound [3,2] f32 (device); gt_depth [R] f32 or NULL (then
+ *   n_surface is ignored and near = 0.01);
+ *   t_samples [n_samples] = torch.linspace(0,1,n_samples); t_surface [n_surface] likewise;
+ *   perturb_rand [n_samples] = torch.rand(n_samples) or NULL when rendering.perturb <= 0;
+ *   z_vals, dists [R, n_samples + n_surface] f32 out.  n_samples + n_surface <= 128.
+ *   workspace: >= 256 bytes (device). */
+int goslam_sample_z(const float* rays_o, const float* rays_d, const float* bound,
+                    const float* gt_depth, const float* t_samples, const float* t_surface,
+                    const float* perturb_rand, int R, int n_samples, int n_surface, int lindisp,
+                    float* z_vals, float* dists, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 /* Training-only entry points of the reference module are exported for ABI completeness
  * and return GOSLAM_EUNSUPPORTED (inference path is torch.no_grad, src/slam.py:45). */

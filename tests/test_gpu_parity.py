@@ -1,6 +1,8 @@
 """GPU parity tests (run on the B200 box): every kernel of the hot path, called through the
 C-ABI (via the droid_backends / CorrBlock / InstantNeuS shims), against the CPU oracle on the
 same seeded inputs.  Tolerances are written next to each assertion."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -137,6 +139,60 @@ def test_corr_block_from_video_matches_gathered_build():
         b = CorrBlock.from_video(km, ii, jj, h, w, rig=rig)
         for x, y in zip(a.corr_pyramid, b.corr_pyramid):
             assert torch.equal(x, y)
+
+
+def test_corr_pool_add_remove_matches_cat_and_mask():
+    """FactorGraph's add_factors / rm_factors sequence (src/factor_graph.py:114,149) on a slot pool:
+    cat() and [mask] edit the slot table only, and the pooled lookup equals the lookup on a
+    pyramid that was really concatenated / masked, bit for bit."""
+    from goslam_b200.modules import CorrBlock
+    from goslam_b200.modules.corr import CorrPool, fmaps_to_kmajor
+    g = torch.Generator().manual_seed(16)
+    h, w = 24, 32
+    fmaps = torch.randn(6, 1, 128, h, w, generator=g).half().to(dev())
+    km = fmaps_to_kmajor(fmaps)
+    pool = CorrPool(10, h, w, device=dev())
+    ptrs = [lvl.data_ptr() for lvl in pool.levels]
+
+    def edges(pairs):
+        t = torch.tensor(pairs, device=dev())
+        return t[:, 0].contiguous(), t[:, 1].contiguous()
+
+    def coords_for(n):
+        base = torch.stack(torch.meshgrid(torch.arange(w).float(), torch.arange(h).float(), indexing="xy"), -1)
+        return (base[None, None] + 3 * torch.randn(1, n, h, w, 2, generator=g)).to(dev())
+
+    i1, j1 = edges([(0, 1), (1, 0), (1, 2), (2, 1)])
+    i2, j2 = edges([(2, 3), (3, 2), (0, 3)])
+    i3, j3 = edges([(4, 5), (5, 4), (3, 5), (5, 3), (4, 2)])
+    plain = CorrBlock.from_video(km, i1, j1, h, w)
+    pooled = CorrBlock.from_video(km, i1, j1, h, w, pool=pool)
+    assert pool.free_slots == 6
+    # add
+    plain = plain.cat(CorrBlock.from_video(km, i2, j2, h, w))
+    pooled = pooled.cat(CorrBlock.from_video(km, i2, j2, h, w, pool=pool))
+    assert pool.free_slots == 3 and len(pooled._slots_host) == 7
+    c = coords_for(7)
+    assert torch.equal(plain(c), pooled(c))
+    # remove (boolean keep-mask, as rm_factors passes ~mask)
+    keep = torch.tensor([True, False, True, True, False, True, False], device=dev())
+    plain, pooled = plain[keep], pooled[keep]
+    assert pool.free_slots == 6
+    c = coords_for(4)
+    assert torch.equal(plain(c), pooled(c))
+    # add again: freed slots are reused, nothing was reallocated or moved
+    plain = plain.cat(CorrBlock.from_video(km, i3, j3, h, w))
+    pooled = pooled.cat(CorrBlock.from_video(km, i3, j3, h, w, pool=pool))
+    assert pool.free_slots == 1 and sorted(pooled._slots_host) == sorted(set(pooled._slots_host))
+    c = coords_for(9)
+    assert torch.equal(plain(c), pooled(c))
+    for x, y in zip(plain.corr_pyramid, pooled.gather_pyramid()):
+        assert torch.equal(x, y)
+    assert [lvl.data_ptr() for lvl in pool.levels] == ptrs
+    with pytest.raises(RuntimeError):
+        CorrBlock.from_video(km, i1, j1, h, w, pool=pool)      # 4 edges, 1 free slot
+    pooled.free()
+    assert pool.free_slots == 10
 
 
 # ------------------------------------------------------------------------------ altcorr
@@ -354,3 +410,57 @@ def test_neus_forward(R):
         # a flipped fine-level cell changes ONE sample's alpha: at most ~2/S of the ray's scale
         assert err.max() < max(8 * sens, 2.0 / 72), (k, float(err.max()), float(sens))
     assert abs(float(got["gradient_error"][0]) - float(ref["gradient_error"][0])) < 2e-3 * abs(float(ref["gradient_error"][0]))
+
+
+# ------------------------------------------------------------------------------ z sampling
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["rgbd", "mono", "lindisp", "noperturb"])
+def test_sample_z_matches_oracle(case, monkeypatch):
+    """goslam_sample_z (one launch) == the eager restatement of src/render.py:99-171, bit for bit on
+    z_vals (same linspace tables, same shared perturb_rand); the last dists column — a mean over
+    n_samples copies of one number in the reference — to 1e-6."""
+    from goslam_b200 import synthetic
+    from goslam_b200.render import sample_z
+    from oracle import render_oracle
+    g = torch.Generator().manual_seed(31)
+    R = 3000
+    ro, rd, _, _ = synthetic.make_rays(R, S=72, seed=9)
+    depth = 0.5 + 2.5 * torch.rand(R, generator=g)
+    depth[::11] = 0.0                                   # no sensor reading
+    ro[5::97] = torch.tensor([1.999, 0.0, 0.5])         # about to leave the box: far < near, the stratified
+    rd[5::97] = torch.tensor([1.0, 0.0, 0.0])           # list is DEscending -> the general sort path
+    ns, nf = (24, 48)
+    if case == "mono":
+        depth, ns, nf = None, 48, 24
+    fixed = torch.rand(ns, generator=g)
+    monkeypatch.setattr(torch, "rand", lambda n, device=None: fixed.to(device))
+    bound = torch.tensor([[-2.0, 2.0], [-2.5, 1.5], [-1.0, 3.0]])
+    kw = dict(perturb=0.0 if case == "noperturb" else 1.0, lindisp=case == "lindisp")
+    z, d = sample_z(ro.to(dev()), rd.to(dev()), bound, None if depth is None else depth.to(dev()), ns, nf, **kw)
+    zo, do = render_oracle.sample_z(ro.to(dev()), rd.to(dev()), bound, None if depth is None else depth.to(dev()),
+                                    ns, nf, **kw)
+    S = ns + (nf if depth is not None else 0)
+    assert z.shape == (R, S) and d.shape == (R, S)
+    # lindisp with a missing depth gives near = 0 -> inf/NaN samples, in the reference too: NaN == NaN here
+    torch.testing.assert_close(z, zo, rtol=0, atol=0, equal_nan=True)
+    torch.testing.assert_close(d[:, :-1], do[:, :-1], rtol=0, atol=0, equal_nan=True)
+    torch.testing.assert_close(d[:, -1], do[:, -1], rtol=1e-6, atol=0, equal_nan=True)
+    # and against the all-CPU run of the restatement (CPU linspace / CPU kernels)
+    zc, dc = render_oracle.sample_z(ro, rd, bound, depth, ns, nf, **kw)
+    torch.testing.assert_close(z.cpu(), zc, rtol=2e-6, atol=1e-7, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_sample_z_golden_from_reference_renderer(monkeypatch):
+    """tests/golden/render_z.npz holds z_vals/dists captured from the reference's own
+    Renderer.render_batch_ray (CPU, seed 1234)."""
+    from goslam_b200.render import sample_z
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "render_z.npz"))
+    torch.manual_seed(int(gold["torch_seed"]))
+    fixed = torch.rand(24)                               # the reference's perturb_rand for that seed
+    monkeypatch.setattr(torch, "rand", lambda n, device=None: fixed.to(device))
+    bound = torch.tensor([[-2.0, 2.0], [-2.0, 2.0], [-2.0, 2.0]])
+    z, d = sample_z(torch.from_numpy(gold["rays_o"]).to(dev()), torch.from_numpy(gold["rays_d"]).to(dev()), bound,
+                    torch.from_numpy(gold["gt_depth"]).to(dev()), 24, 48, perturb=1.0, lindisp=False)
+    np.testing.assert_allclose(z.cpu().numpy(), gold["z_vals"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(d.cpu().numpy(), gold["dists"], rtol=1e-4, atol=2e-6)

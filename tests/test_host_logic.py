@@ -123,3 +123,18 @@ def test_synthetic_graph_matches_reference_neighbourhood_rule():
     sc2, _ = synthetic.make_scene(8, 40, 80, with_fmaps=False)
     assert torch.equal(sc["poses"], sc2["poses"]) and torch.equal(sc["disps"], sc2["disps"])   # deterministic
     assert abs(float(sc["poses"][:, 3:].norm(dim=-1).mean()) - 1.0) < 1e-5
+
+
+def test_corr_pool_slot_bookkeeping():
+    """CorrPool is host-side bookkeeping only: allocation order, release, exhaustion."""
+    from goslam_b200.modules.corr import CorrPool
+    pool = CorrPool(5, 8, 8, num_levels=2, device="cpu")
+    assert [tuple(l.shape) for l in pool.levels] == [(5, 8, 8, 8, 8), (5, 8, 8, 4, 4)]
+    a = pool.alloc(3)
+    assert a == [0, 1, 2] and pool.free_slots == 2
+    pool.release([1])
+    assert pool.alloc(2) == [1, 3]
+    with pytest.raises(RuntimeError):
+        pool.alloc(2)
+    pool.release([0, 2, 1, 3])
+    assert pool.free_slots == 5 and sorted(pool.alloc(5)) == [0, 1, 2, 3, 4]

@@ -178,9 +178,9 @@ def test_neus_oracle_edge_cases():
     assert out["weight_sum"][3, 0] == 0.0 and out["weight_sum"][0, 0] > 0.0
 
 
-def test_render_z_sampling_mirror_bit_exact():
+def test_render_z_sampling_oracle_bit_exact():
     g = _load("render_z.npz")
-    from goslam_b200.render import sample_z
+    from oracle.render_oracle import sample_z
     torch.manual_seed(int(g["torch_seed"]))
     bound = torch.tensor([[-2.0, 2.0], [-2.0, 2.0], [-2.0, 2.0]])
     z, d = sample_z(torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"]), bound,
