@@ -67,13 +67,15 @@ SIGNATURES = {
                             [ctypes.POINTER(NeusOut), c_void_p, c_size_t, c_void_p]),
     "goslam_hashgrid_layout": (c_int64, [c_void_p, c_void_p, c_void_p]),
     "goslam_sample_z": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "goslam_cvx_upsample": (c_int, [c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_void_p]),
     "goslam_corr_index_backward": (c_int, []),
     "goslam_altcorr_backward": (c_int, []),
 }
 
 
 def lib_path():
-    return _build.LIB
+    # GOSLAM_B200_LIB: load another build of the same library (kernel A/B experiments)
+    return os.environ.get("GOSLAM_B200_LIB") or _build.LIB
 
 
 def load(build_if_missing=True):

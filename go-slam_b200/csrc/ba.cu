@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "se3.cuh"
 #include <cstdlib>
+#include <cstdio>
 
 namespace {
 
@@ -50,7 +51,7 @@ struct BaWs {
   float* Ei;           // [num(slot),6,hw]
   float* Q;            // [num(slot),hw]
   float* w;            // [num(slot),hw]
-  float* part;         // [N,ntiles,27]
+  float* part;         // [N,ntiles*kTP/32,27]  one partial per (edge, tile, warp)
   double* sys;         // [n*n + n]  reduced camera system (H row-major, then b)
   double* chol;        // [n*n]      factor scratch (global path)
   double* rhs;         // [n]        rhs / solution scratch (global path)
@@ -79,7 +80,7 @@ size_t ba_layout(const BaDims& d, void* base, size_t cap, BaWs* ws) {
   w.Ei = a.take<float>((size_t)d.num * 6 * d.hw);
   w.Q = a.take<float>((size_t)d.num * d.hw);
   w.w = a.take<float>((size_t)d.num * d.hw);
-  w.part = a.take<float>((size_t)(d.N > 0 ? d.N : 1) * ntiles * kNRed);
+  w.part = a.take<float>((size_t)(d.N > 0 ? d.N : 1) * ntiles * (kTP / 32) * kNRed);
   w.sys = a.take<double>((size_t)d.n * d.n + d.n);
   w.chol = a.take<double>((size_t)d.n * d.n);
   w.rhs = a.take<double>(d.n > 0 ? d.n : 1);
@@ -189,8 +190,7 @@ struct BaIn {
 // One (frame slot k, kTP-pixel tile) unit; blockDim.x == kTP.  poses / disps are deliberately
 // NOT __restrict__: the single-kernel path below rewrites them between iterations.
 __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, const BaWs& ws,
-                                               int motion_only, int k, int tile,
-                                               float (*red)[32]) {
+                                               int motion_only, int k, int tile) {
   const float* poses = in.poses; const float* disps = in.disps;
   const float* __restrict__ intr = in.intr; const float* __restrict__ disps_sens = in.disps_sens;
   const float* __restrict__ targets = in.targets; const float* __restrict__ weights = in.weights;
@@ -210,9 +210,20 @@ __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, 
   float Ei[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
   const int r0 = ws.row_ptr[f], r1 = ws.row_ptr[f + 1];
+  // targets / weights of the next edge are fetched while the current one is processed
+  float nx[4] = {0.f, 0.f, 0.f, 0.f};
+  if (act && r0 < r1) {
+    const size_t o = ((size_t)ws.edge_idx[r0] * 2) * d.hw + px;
+    nx[0] = targets[o]; nx[1] = targets[o + d.hw]; nx[2] = weights[o]; nx[3] = weights[o + d.hw];
+  }
   for (int r = r0; r < r1; ++r) {
     const int e = ws.edge_idx[r];
     const int jx = (int)jj[e];
+    const float tu = nx[0], tv = nx[1], qu = nx[2], qv = nx[3];
+    if (act && r + 1 < r1) {
+      const size_t o = ((size_t)ws.edge_idx[r + 1] * 2) * d.hw + px;
+      nx[0] = targets[o]; nx[1] = targets[o + d.hw]; nx[2] = weights[o]; nx[3] = weights[o + d.hw];
+    }
     const bool stereo = (jx == f);
     GsSE3 G;
     gs_edge_pose(poses, f, jx, G);
@@ -227,12 +238,6 @@ __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, 
     // single-instruction float reciprocal is used instead of an fp64 divide.
     const float dd = behind ? 0.0f : __frcp_rn(Xj[2]);
     const float d2 = dd * dd;
-    float tu = 0.f, tv = 0.f, qu = 0.f, qv = 0.f;
-    if (act) {
-      const size_t o = ((size_t)e * 2) * d.hw + px;
-      tu = targets[o]; tv = targets[o + d.hw];
-      qu = weights[o]; qv = weights[o + d.hw];
-    }
     float wu = (behind || !act) ? 0.0f : (float)(.001 * (double)qu);
     float wv = (behind || !act) ? 0.0f : (float)(.001 * (double)qv);
     const float ru = tu - (fx * dd * x + cx);
@@ -265,16 +270,10 @@ __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, 
 #pragma unroll
       for (int a = kNRed; a < 32; ++a) val[a] = 0.f;
     }
+    // one partial per warp: no block barrier anywhere in the linearisation
     const float tot = warp_transpose_reduce32(val, lane);
-    red[warp][lane] = tot;
-    __syncthreads();
-    if (threadIdx.x < kNRed) {
-      float s = 0.f;
-#pragma unroll
-      for (int wq = 0; wq < kTP / 32; ++wq) s += red[wq][threadIdx.x];
-      ws.part[((size_t)e * ws.ntiles + tile) * kNRed + threadIdx.x] = s;
-    }
-    __syncthreads();
+    if (lane < kNRed)
+      ws.part[(((size_t)e * ws.ntiles + tile) * (kTP / 32) + warp) * kNRed + lane] = tot;
 
     if (!motion_only) {
       float Ee[6], Eii[6];
@@ -309,9 +308,8 @@ __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, 
 
 __global__ void __launch_bounds__(kTP)
 ba_linearize_kernel(BaIn in, BaDims d, BaWs ws, int motion_only) {
-  __shared__ float red[kTP / 32][32];
   if ((int)blockIdx.y >= ws.counts[0]) return;
-  linearize_tile(in, d, ws, motion_only, blockIdx.y, blockIdx.x, red);
+  linearize_tile(in, d, ws, motion_only, blockIdx.y, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------
@@ -323,6 +321,7 @@ ba_linearize_kernel(BaIn in, BaDims d, BaWs ws, int motion_only) {
 // ------------------------------------------------------------------------------------
 struct SysSmem {
   float red[8][64];
+  double redd[8][32];
   double Hs[36], Ms[36], Ts[36], vs[6];
 };
 
@@ -330,151 +329,197 @@ struct SysSmem {
 template <int NT>
 __device__ __forceinline__ void system_items(const float* poses, const int64_t* __restrict__ ii,
                                              const int64_t* __restrict__ jj, const BaDims& d,
-                                             const BaWs& ws, int motion_only, int first, int stride,
+                                             const BaWs& ws, int motion_only, int bid, int nb,
                                              SysSmem& sm) {
   float (*red)[64] = sm.red;
   double* Hs = sm.Hs; double* Ms = sm.Ms; double* Ts = sm.Ts; double* vs = sm.vs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = ws.counts[0];
   const int npairs = motion_only ? 0 : ws.counts[2];
-  constexpr int kChunk = 1024;                       // pixels per Schur work unit
+  constexpr int kChunk = 4 * NT;                     // pixels per Schur work unit (4 per thread)
   const int nchunk = (d.hw + kChunk - 1) / kChunk;
-  const int nitems = d.N + npairs * nchunk;
   double* H = ws.sys;
   double* bvec = ws.sys + (size_t)d.n * d.n;
 
-  for (int item = first; item < nitems; item += stride) {
-    if (item < d.N) {
-      // ---------------- pose blocks of one edge ----------------
-      const int e = item;
-      const int ix = (int)ii[e], jx = (int)jj[e];
-      const int pi = ix - d.t0, pj = jx - d.t0;
-      const bool vi_ok = pi >= 0 && pi < d.P, vj_ok = pj >= 0 && pj < d.P;
-      if ((!vi_ok && !vj_ok) || ix < 0 || ix >= d.num) continue;
-      if (tid < kNRed) {
+  // ---------------- pose blocks of the edges ----------------
+  // Edges go to the blocks at the END of the grid: the Schur ranges below fill it from the front
+  // and usually leave the tail idle.
+  for (int e = nb - 1 - bid; e < d.N; e += nb) {
+    const int ix = (int)ii[e], jx = (int)jj[e];
+    const int pi = ix - d.t0, pj = jx - d.t0;
+    const bool vi_ok = pi >= 0 && pi < d.P, vj_ok = pj >= 0 && pj < d.P;
+    if ((!vi_ok && !vj_ok) || ix < 0 || ix >= d.num) continue;
+    // per-tile partials -> 27 sums: warp w takes tiles w, w + NT/32, ... (independent loads)
+    {
+      double ps = 0.0;
+      if (lane < kNRed) {
+        const int nparts = ws.ntiles * (kTP / 32);
+        const float* pp = ws.part + (size_t)e * nparts * kNRed + lane;
+#pragma unroll 4
+        for (int t = warp; t < nparts; t += NT / 32) ps += (double)pp[(size_t)t * kNRed];
+      }
+      sm.redd[warp][lane] = ps;
+    }
+    __syncthreads();
+    if (tid < kNRed) {
+      double s = 0.0;
+#pragma unroll
+      for (int wq = 0; wq < NT / 32; ++wq) s += sm.redd[wq][tid];
+      if (tid < 21) {
+        // unpack upper-triangular index -> (a,b)
+        int a = 0, l = tid;
+        while (l >= 6 - a) { l -= 6 - a; ++a; }
+        const int b = a + l;
+        Hs[a * 6 + b] = s; Hs[b * 6 + a] = s;
+      } else {
+        vs[tid - 21] = s;
+      }
+    }
+    if (tid >= 32 && tid < 38) {
+      // column c of M = Ad^T (apply the dual adjoint to unit vector c)
+      const int c = tid - 32;
+      GsSE3 G;
+      gs_edge_pose(poses, ix, jx, G);
+      float X[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Y[6];
+      X[c] = 1.0f;
+      gs_adjT(G, X, Y);
+      for (int r = 0; r < 6; ++r) Ms[r * 6 + c] = (double)Y[r];
+    }
+    __syncthreads();
+    // T = M * Hjj
+    if (tid < 36) {
+      const int r = tid / 6, c = tid % 6;
+      double s = 0.0;
+      for (int q = 0; q < 6; ++q) s += Ms[r * 6 + q] * Hs[q * 6 + c];
+      Ts[tid] = s;
+    }
+    __syncthreads();
+    if (tid < 36) {
+      const int r = tid / 6, c = tid % 6;
+      // Hii = M Hjj M^T = T M^T ; Hij = -M Hjj = -T ; Hji = Hij^T ; vi = -M vj
+      if (vi_ok) {
         double s = 0.0;
-        for (int t = 0; t < ws.ntiles; ++t)
-          s += (double)ws.part[((size_t)e * ws.ntiles + t) * kNRed + tid];
-        if (tid < 21) {
-          // unpack upper-triangular index -> (a,b)
-          int a = 0, l = tid;
-          while (l >= 6 - a) { l -= 6 - a; ++a; }
-          const int b = a + l;
-          Hs[a * 6 + b] = s; Hs[b * 6 + a] = s;
-        } else {
-          vs[tid - 21] = s;
-        }
+        for (int q = 0; q < 6; ++q) s += Ts[r * 6 + q] * Ms[c * 6 + q];
+        atomicAdd(&H[(size_t)(6 * pi + r) * d.n + 6 * pi + c], s);
       }
-      if (tid >= 32 && tid < 38) {
-        // column c of M = Ad^T (apply the dual adjoint to unit vector c)
-        const int c = tid - 32;
-        GsSE3 G;
-        gs_edge_pose(poses, ix, jx, G);
-        float X[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Y[6];
-        X[c] = 1.0f;
-        gs_adjT(G, X, Y);
-        for (int r = 0; r < 6; ++r) Ms[r * 6 + c] = (double)Y[r];
+      if (vi_ok && vj_ok) {
+        atomicAdd(&H[(size_t)(6 * pi + r) * d.n + 6 * pj + c], -Ts[r * 6 + c]);
+        atomicAdd(&H[(size_t)(6 * pj + r) * d.n + 6 * pi + c], -Ts[c * 6 + r]);
       }
-      __syncthreads();
-      // T = M * Hjj
+      if (vj_ok) atomicAdd(&H[(size_t)(6 * pj + r) * d.n + 6 * pj + c], Hs[r * 6 + c]);
+    } else if (tid >= 64 && tid < 70) {
+      const int r = tid - 64;
+      if (vj_ok) atomicAdd(&bvec[6 * pj + r], vs[r]);
+      if (vi_ok) {
+        double s = 0.0;
+        for (int q = 0; q < 6; ++q) s += Ms[r * 6 + q] * vs[q];
+        atomicAdd(&bvec[6 * pi + r], -s);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---------------- Schur pairs ----------------
+  // Work unit = (pair, 4*NT-pixel chunk); every block takes a CONTIGUOUS range of units, so it
+  // mostly stays inside one pair: the pair is decoded once (a chain of dependent table look-ups)
+  // and its 42 sums are reduced and flushed once, however many chunks the block adds to them.
+  const int total = npairs * nchunk;
+  const int per = (total + nb - 1) / nb;
+  const int u0 = bid * per;
+  const int u1 = min(total, u0 + per);
+  int cur = -1, pa = 0, pb = 0;
+  bool diag = false;
+  const float* Ea = nullptr; const float* Eb = nullptr; const float* Qk = nullptr; const float* wk = nullptr;
+  float acc[64];
+  auto flush = [&]() {
+    // two 32-wide transpose reductions: values [0,32) and [32,64)
+    float lo32[32], hi32[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { lo32[i] = acc[i]; hi32[i] = acc[32 + i]; }
+    const float s0 = warp_transpose_reduce32(lo32, lane);
+    const float s1 = warp_transpose_reduce32(hi32, lane);
+    red[warp][lane] = s0;
+    red[warp][32 + lane] = s1;
+    __syncthreads();
+    if (tid < 42) {
+      double s = 0.0;
+#pragma unroll
+      for (int wq = 0; wq < NT / 32; ++wq) s += (double)red[wq][tid];
       if (tid < 36) {
         const int r = tid / 6, c = tid % 6;
-        double s = 0.0;
-        for (int q = 0; q < 6; ++q) s += Ms[r * 6 + q] * Hs[q * 6 + c];
-        Ts[tid] = s;
+        atomicAdd(&H[(size_t)(6 * pa + r) * d.n + 6 * pb + c], -s);
+        if (!diag) atomicAdd(&H[(size_t)(6 * pb + c) * d.n + 6 * pa + r], -s);
+      } else {
+        atomicAdd(&bvec[6 * pa + (tid - 36)], -s);
       }
-      __syncthreads();
-      if (tid < 36) {
-        const int r = tid / 6, c = tid % 6;
-        // Hii = M Hjj M^T = T M^T ; Hij = -M Hjj = -T ; Hji = Hij^T ; vi = -M vj
-        if (vi_ok) {
-          double s = 0.0;
-          for (int q = 0; q < 6; ++q) s += Ts[r * 6 + q] * Ms[c * 6 + q];
-          atomicAdd(&H[(size_t)(6 * pi + r) * d.n + 6 * pi + c], s);
-        }
-        if (vi_ok && vj_ok) {
-          atomicAdd(&H[(size_t)(6 * pi + r) * d.n + 6 * pj + c], -Ts[r * 6 + c]);
-          atomicAdd(&H[(size_t)(6 * pj + r) * d.n + 6 * pi + c], -Ts[c * 6 + r]);
-        }
-        if (vj_ok) atomicAdd(&H[(size_t)(6 * pj + r) * d.n + 6 * pj + c], Hs[r * 6 + c]);
-      } else if (tid >= 64 && tid < 70) {
-        const int r = tid - 64;
-        if (vj_ok) atomicAdd(&bvec[6 * pj + r], vs[r]);
-        if (vi_ok) {
-          double s = 0.0;
-          for (int q = 0; q < 6; ++q) s += Ms[r * 6 + q] * vs[q];
-          atomicAdd(&bvec[6 * pi + r], -s);
-        }
-      }
-      __syncthreads();
-    } else {
-      // ---------------- one Schur pair ----------------
-      const int p = (item - d.N) / nchunk;
-      const int px0 = ((item - d.N) % nchunk) * kChunk;
-      const int px1 = min(d.hw, px0 + kChunk);
+    }
+    __syncthreads();
+  };
+  for (int u = u0; u < u1; ++u) {
+    const int p = u / nchunk;
+    const int px0 = (u - p * nchunk) * kChunk;
+    const int px1 = min(d.hw, px0 + kChunk);
+    if (p != cur) {
+      if (cur >= 0) flush();
+      cur = p;
       // slot k with pair_ptr[k] <= p < pair_ptr[k+1]
-      int lo = 0, hi = M;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (ws.pair_ptr[mid] <= p) lo = mid; else hi = mid;
+      int k;
+      if (M <= 32) {
+        const int v = lane < M ? ws.pair_ptr[lane] : 0x7fffffff;
+        k = __popc(__ballot_sync(0xffffffffu, v <= p)) - 1;
+      } else {
+        int lo = 0, hi = M;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (ws.pair_ptr[mid] <= p) lo = mid; else hi = mid;
+        }
+        k = lo;
       }
-      const int k = lo;
-      const int ne = ws.entry_ptr[k + 1] - ws.entry_ptr[k];
+      const int e0 = ws.entry_ptr[k];
+      const int ne = ws.entry_ptr[k + 1] - e0;
       int q = p - ws.pair_ptr[k];
       int a = 0;
       while (q >= ne - a) { q -= ne - a; ++a; }      // row a of the upper triangle
       const int b = a + q;
-      const int ca = ws.entry_code[ws.entry_ptr[k] + a];
-      const int cb = ws.entry_code[ws.entry_ptr[k] + b];
-      const float* Ea = (ca >= 0) ? ws.Eij + (size_t)ca * 6 * d.hw : ws.Ei + (size_t)k * 6 * d.hw;
-      const float* Eb = (cb >= 0) ? ws.Eij + (size_t)cb * 6 * d.hw : ws.Ei + (size_t)k * 6 * d.hw;
-      const int pa = (ca >= 0) ? (int)jj[ca] - d.t0 : -ca - 1;
-      const int pb = (cb >= 0) ? (int)jj[cb] - d.t0 : -cb - 1;
-      const float* Qk = ws.Q + (size_t)k * d.hw;
-      const float* wk = ws.w + (size_t)k * d.hw;
-
-      float acc[64];
+      const int ca = ws.entry_code[e0 + a];
+      const int cb = ws.entry_code[e0 + b];
+      Ea = (ca >= 0) ? ws.Eij + (size_t)ca * 6 * d.hw : ws.Ei + (size_t)k * 6 * d.hw;
+      Eb = (cb >= 0) ? ws.Eij + (size_t)cb * 6 * d.hw : ws.Ei + (size_t)k * 6 * d.hw;
+      pa = (ca >= 0) ? ws.edge_j[ca] - d.t0 : -ca - 1;
+      pb = (cb >= 0) ? ws.edge_j[cb] - d.t0 : -cb - 1;
+      Qk = ws.Q + (size_t)k * d.hw;
+      wk = ws.w + (size_t)k * d.hw;
+      diag = a == b;
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-      for (int px = px0 + tid; px < px1; px += NT) {
-        const float qv = Qk[px];
-        float ea[6], eb[6];
+    }
+    // predicated, branch-free body: all 4 x 14 loads of the chunk are in flight together
+    float qv[kChunk / NT], wv[kChunk / NT], ea[kChunk / NT][6], eb[kChunk / NT][6];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) { ea[r] = Ea[(size_t)r * d.hw + px] * qv; eb[r] = Eb[(size_t)r * d.hw + px]; }
+    for (int v = 0; v < kChunk / NT; ++v) {
+      const int px = px0 + tid + v * NT;
+      const bool ok = px < px1;
+      qv[v] = ok ? Qk[px] : 0.f;
+      wv[v] = (ok && diag) ? wk[px] : 0.f;
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-          for (int c = 0; c < 6; ++c) acc[r * 6 + c] += ea[r] * eb[c];
-        if (a == b) {
-          const float wv = wk[px];
-#pragma unroll
-          for (int r = 0; r < 6; ++r) acc[36 + r] += ea[r] * wv;
-        }
+      for (int r = 0; r < 6; ++r) {
+        ea[v][r] = ok ? Ea[(size_t)r * d.hw + px] : 0.f;
+        eb[v][r] = ok ? Eb[(size_t)r * d.hw + px] : 0.f;
       }
-      // two 32-wide transpose reductions: values [0,32) and [32,64)
-      float lo32[32], hi32[32];
+    }
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { lo32[i] = acc[i]; hi32[i] = acc[32 + i]; }
-      const float s0 = warp_transpose_reduce32(lo32, lane);
-      const float s1 = warp_transpose_reduce32(hi32, lane);
-      red[warp][lane] = s0;
-      red[warp][32 + lane] = s1;
-      __syncthreads();
-      if (tid < 42) {
-        double s = 0.0;
+    for (int v = 0; v < kChunk / NT; ++v) {
 #pragma unroll
-        for (int wq = 0; wq < NT / 32; ++wq) s += (double)red[wq][tid];
-        if (tid < 36) {
-          const int r = tid / 6, c = tid % 6;
-          atomicAdd(&H[(size_t)(6 * pa + r) * d.n + 6 * pb + c], -s);
-          if (a != b) atomicAdd(&H[(size_t)(6 * pb + c) * d.n + 6 * pa + r], -s);
-        } else {
-          atomicAdd(&bvec[6 * pa + (tid - 36)], -s);
-        }
-      }
-      __syncthreads();
+      for (int r = 0; r < 6; ++r) ea[v][r] *= qv[v];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc[r * 6 + c] += ea[v][r] * eb[v][c];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[36 + r] += ea[v][r] * wv[v];
     }
   }
+  if (cur >= 0) flush();
 }
 
 __global__ void __launch_bounds__(256)
@@ -516,137 +561,160 @@ __device__ __forceinline__ void retract_poses(float* poses, const BaDims& d, con
 // window of 8 keyframes is 7 block columns).  The 6x6 diagonal factor is computed redundantly in
 // registers; one rsqrt per column and no divisions.  Blocked forward/backward substitution.
 struct SolveSmem {
-  double Ld[6][6];       // factor of the current diagonal block (diag = 1/l_kk)
+  double Lblk[16][15];   // strictly-lower part of each factored 6x6 diagonal block (P <= 16)
   double xs[6];
   int failed;
 };
 
-// 128 threads; smd = (n*n + 2n) doubles of shared memory
+#ifdef GOSLAM_BA_PROBE
+__device__ long long g_solve_probe[8];
+__device__ int g_phase_cycles[2][1024];
+#define SOLVE_PROBE(slot) do { if (threadIdx.x == 0) g_solve_probe[slot] = clock64(); } while (0)
+#else
+#define SOLVE_PROBE(slot) do {} while (0)
+#endif
+
+// 128 threads; smd = (n*n + 2n) doubles of shared memory.
+//  * The right-hand side rides along as row n of the matrix, so the forward substitution happens
+//    inside the factorisation (its panel step) and costs no extra pass.
+//  * Every thread factors the current 6x6 diagonal block redundantly in registers (21 broadcast
+//    loads, one rsqrt per column): no barrier and no shared-memory hop between the block factor
+//    and the panel solve.  2 barriers per block column.
+//  * Backward substitution is right-looking: solve a block, push it into the rows above.
 __device__ __forceinline__ void solve_small(float* poses, const BaDims& d, const BaWs& ws,
                                             const double* sys_in, float lm, float ep, float* dx_out,
                                             int* status_out, double* smd, SolveSmem& ss) {
-  double (*Ld)[6] = ss.Ld;
   double* xs = ss.xs;
   int& failed = ss.failed;
   const int n = d.n, P = d.P, tid = threadIdx.x, lane = tid & 31;
-  double* __restrict__ A = smd;                       // lower triangle is used
-  double* __restrict__ y = smd + (size_t)n * n;
-  double* __restrict__ invd = y + n;                  // 1/l_jj
-  for (int r = tid >> 5; r < n; r += 4)
-    for (int c = lane; c < n; c += 32) {
-      double val = sys_in[(size_t)r * n + c];
-      if (r == c) val += (double)ep + (double)lm * val;
-      A[r * n + c] = val;
+  double* __restrict__ A = smd;                       // rows 0..n-1: lower triangle; row n: rhs
+  double* __restrict__ invd = smd + (size_t)(n + 1) * n;   // 1/l_jj
+  SOLVE_PROBE(0);
+  // ---- load (lower triangle + rhs row), damping on the diagonal.  All of a thread's loads are
+  // issued before the first store: one L2 round trip for a local window (n = 42 -> 15 loads) ----
+  {
+    const int tot = (n + 1) * n;
+    for (int base = 0; base < tot; base += 128 * 16) {
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int idx = base + tid + 128 * u;
+        const int r = idx / n, c = idx - r * n;
+        v[u] = (idx < tot && (c <= r || r == n)) ? sys_in[idx] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int idx = base + tid + 128 * u;
+        const int r = idx / n, c = idx - r * n;
+        if (idx < tot && (c <= r || r == n)) {
+          double val = v[u];
+          if (r == c) val += (double)ep + (double)lm * val;
+          A[idx] = val;
+        }
+      }
     }
-  for (int i = tid; i < n; i += 128) y[i] = sys_in[(size_t)n * n + i];
+  }
   if (tid == 0) failed = 0;
   __syncthreads();
+  SOLVE_PROBE(1);
 
+  bool bad = false;
   for (int jb = 0; jb < P; ++jb) {
     const int j0 = 6 * jb;
-    // (a) 6x6 diagonal block, left-looking, every thread of warp 0 redundantly (registers)
-    if (tid < 32) {
-      double l[6][6];
-      bool bad = false;
+    // (a) 6x6 diagonal block, redundantly per thread
+    double l[6][6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        double dkk = A[(j0 + k) * n + j0 + k];
+    for (int r = 0; r < 6; ++r)
 #pragma unroll
-        for (int m = 0; m < k; ++m) dkk -= l[k][m] * l[k][m];
-        if (!(dkk > 0.0)) bad = true;
-        const double inv = rsqrt(dkk);
-        l[k][k] = inv;
+      for (int c = 0; c <= r; ++c) l[r][c] = A[(j0 + r) * n + j0 + c];
 #pragma unroll
-        for (int r = k + 1; r < 6; ++r) {
-          double v = A[(j0 + r) * n + j0 + k];
+    for (int k = 0; k < 6; ++k) {
+      double dkk = l[k][k];
 #pragma unroll
-          for (int m = 0; m < k; ++m) v -= l[r][m] * l[k][m];
-          l[r][k] = v * inv;
-        }
-      }
-      if (lane == 0) {
-        if (bad) failed = 1;
+      for (int m = 0; m < k; ++m) dkk -= l[k][m] * l[k][m];
+      bad = bad || !(dkk > 0.0);
+      const double inv = rsqrt(dkk);
+      l[k][k] = inv;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
+      for (int r = k + 1; r < 6; ++r) {
+        double v = l[r][k];
 #pragma unroll
-          for (int c = 0; c <= r; ++c) {
-            Ld[r][c] = l[r][c];
-            if (c < r) A[(j0 + r) * n + j0 + c] = l[r][c];   // L below the diagonal; 1/l_rr in invd
-          }
-          invd[j0 + r] = l[r][r];
-        }
+        for (int m = 0; m < k; ++m) v -= l[r][m] * l[k][m];
+        l[r][k] = v * inv;
       }
     }
-    __syncthreads();
-    if (failed) break;
-    // (b) panel: rows below the block, x L_d^T = a_row
-    for (int i = j0 + 6 + tid; i < n; i += 128) {
+    if (tid < 6) {                                    // keep L of the block for the back-substitution
+      invd[j0 + tid] = l[0][0] * (tid == 0) + l[1][1] * (tid == 1) + l[2][2] * (tid == 2) +
+                       l[3][3] * (tid == 3) + l[4][4] * (tid == 4) + l[5][5] * (tid == 5);
+    } else if (tid == 32) {
+      // (not into A: slower threads may still be reading the unfactored block)
+#pragma unroll
+      for (int r = 1; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < r; ++c) ss.Lblk[jb][r * (r - 1) / 2 + c] = l[r][c];
+    }
+    // (b) panel: rows below the block (and the rhs row), x L_d^T = a_row
+    for (int i = j0 + 6 + tid; i <= n; i += 128) {
       double x[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        double v = A[i * n + j0 + k];
+      for (int k = 0; k < 6; ++k) x[k] = A[i * n + j0 + k];
 #pragma unroll
-        for (int m = 0; m < k; ++m) v -= x[m] * Ld[k][m];
-        x[k] = v * Ld[k][k];
+      for (int k = 0; k < 6; ++k) {
+        double v = x[k];
+#pragma unroll
+        for (int m = 0; m < k; ++m) v -= x[m] * l[k][m];
+        x[k] = v * l[k][k];
       }
 #pragma unroll
       for (int k = 0; k < 6; ++k) A[i * n + j0 + k] = x[k];
     }
     __syncthreads();
-    // (c) rank-6 update of the trailing lower triangle
-    const int m = n - j0 - 6;
-    for (int idx = tid; idx < m * m; idx += 128) {
-      const int q = idx / m;
-      const int i = j0 + 6 + q, c = j0 + 6 + (idx - q * m);
-      if (c > i) continue;
-      double acc = A[i * n + c];
+    // (c) rank-6 update of the trailing lower triangle and of the rhs row.
+    // 4 threads per row (columns c = t, t+4, ...), 32 rows per pass.
+    {
+      const int t4 = tid & 3;
+      for (int i = j0 + 6 + (tid >> 2); i <= n; i += 32) {
+        double ri[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) acc -= A[i * n + j0 + k] * A[c * n + j0 + k];
-      A[i * n + c] = acc;
+        for (int k = 0; k < 6; ++k) ri[k] = A[i * n + j0 + k];
+        const int cend = i < n ? i : n - 1;
+        for (int c = j0 + 6 + t4; c <= cend; c += 4) {
+          double acc = A[i * n + c];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) acc -= ri[k] * A[c * n + j0 + k];
+          A[i * n + c] = acc;
+        }
+      }
     }
     __syncthreads();
   }
+  if (bad && tid == 0) failed = 1;
+  __syncthreads();
+  SOLVE_PROBE(2);
 
+  double* __restrict__ y = A + (size_t)n * n;        // row n = L^-1 b
   int fail = failed;
   if (!fail) {
-    // forward: L z = b, block by block
-    for (int jb = 0; jb < P; ++jb) {
-      const int j0 = 6 * jb;
-      if (tid == 0) {
-        double z[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          double v = y[j0 + k];
-#pragma unroll
-          for (int mm = 0; mm < k; ++mm) v -= A[(j0 + k) * n + j0 + mm] * z[mm];
-          z[k] = v * invd[j0 + k];
-          xs[k] = z[k];
-          y[j0 + k] = z[k];
-        }
-      }
-      __syncthreads();
-      for (int i = j0 + 6 + tid; i < n; i += 128) {
-        double v = y[i];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) v -= A[i * n + j0 + k] * xs[k];
-        y[i] = v;
-      }
-      __syncthreads();
-    }
-    // backward: L^T x = z, right-looking (solved block is pushed into the rows above it)
+    // backward: L^T x = z, right-looking
     for (int jb = P - 1; jb >= 0; --jb) {
       const int j0 = 6 * jb;
       if (tid == 0) {
-        double x[6];
+        double lt[6][6], x[6], iv[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { x[k] = y[j0 + k]; iv[k] = invd[j0 + k]; }
+#pragma unroll
+        for (int r = 1; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c < r; ++c) lt[r][c] = ss.Lblk[jb][r * (r - 1) / 2 + c];
 #pragma unroll
         for (int k = 5; k >= 0; --k) {
-          double v = y[j0 + k];
+          double v = x[k];
 #pragma unroll
-          for (int mm = k + 1; mm < 6; ++mm) v -= A[(j0 + mm) * n + j0 + k] * x[mm];
-          x[k] = v * invd[j0 + k];
-          y[j0 + k] = x[k];
-          xs[k] = x[k];
+          for (int mm = k + 1; mm < 6; ++mm) v -= lt[mm][k] * x[mm];
+          x[k] = v * iv[k];
         }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { y[j0 + k] = x[k]; xs[k] = x[k]; }
       }
       __syncthreads();
       for (int i = tid; i < j0; i += 128) {
@@ -658,16 +726,18 @@ __device__ __forceinline__ void solve_small(float* poses, const BaDims& d, const
       __syncthreads();
     }
     if (tid < 32) {
-      int bad = 0;
-      for (int i = lane; i < n; i += 32) bad |= !isfinite(y[i]);
-      if (__any_sync(0xffffffffu, bad) && lane == 0) failed = 1;
+      int nf = 0;
+      for (int i = lane; i < n; i += 32) nf |= !isfinite(y[i]);
+      if (__any_sync(0xffffffffu, nf) && lane == 0) failed = 1;
     }
     __syncthreads();
     fail = failed;
   }
+  SOLVE_PROBE(3);
   solve_finish(poses, d, ws, y, fail, dx_out, status_out, tid, 128);
   __syncthreads();
   retract_poses(poses, d, ws, tid, 128);
+  SOLVE_PROBE(4);
 }
 
 __global__ void __launch_bounds__(128)
@@ -792,6 +862,12 @@ ba_backsub_kernel(float* disps, BaDims d, BaWs ws, int owner_lo, int owner_hi, f
 // of iteration i runs fused with the linearisation of iteration i+1 (same pixel, same thread).
 // 3 grid barriers per iteration replace 5 launches.
 // ------------------------------------------------------------------------------------
+#ifdef GOSLAM_BA_PROBE
+#define BA_PROBE(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) probe[slot] = clock64(); } while (0)
+#else
+#define BA_PROBE(slot) do {} while (0)
+#endif
+
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
   __syncthreads();
   ++epoch;
@@ -813,29 +889,70 @@ ba_persistent_kernel(float* poses, float* disps, BaIn in, BaDims d, BaWs ws, int
                      float ep, int motion_only, float* dx_out, float* dz_out, int* status_out,
                      unsigned* barrier) {
   extern __shared__ double smd[];
-  __shared__ float red[kTP / 32][32];
   __shared__ SysSmem sys_sm;
   __shared__ SolveSmem solve_sm;
   unsigned epoch = 0;
+#ifdef GOSLAM_BA_PROBE
+  __shared__ long long probe[8];
+#endif
   const int M = ws.counts[0];
   const int units = M * ws.ntiles;
   const size_t nsys = (size_t)d.n * d.n + d.n;
   for (int it = 0; it < iterations; ++it) {
+    BA_PROBE(0);
+#ifdef GOSLAM_BA_PROBE
+    const long long tl0 = clock64();
+#endif
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int k = u / ws.ntiles, tile = u - k * ws.ntiles;
       if (it > 0 && !motion_only) backsub_tile(disps, d, ws, 0, d.num, dz_out, k, tile);
-      linearize_tile(in, d, ws, motion_only, k, tile, red);
+      linearize_tile(in, d, ws, motion_only, k, tile);
     }
+#ifdef GOSLAM_BA_PROBE
+    if (threadIdx.x == 0 && blockIdx.x < 1024) g_phase_cycles[0][blockIdx.x] = (int)(clock64() - tl0);
+#endif
+    BA_PROBE(1);
     grid_barrier(barrier, epoch);
+    BA_PROBE(2);
+#ifdef GOSLAM_BA_PROBE
+    const long long ts0 = clock64();
+#endif
     system_items<kTP>(poses, in.ii, in.jj, d, ws, motion_only, blockIdx.x, gridDim.x, sys_sm);
+#ifdef GOSLAM_BA_PROBE
+    if (threadIdx.x == 0 && blockIdx.x < 1024) g_phase_cycles[1][blockIdx.x] = (int)(clock64() - ts0);
+#endif
+    BA_PROBE(3);
     grid_barrier(barrier, epoch);
+    BA_PROBE(4);
     if (blockIdx.x == 0) {
       solve_small(poses, d, ws, ws.sys, lm, ep, dx_out, status_out ? status_out + it : nullptr, smd,
                   solve_sm);
       __syncthreads();
       for (size_t i = threadIdx.x; i < nsys; i += kTP) ws.sys[i] = 0.0;   // for the next iteration
     }
+    BA_PROBE(5);
     grid_barrier(barrier, epoch);
+    BA_PROBE(6);
+#ifdef GOSLAM_BA_PROBE
+    if (threadIdx.x == 0 && blockIdx.x == 0 && it == iterations - 1) {
+      for (int ph = 0; ph < 2; ++ph) {
+        int mx = 0, arg = 0;
+        for (int b = 0; b < (int)gridDim.x && b < 1024; ++b)
+          if (g_phase_cycles[ph][b] > mx) { mx = g_phase_cycles[ph][b]; arg = b; }
+        printf("[phase %d] slowest block %d: %d cycles; blocks 0/100/200/244/250/270/290/295: %d %d %d %d %d %d %d %d\n", ph, arg,
+               mx, g_phase_cycles[ph][0], g_phase_cycles[ph][100], g_phase_cycles[ph][200], g_phase_cycles[ph][244],
+               g_phase_cycles[ph][250], g_phase_cycles[ph][270], g_phase_cycles[ph][290], g_phase_cycles[ph][295]);
+      }
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+      printf("[solve probe it=%d] load %lld | factor %lld | backward %lld | finish+retract %lld\n", it,
+             g_solve_probe[1] - g_solve_probe[0], g_solve_probe[2] - g_solve_probe[1],
+             g_solve_probe[3] - g_solve_probe[2], g_solve_probe[4] - g_solve_probe[3]);
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+      printf("[ba probe it=%d] linearize %lld | barrier %lld | system %lld | barrier %lld | solve %lld | barrier %lld (cycles)\n",
+             it, probe[1] - probe[0], probe[2] - probe[1], probe[3] - probe[2], probe[4] - probe[3],
+             probe[5] - probe[4], probe[6] - probe[5]);
+#endif
   }
   if (!motion_only)
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -946,14 +1063,15 @@ int goslam_ba(float* poses, float* disps, const float* intrinsics, const float* 
   }();
   if (d.n <= kWarpSolveMaxN && !multi_kernel) {
     static int blocks_per_sm = -1, sms = 0;
-    const size_t smem = ((size_t)kWarpSolveMaxN * kWarpSolveMaxN + 2 * kWarpSolveMaxN) * sizeof(double);
+    const size_t smem_max = ((size_t)kWarpSolveMaxN * kWarpSolveMaxN + 2 * kWarpSolveMaxN) * sizeof(double);
+    const size_t smem = ((size_t)d.n * d.n + 2 * d.n) * sizeof(double);
     if (blocks_per_sm < 0) {
       int dev = 0, occ = 0, coop = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-      cudaFuncSetAttribute(ba_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ba_persistent_kernel, kTP, smem);
+      cudaFuncSetAttribute(ba_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ba_persistent_kernel, kTP, smem_max);
       int want = 2;
       if (const char* e = getenv("GOSLAM_BA_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
       blocks_per_sm = (!coop || occ < 1) ? 0 : (occ > want ? want : occ);

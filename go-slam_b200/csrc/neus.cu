@@ -27,7 +27,10 @@
 namespace {
 
 constexpr int kLevels = 16;
-constexpr int kThreadsN = 384;
+#ifndef GOSLAM_NEUS_THREADS
+#define GOSLAM_NEUS_THREADS 384
+#endif
+constexpr int kThreadsN = GOSLAM_NEUS_THREADS;
 constexpr int kWarpsN = kThreadsN / 32;
 constexpr int kDenseLevels = 5;     // levels whose res^3 fits the table (16,24,34,49,71)
 constexpr int kIn = 80, kInPad = 88;     // MLP input width / padded smem row (halves)
@@ -141,14 +144,17 @@ __device__ __forceinline__ void store_relu_half(const float (&acc)[2][NT][4], __
 // Shared memory: network weights once per (persistent) block + a private slab per warp.
 // ---------------------------------------------------------------------------------------
 constexpr int kEncPad = 40;            // enc row stride (halves): 80 B, conflict-free ldmatrix
-constexpr int kMaxGroup = 320;         // samples per warp work item (rays_per_group * S, padded)
+constexpr int kMaxGroup = 288;         // samples per warp work item (rays_per_group * S): 4 rays x 72
 
 struct WarpSlab {
   alignas(16) __half actA[32 * kInPad];    // MLP input rows / hidden 2; also the fp32 SDF-head tile
   alignas(16) __half actB[32 * kHidPad];   // enc rows (stride kEncPad) then hidden 1, rgb scratch
   float w[kMaxGroup];                      // compositing weights of the open group
-  float z[kMaxGroup];                      // mid-point depths
 };
+// Shared memory is sized so that 12 warps + the weights stay under the 164 KB carve-out step:
+// the remaining ~90 KB of the SM's 256 KB serve as L1 for the hash-grid gathers (measured:
+// 14 warps with a 228 KB carve-out are 40 % SLOWER than 12 warps, 8 warps with 124 KB L1 only
+// 3 % slower).  Mid-point depths for the variance pass are recomputed from z_vals/dists.
 
 struct Smem {
   alignas(16) __half W1[kHid * kInPad];
@@ -156,8 +162,8 @@ struct Smem {
   alignas(16) __half W3[kOutW * kHidPad];
   alignas(16) __half sdfWhi[32 * kEncPad];   // Linear(35,32) weight, enc part, fp16 hi/lo split:
   alignas(16) __half sdfWlo[32 * kEncPad];   //   W = hi + lo to 2^-22 relative, products exact
-  float sdfWxyz[3 * 32];                     // xyz part [k][out], fp32
-  float sdfB[32];
+  alignas(16) float sdfWxyz[3 * 32];         // xyz part [k][out], fp32
+  alignas(16) float sdfB[32];
   float gy[32];                              // dL/dy of the normal: W[0,3:] rounded to half
   float colB[3 * 33];
   WarpSlab slab[kWarpsN];
@@ -166,6 +172,7 @@ struct Smem {
 };
 
 static_assert(32 * 33 * 4 <= 32 * kInPad * 2, "fp32 SDF-head tile must fit in actA");
+static_assert(kThreadsN != 384 || sizeof(Smem) + 1024 <= 164 * 1024, "12-warp layout must fit the 164 KB carve-out");
 
 struct LevelConst {
   float scale;
@@ -180,6 +187,8 @@ __device__ __forceinline__ float fast_sin(float x) {
   r = fmaf(-k, 1.9353071795864769e-3f, r);
   return __sinf(r);
 }
+
+__device__ __forceinline__ unsigned h2_as_u32(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
 
 template <bool HASHED>
 __device__ __forceinline__ void encode_level(int l, const __half2* __restrict__ table,
@@ -229,23 +238,21 @@ __device__ __forceinline__ void encode_level(int l, const __half2* __restrict__ 
     r = __hadd2_rn(r, __floats2half2_rn(w * vf[q].x, w * vf[q].y));      // half accumulation (tcnn)
   }
   enc = r;
+  // d(sdf)/d(x01) through this level: contract the two features with dL/dy first (c = v . gy at
+  // the 8 corners), then the gradient of the trilinear interpolant of that one scalar field.
   const float gy0 = gyv[2 * l], gy1 = gyv[2 * l + 1];
+  float c[8];
 #pragma unroll
-  for (int gd = 0; gd < 3; ++gd) {
-    const int d1 = (gd + 1) % 3, d2 = (gd + 2) % 3;
-    float gsum = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int b1 = q & 1, b2 = (q >> 1) & 1;
-      const float w1 = (d1 == 0 ? wx[b1] : d1 == 1 ? wy[b1] : wz[b1]);
-      const float w2 = (d2 == 0 ? wx[b2] : d2 == 1 ? wy[b2] : wz[b2]);
-      const float w = L.scale * w1 * w2;
-      const int il = (b1 << d1) | (b2 << d2);
-      const int ir = il | (1 << gd);
-      gsum += w * ((vf[ir].x - vf[il].x) * gy0 + (vf[ir].y - vf[il].y) * gy1);
-    }
-    genc[gd] += gsum;
-  }
+  for (int q = 0; q < 8; ++q) c[q] = fmaf(vf[q].y, gy1, vf[q].x * gy0);
+  const float dx0 = c[1] - c[0], dx1 = c[3] - c[2], dx2 = c[5] - c[4], dx3 = c[7] - c[6];
+  const float dy0 = c[2] - c[0], dy1 = c[3] - c[1], dy2 = c[6] - c[4], dy3 = c[7] - c[5];
+  const float dz0 = c[4] - c[0], dz1 = c[5] - c[1], dz2 = c[6] - c[2], dz3 = c[7] - c[3];
+  const float gx = wz[0] * fmaf(wy[1], dx1, wy[0] * dx0) + wz[1] * fmaf(wy[1], dx3, wy[0] * dx2);
+  const float gyy = wz[0] * fmaf(wx[1], dy1, wx[0] * dy0) + wz[1] * fmaf(wx[1], dy3, wx[0] * dy2);
+  const float gz = wy[0] * fmaf(wx[1], dz1, wx[0] * dz0) + wy[1] * fmaf(wx[1], dz3, wx[0] * dz2);
+  genc[0] = fmaf(L.scale, gx, genc[0]);
+  genc[1] = fmaf(L.scale, gyy, genc[1]);
+  genc[2] = fmaf(L.scale, gz, genc[2]);
 }
 
 __global__ void __launch_bounds__(kThreadsN, 1)
@@ -415,9 +422,17 @@ neus_forward_kernel(const NeusArgs a) {
       __syncwarp();
       float out[32];
 #pragma unroll
-      for (int o = 0; o < 32; ++o)
-        out[o] = outf[lane * 33 + o] + (sm.sdfB[o] + sm.sdfWxyz[o] * xn[0] + sm.sdfWxyz[32 + o] * xn[1] +
-                                        sm.sdfWxyz[64 + o] * xn[2]);
+      for (int o4 = 0; o4 < 8; ++o4) {
+        const float4 bb = reinterpret_cast<const float4*>(sm.sdfB)[o4];
+        const float4 w0 = reinterpret_cast<const float4*>(sm.sdfWxyz)[o4];
+        const float4 w1 = reinterpret_cast<const float4*>(sm.sdfWxyz + 32)[o4];
+        const float4 w2 = reinterpret_cast<const float4*>(sm.sdfWxyz + 64)[o4];
+        const float* of = outf + lane * 33 + 4 * o4;
+        out[4 * o4 + 0] = of[0] + (bb.x + w0.x * xn[0] + w1.x * xn[1] + w2.x * xn[2]);
+        out[4 * o4 + 1] = of[1] + (bb.y + w0.y * xn[0] + w1.y * xn[1] + w2.y * xn[2]);
+        out[4 * o4 + 2] = of[2] + (bb.z + w0.z * xn[0] + w1.z * xn[1] + w2.z * xn[2]);
+        out[4 * o4 + 3] = of[3] + (bb.w + w0.w * xn[0] + w1.w * xn[1] + w2.w * xn[2]);
+      }
       __syncwarp();                                  // everyone has read outf before actA is reused
 
       if (inb) {
@@ -449,18 +464,28 @@ neus_forward_kernel(const NeusArgs a) {
 
       // ---- MLP input row: [sin(p B)(33) | normal(3) | feat(31) | 1-padding(13)] ----
       {
-        __half* rowA = sl.actA + lane * kInPad;
+        float row[kIn];
 #pragma unroll
         for (int j = 0; j < 33; ++j) {
           const float arg = pt[0] * sm.colB[j] + pt[1] * sm.colB[33 + j] + pt[2] * sm.colB[66 + j];
-          rowA[j] = __float2half_rn(fast_sin(arg));
+          row[j] = fast_sin(arg);
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) rowA[33 + c] = __float2half_rn(g3[c]);
+        for (int c = 0; c < 3; ++c) row[33 + c] = g3[c];
 #pragma unroll
-        for (int i = 0; i < 31; ++i) rowA[36 + i] = __float2half_rn(inb ? out[1 + i] : 0.f);
+        for (int i = 0; i < 31; ++i) row[36 + i] = inb ? out[1 + i] : 0.f;
 #pragma unroll
-        for (int i = 67; i < kIn; ++i) rowA[i] = __float2half_rn(1.0f);
+        for (int i = 67; i < kIn; ++i) row[i] = 1.0f;
+        uint4* rowA = reinterpret_cast<uint4*>(sl.actA + lane * kInPad);   // 176-byte rows: 16-B aligned
+#pragma unroll
+        for (int v8 = 0; v8 < kIn / 8; ++v8) {
+          uint4 u;
+          u.x = h2_as_u32(__floats2half2_rn(row[8 * v8 + 0], row[8 * v8 + 1]));
+          u.y = h2_as_u32(__floats2half2_rn(row[8 * v8 + 2], row[8 * v8 + 3]));
+          u.z = h2_as_u32(__floats2half2_rn(row[8 * v8 + 4], row[8 * v8 + 5]));
+          u.w = h2_as_u32(__floats2half2_rn(row[8 * v8 + 6], row[8 * v8 + 7]));
+          rowA[v8] = u;
+        }
       }
       __syncwarp();
 
@@ -514,7 +539,7 @@ neus_forward_kernel(const NeusArgs a) {
         if (lane == 0 || prev_lr != lr) exc = 1.0f;
         const float T = (lr == open_ray ? carry_T : 1.0f) * exc;
         const float wgt = alpha * T;
-        if (valid) { sl.w[ls] = wgt; sl.z[ls] = zm; }
+        if (valid) sl.w[ls] = wgt;
         const int first_ray = (tile * 32) / S;
         const int last_ray = min((tile * 32 + 31) / S, nrays - 1);
         // carry for the ray that stays open after this tile
@@ -541,7 +566,8 @@ neus_forward_kernel(const NeusArgs a) {
             float var = 0.f;
             __syncwarp();
             for (int s = lane; s < S; s += 32) {
-              const float dz = sl.z[q * S + s] - dep;
+              const size_t gi = (size_t)(ray0 + q) * S + s;
+              const float dz = __fadd_rn(a.z_vals[gi], a.dists[gi] / 2.0f) - dep;
               var += dz * dz * sl.w[q * S + s];
             }
             var = gs_warp_sum(var);

@@ -238,6 +238,16 @@ int goslam_sample_z(const float* rays_o, const float* rays_d, const float* bound
                     float* z_vals, float* dists, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Convex 8x upsampling (cvx_upsample, src/droid_net.py:9-23; DepthVideo.upsample,
+ * src/depth_video.py:194-196): out[b,8y+sy,8x+sx,:] = sum_k softmax_k(mask[b,k,sy,sx,y,x]) *
+ * data[b,y+ky-1,x+kx-1,:] over the zero-padded 3x3 neighbourhood, k = 3*ky + kx.
+ *   data [B,ht,wd,dim] f32 (dim <= 4), mask [B,576,ht,wd] f16 or f32 (mask_dtype = GOSLAM_F16 /
+ *   GOSLAM_F32; an f16 mask gives f16-rounded softmax weights, as torch.softmax does),
+ *   out [B,8ht,8wd,dim] f32, fully overwritten. */
+int goslam_cvx_upsample(const float* data, const void* mask, int mask_dtype, float* out, int B,
+                        int ht, int wd, int dim, void* stream);
+
 /* Training-only entry points of the reference module are exported for ABI completeness
  * and return GOSLAM_EUNSUPPORTED (inference path is torch.no_grad, src/slam.py:45). */
 int goslam_corr_index_backward(void);

@@ -13,6 +13,7 @@ What each fixture pins:
     ba_torch.npz      dx of the reference's dense pure-torch BA   src/geom/ba.py:26-101 + chol.py
     neus.npz          InstantNeuS.forward (9 outputs)             src/InstantNeuS.py:295-370
     render_z.npz      Renderer.render_batch_ray z-sampling        src/render.py:99-171
+    cvx_upsample.npz  cvx_upsample (f32 and f16 masks)            src/droid_net.py:9-23
 Run:  python tests/golden/make_golden.py      (writes next to this file)
 """
 import importlib
@@ -251,11 +252,24 @@ def gen_render_z():
                         z_vals=cap["z"].numpy(), dists=cap["d"].numpy(), torch_seed=1234)
 
 
+def gen_cvx_upsample():
+    dn = ref_import("src.droid_net")
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for tag, (b, ht, wd, dim) in {"disp": (3, 6, 9, 1), "flow": (2, 5, 7, 2)}.items():
+        data = torch.rand(b, ht, wd, dim, generator=g) + 0.1
+        mask = 2.0 * torch.randn(b, 576, ht, wd, generator=g)
+        out[tag + "_data"], out[tag + "_mask"] = data.numpy(), mask.numpy()
+        out[tag + "_out_f32"] = dn.cvx_upsample(data, mask).numpy()
+        out[tag + "_out_f16mask"] = dn.cvx_upsample(data, mask.half()).float().numpy()
+    np.savez_compressed(os.path.join(HERE, "cvx_upsample.npz"), **out)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("needs /root/reference (build container only)")
     install_stubs()
-    which = sys.argv[1:] or ["corr_block", "reproject", "ba_torch", "neus", "render_z"]
+    which = sys.argv[1:] or ["corr_block", "reproject", "ba_torch", "neus", "render_z", "cvx_upsample"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)

@@ -464,3 +464,41 @@ def test_sample_z_golden_from_reference_renderer(monkeypatch):
                     torch.from_numpy(gold["gt_depth"]).to(dev()), 24, 48, perturb=1.0, lindisp=False)
     np.testing.assert_allclose(z.cpu().numpy(), gold["z_vals"], rtol=2e-6, atol=1e-7)
     np.testing.assert_allclose(d.cpu().numpy(), gold["dists"], rtol=1e-4, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------ convex upsampling
+@pytest.mark.parametrize("shape", [(2, 40, 80, 1), (1, 30, 40, 1), (2, 7, 45, 2), (1, 5, 33, 4)])
+@pytest.mark.parametrize("mask_dtype", [torch.float32, torch.float16])
+def test_cvx_upsample(shape, mask_dtype):
+    """goslam_cvx_upsample == softmax/unfold/sum of src/droid_net.py:9-23 (oracle); 1e-6 relative: the
+    9-term softmax and dot product are fp32 in both, only the summation order differs."""
+    from goslam_b200 import droid_net
+    from oracle import upsample_oracle
+    b, ht, wd, dim = shape
+    g = torch.Generator().manual_seed(b * 1000 + wd)
+    data = torch.rand(b, ht, wd, dim, generator=g) + 0.1
+    mask = (3.0 * torch.randn(b, 576, ht, wd, generator=g)).to(mask_dtype)
+    out = droid_net.cvx_upsample(data.to(dev()), mask.to(dev()))
+    ref = upsample_oracle.cvx_upsample(data, mask)
+    assert out.shape == (b, 8 * ht, 8 * wd, dim)
+    if mask_dtype == torch.float32:
+        torch.testing.assert_close(out.cpu(), ref, rtol=2e-6, atol=2e-7)
+    else:
+        # torch.softmax(half) rounds the 9 weights to half: a 1-ulp fp32 difference before that
+        # rounding can flip one weight by half an ulp (2^-11 relative) in a few of the 10^5 outputs
+        diff = (out.cpu() - ref).abs()
+        assert diff.max().item() <= 2.0 ** -11 * float(data.max()) * 1.01
+        assert (diff > 2e-6).float().mean().item() < 1e-3
+    if dim == 1:
+        up = droid_net.upsample_disp(data[..., 0][None].to(dev()), mask[None].to(dev()))
+        assert torch.equal(up[0], out[..., 0])
+
+
+def test_cvx_upsample_golden_from_reference():
+    from goslam_b200 import droid_net
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "cvx_upsample.npz"))
+    for tag in ("disp", "flow"):
+        data, mask = torch.from_numpy(gold[tag + "_data"]).to(dev()), torch.from_numpy(gold[tag + "_mask"]).to(dev())
+        np.testing.assert_allclose(droid_net.cvx_upsample(data, mask).cpu().numpy(), gold[tag + "_out_f32"], rtol=2e-6, atol=2e-7)
+        np.testing.assert_allclose(droid_net.cvx_upsample(data, mask.half()).cpu().numpy(), gold[tag + "_out_f16mask"],
+                                   rtol=0, atol=2.0 ** -11 * 1.2)

@@ -187,3 +187,14 @@ def test_render_z_sampling_oracle_bit_exact():
                     torch.from_numpy(g["gt_depth"]), 24, 48, perturb=1.0, lindisp=False)
     np.testing.assert_array_equal(z.numpy(), g["z_vals"])
     np.testing.assert_array_equal(d.numpy(), g["dists"])
+
+
+def test_cvx_upsample_oracle_matches_reference_function():
+    """oracle/upsample_oracle.py against outputs of the reference's own cvx_upsample (src/droid_net.py:9-23)."""
+    from oracle import upsample_oracle
+    g = _load("cvx_upsample.npz")
+    for tag in ("disp", "flow"):
+        data, mask = torch.from_numpy(g[tag + "_data"]), torch.from_numpy(g[tag + "_mask"])
+        np.testing.assert_allclose(upsample_oracle.cvx_upsample(data, mask).numpy(), g[tag + "_out_f32"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(upsample_oracle.cvx_upsample(data, mask.half()).numpy(), g[tag + "_out_f16mask"],
+                                   rtol=1e-6, atol=1e-7)
