@@ -195,7 +195,6 @@ __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, 
   const float* __restrict__ intr = in.intr; const float* __restrict__ disps_sens = in.disps_sens;
   const float* __restrict__ targets = in.targets; const float* __restrict__ weights = in.weights;
   const float* __restrict__ eta = in.eta; const int eta_rows = in.eta_rows;
-  const int64_t* __restrict__ jj = in.jj;
   const int f = ws.kx[k];
   const int px = tile * kTP + threadIdx.x;
   const bool act = px < d.hw;
@@ -210,23 +209,48 @@ __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, 
   float Ei[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
   const int r0 = ws.row_ptr[f], r1 = ws.row_ptr[f + 1];
-  // targets / weights of the next edge are fetched while the current one is processed
-  float nx[4] = {0.f, 0.f, 0.f, 0.f};
-  if (act && r0 < r1) {
-    const size_t o = ((size_t)ws.edge_idx[r0] * 2) * d.hw + px;
-    nx[0] = targets[o]; nx[1] = targets[o + d.hw]; nx[2] = weights[o]; nx[3] = weights[o + d.hw];
-  }
-  for (int r = r0; r < r1; ++r) {
-    const int e = ws.edge_idx[r];
-    const int jx = (int)jj[e];
-    const float tu = nx[0], tv = nx[1], qu = nx[2], qv = nx[3];
-    if (act && r + 1 < r1) {
-      const size_t o = ((size_t)ws.edge_idx[r + 1] * 2) * d.hw + px;
+  // Software pipeline over the frame's edges (the loop is a chain of dependent look-ups otherwise:
+  // edge id -> target frame -> pose): the edge id / target frame are fetched two edges ahead, the
+  // target pose and the pixel's target / weight one edge ahead.
+  float pi[7];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) pi[c] = poses[7 * (size_t)f + c];
+  int e1 = 0, j1 = f, e2 = 0, j2 = f;                  // edge r (then r+1) and edge r+1 (then r+2)
+  if (r0 < r1) { e1 = ws.edge_idx[r0]; j1 = ws.edge_j[e1]; }
+  if (r0 + 1 < r1) { e2 = ws.edge_idx[r0 + 1]; j2 = ws.edge_j[e2]; }
+  float nx[4] = {0.f, 0.f, 0.f, 0.f}, pn[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+  if (r0 < r1) {
+    if (act) {
+      const size_t o = ((size_t)e1 * 2) * d.hw + px;
       nx[0] = targets[o]; nx[1] = targets[o + d.hw]; nx[2] = weights[o]; nx[3] = weights[o + d.hw];
     }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) pn[c] = poses[7 * (size_t)j1 + c];
+  }
+  for (int r = r0; r < r1; ++r) {
+    const int e = e1, jx = j1;
+    const float tu = nx[0], tv = nx[1], qu = nx[2], qv = nx[3];
+    float pj[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) pj[c] = pn[c];
+    e1 = e2; j1 = j2;
+    if (r + 1 < r1) {
+      if (act) {
+        const size_t o = ((size_t)e1 * 2) * d.hw + px;
+        nx[0] = targets[o]; nx[1] = targets[o + d.hw]; nx[2] = weights[o]; nx[3] = weights[o + d.hw];
+      }
+#pragma unroll
+      for (int c = 0; c < 7; ++c) pn[c] = poses[7 * (size_t)j1 + c];
+    }
+    if (r + 2 < r1) { e2 = ws.edge_idx[r + 2]; j2 = ws.edge_j[e2]; }
     const bool stereo = (jx == f);
     GsSE3 G;
-    gs_edge_pose(poses, f, jx, G);
+    if (stereo) {                                     // fixed stereo baseline (see gs_edge_pose)
+      G.t[0] = -0.1f; G.t[1] = 0.f; G.t[2] = 0.f;
+      G.q[0] = 0.f; G.q[1] = 0.f; G.q[2] = 0.f; G.q[3] = 1.f;
+    } else {
+      gs_rel(pi, pi + 3, pj, pj + 3, G);
+    }
 
     float Xj[4];
     gs_act4(G, Xi, Xj);
@@ -355,7 +379,7 @@ __device__ __forceinline__ void system_items(const float* poses, const int64_t* 
       if (lane < kNRed) {
         const int nparts = ws.ntiles * (kTP / 32);
         const float* pp = ws.part + (size_t)e * nparts * kNRed + lane;
-#pragma unroll 4
+#pragma unroll 8
         for (int t = warp; t < nparts; t += NT / 32) ps += (double)pp[(size_t)t * kNRed];
       }
       sm.redd[warp][lane] = ps;
@@ -590,6 +614,12 @@ __device__ __forceinline__ void solve_small(float* poses, const BaDims& d, const
   double* __restrict__ A = smd;                       // rows 0..n-1: lower triangle; row n: rhs
   double* __restrict__ invd = smd + (size_t)(n + 1) * n;   // 1/l_jj
   SOLVE_PROBE(0);
+  // the pose this thread will retract, fetched now so that its latency hides under the factorisation
+  float pose_old[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+  if (tid < P) {
+#pragma unroll
+    for (int c = 0; c < 7; ++c) pose_old[c] = poses[7 * (size_t)(d.t0 + tid) + c];
+  }
   // ---- load (lower triangle + rhs row), damping on the diagonal.  All of a thread's loads are
   // issued before the first store: one L2 round trip for a local window (n = 42 -> 15 loads) ----
   {
@@ -735,8 +765,15 @@ __device__ __forceinline__ void solve_small(float* poses, const BaDims& d, const
   }
   SOLVE_PROBE(3);
   solve_finish(poses, d, ws, y, fail, dx_out, status_out, tid, 128);
-  __syncthreads();
-  retract_poses(poses, d, ws, tid, 128);
+  if (tid < P) {                                       // P <= 16: one pose per thread, dx straight from smem
+    float xi[6], t1[3], q1[4];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) xi[c] = fail ? 0.0f : (float)y[6 * tid + c];
+    gs_retr(xi, pose_old, pose_old + 3, t1, q1);
+    float* p = poses + 7 * (size_t)(d.t0 + tid);
+    p[0] = t1[0]; p[1] = t1[1]; p[2] = t1[2];
+    p[3] = q1[0]; p[4] = q1[1]; p[5] = q1[2]; p[6] = q1[3];
+  }
   SOLVE_PROBE(4);
 }
 
