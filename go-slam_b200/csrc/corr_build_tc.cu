@@ -26,6 +26,7 @@
 // The 1/4 feature scaling of the reference (`fmap / 4.0` in half) is applied by the K-major
 // re-layout prepass, exactly as the reference does it, so the accumulator needs no scaling.
 #include "common.cuh"
+#include <cstdio>
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
@@ -122,6 +123,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -160,6 +176,10 @@ struct TcParams {
   // slot1 = rig*ii[e], slot2 = rig*jj[e] + (ii[e]==jj[e])   (src/factor_graph.py:108-113,290)
   const int64_t* ii; const int64_t* jj; int rig;
   const int* out_slot;        // optional edge -> output slot of the level buffers (CorrPool)
+  // tiled = 1: levels 0 and 1 are stored as 4x4-element (32-byte) tiles, tile-row-major inside each
+  // source pixel's plane (plane = H4*W4 tiles, padded with zeros); levels 2, 3 stay row-major.
+  int tiled, w4_0, h4_0, w4_1, h4_1;
+  int pitch2, pitch3;         // tiled: bytes per (source pixel, band) of levels 2 / 3 (multiples of 32)
   int aligned;                // w % 16 == 0 && h % 8 == 0: every store is a whole aligned sector run
   int experiment;             // profiling only: 1 = no output writes
 };
@@ -322,13 +342,21 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
     const int ts = group;
     // band staging strides (bytes); the +16 / +8 pads make the per-source-pixel stride conflict-free
     const int p1row = p.n_xb * 16, p1src = 4 * p1row + 16;
-    const int p2row = p.n_xb * 8, p2src = 2 * p2row + 8;
+    const int p2row = p.n_xb * 8, p2src = (p.tiled ? p.pitch2 : 2 * p2row) + 8;
     unsigned char* pool1 = smPool;
     unsigned char* pool2 = smPool + kBM * p1src;
     const int h1 = p.h >> 1, w1 = p.w >> 1, h2 = p.h >> 2, w2 = p.w >> 2, h3 = p.h >> 3, w3 = p.w >> 3;
     const bool wr = p.experiment != 1;
     int tph = 0, tile = 0;
+#ifdef GOSLAM_TC_PROBE
+    long long pr_wait = 0, pr_tiles = 0, pr_bar1 = 0, pr_wo = 0, pr_bar2 = 0, pr_t0 = clock64();
+    const bool pr_on = (etid == 0 || etid == 256) && blockIdx.x == 0;
+#define TCP(x) x
+#else
+#define TCP(x)
+#endif
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      TCP(const long long ta = clock64();)
       const int yb = item % p.n_yb;
       const int mt = (item / p.n_yb) % p.n_mt;
       const int n = item / (p.n_yb * p.n_mt);
@@ -340,10 +368,57 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
       for (int xb = 0; xb < p.n_xb; ++xb, ++tile) {
         if ((tile & (kTStages - 1)) != ts) continue;
         const int x0 = xb * kPX;
+        TCP(const long long tw = clock64();)
         mbar_wait(&tm_full[ts], tph);
+        TCP(pr_wait += clock64() - tw;)
         tc_fence_after();
         const uint32_t taddr = tmem_base + ts * kBN + ((uint32_t)(quad * 32) << 16);
         uint32_t l1[2][4];     // the two level-1 rows this thread produces (8 halves each)
+        if (p.tiled) {
+          // ---- tiled layout: this thread's 4 patch rows x 16 columns are exactly four 4x4 tiles,
+          // adjacent in memory: one 128-byte run per thread (4 x STG.256) ----
+          uint32_t hr[4][8];
+          {
+            uint32_t va[32], vb[32];
+            tmem_ld32_issue(taddr + (2 * half) * 32, va);
+            tmem_ld32_issue(taddr + (2 * half + 1) * 32, vb);
+            tmem_ld_wait();
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int x = 0; x < 8; ++x) {
+                hr[r][x] = pack2(__uint_as_float(va[r * 16 + 2 * x]), __uint_as_float(va[r * 16 + 2 * x + 1]));
+                hr[2 + r][x] = pack2(__uint_as_float(vb[r * 16 + 2 * x]), __uint_as_float(vb[r * 16 + 2 * x + 1]));
+              }
+          }
+          // this warp's part of the accumulator stage is in registers: hand it back before storing
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tm_empty[ts]);
+          const int ty = 2 * yb + half;
+          if (src_ok && ty < p.h4_0) {
+            unsigned char* dst = reinterpret_cast<unsigned char*>(p.lvl[0]) +
+                                 ((plane_id * p.h4_0 + ty) * p.w4_0 + xb * 4) * 32LL;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (xb * 4 + t < p.w4_0)
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + t * 32),
+                             "r"(hr[0][2 * t]), "r"(hr[0][2 * t + 1]), "r"(hr[1][2 * t]), "r"(hr[1][2 * t + 1]),
+                             "r"(hr[2][2 * t]), "r"(hr[2][2 * t + 1]), "r"(hr[3][2 * t]), "r"(hr[3][2 * t + 1])
+                             : "memory");
+          }
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              l1[cc][j] = pack2(pool_pair(hr[2 * cc][2 * j], hr[2 * cc + 1][2 * j]),
+                                pool_pair(hr[2 * cc][2 * j + 1], hr[2 * cc + 1][2 * j + 1]));
+            // level-1 row (2*half+cc) of the band, columns 8*xb .. 8*xb+7 = sub-row of two 4x4 tiles
+            unsigned char* st = pool1 + row * p1src + (2 * half + cc) * 8;
+            *reinterpret_cast<uint2*>(st + (xb * 2) * 32) = make_uint2(l1[cc][0], l1[cc][1]);
+            *reinterpret_cast<uint2*>(st + (xb * 2 + 1) * 32) = make_uint2(l1[cc][2], l1[cc][3]);
+          }
+        } else {
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int c = 2 * half + cc;           // 32-column chunk = patch rows 2c, 2c+1
@@ -369,10 +444,13 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
           *reinterpret_cast<uint4*>(pool1 + row * p1src + c * p1row + xb * 16) =
               make_uint4(l1[cc][0], l1[cc][1], l1[cc][2], l1[cc][3]);
         }
+        }
         // all TMEM reads of this warp for this stage are complete (tmem_ld32 waits): hand it back
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tm_empty[ts]);
+        if (!p.tiled) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tm_empty[ts]);
+        }
         // level-2 row `half` of the band, from the two level-1 rows
         {
           const uint32_t a0 = pack2(pool_pair(l1[0][0], l1[1][0]), pool_pair(l1[0][1], l1[1][1]));
@@ -382,7 +460,9 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
         tph ^= 1;
       }
       // ---- band write-out: all 16 epilogue warps have staged every x-tile of this 8-row band ----
+      TCP(const long long tb = clock64(); pr_tiles += tb - ta;)
       asm volatile("bar.sync 3, 512;" ::: "memory");
+      TCP(const long long tc = clock64(); pr_bar1 += tc - tb;)
       if (wr && p.num_levels > 1) {
         const int s_loc = etid >> 2, part = etid & 3;          // four threads per source pixel
         const int s_glb = mt * kBM + s_loc;
@@ -390,7 +470,53 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
           const long long pl = (long long)n_out * p.hw + s_glb;
           const unsigned char* sp1 = pool1 + s_loc * p1src;
           const unsigned char* sp2 = pool2 + s_loc * p2src;
+          if (p.tiled) {
+            // level 1: one tile-row of 4x4 tiles = w4_1 contiguous sectors, already in tile order
+            if (yb < p.h4_1) {
+              unsigned char* g1 = reinterpret_cast<unsigned char*>(p.lvl[1]) +
+                                  ((pl * p.h4_1 + yb) * p.w4_1) * 32LL;
+              for (int off = part * 32; off < p.w4_1 * 32; off += 128) {
+                uint32_t rr[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) rr[k] = *reinterpret_cast<const uint32_t*>(sp1 + off + 4 * k);
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(g1 + off), "r"(rr[0]),
+                             "r"(rr[1]), "r"(rr[2]), "r"(rr[3]), "r"(rr[4]), "r"(rr[5]), "r"(rr[6]), "r"(rr[7])
+                             : "memory");
+              }
+            }
+            // levels 2 / 3: one padded, sector-aligned piece per (source pixel, band): whole sectors only
+            if (part == 1 && p.num_levels > 2 && 2 * yb < h2) {
+              unsigned char* g2 = reinterpret_cast<unsigned char*>(p.lvl[2]) + (pl * p.n_yb + yb) * (long long)p.pitch2;
+              for (int off = 0; off < p.pitch2; off += 32) {
+                uint32_t rr[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) rr[k] = *reinterpret_cast<const uint32_t*>(sp2 + off + 4 * k);
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(g2 + off), "r"(rr[0]),
+                             "r"(rr[1]), "r"(rr[2]), "r"(rr[3]), "r"(rr[4]), "r"(rr[5]), "r"(rr[6]), "r"(rr[7])
+                             : "memory");
+              }
+            }
+            if (part == 2 && p.num_levels > 3 && yb < h3) {
+              uint32_t rr[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {                    // level-3 columns 2k, 2k+1 of this band's row
+                rr[k] = 0u;
+                if (k < p.n_xb) {
+                  const uint32_t t = *reinterpret_cast<const uint32_t*>(sp2 + 8 * k);
+                  const uint32_t t2 = *reinterpret_cast<const uint32_t*>(sp2 + 8 * k + 4);
+                  const uint32_t b = *reinterpret_cast<const uint32_t*>(sp2 + p2row + 8 * k);
+                  const uint32_t b2 = *reinterpret_cast<const uint32_t*>(sp2 + p2row + 8 * k + 4);
+                  rr[k] = pack2(pool_pair(t, b), pool_pair(t2, b2));
+                }
+              }
+              unsigned char* g3 = reinterpret_cast<unsigned char*>(p.lvl[3]) + (pl * p.n_yb + yb) * 32LL;
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(g3), "r"(rr[0]),
+                           "r"(rr[1]), "r"(rr[2]), "r"(rr[3]), "r"(rr[4]), "r"(rr[5]), "r"(rr[6]), "r"(rr[7])
+                           : "memory");
+            }
+          } else
           if (p.aligned) {
+            if (!p.tiled) {
             // level 1: 4 full rows, contiguous in memory, 32-byte aligned: whole sectors
             unsigned char* g1 = reinterpret_cast<unsigned char*>(p.lvl[1]) +
                                 (pl * h1 + (y0 >> 1)) * (long long)p1row;
@@ -401,6 +527,7 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
               asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(g1 + off), "r"(rr[0]),
                            "r"(rr[1]), "r"(rr[2]), "r"(rr[3]), "r"(rr[4]), "r"(rr[5]), "r"(rr[6]), "r"(rr[7])
                            : "memory");
+            }
             }
             if (part == 1 && p.num_levels > 2) {                // level 2: 2 rows, 16-byte chunks
               unsigned char* g2 = reinterpret_cast<unsigned char*>(p.lvl[2]) +
@@ -424,12 +551,13 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
             // ragged shapes: element-wise with bounds (staging rows are n_xb*8 / n_xb*4 halves wide)
             const __half* s1 = reinterpret_cast<const __half*>(sp1);
             const __half* s2 = reinterpret_cast<const __half*>(sp2);
-            for (int r = 0; r < 4; ++r) {
-              const int y = (y0 >> 1) + r;
-              if (y >= h1) break;
-              __half* g = p.lvl[1] + (pl * h1 + y) * w1;
-              for (int x = part; x < w1; x += 4) g[x] = s1[r * (p1row / 2) + x];
-            }
+            if (!p.tiled)
+              for (int r = 0; r < 4; ++r) {
+                const int y = (y0 >> 1) + r;
+                if (y >= h1) break;
+                __half* g = p.lvl[1] + (pl * h1 + y) * w1;
+                for (int x = part; x < w1; x += 4) g[x] = s1[r * (p1row / 2) + x];
+              }
             if (p.num_levels > 2)
               for (int r = 0; r < 2; ++r) {
                 const int y = (y0 >> 2) + r;
@@ -450,8 +578,15 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
           }
         }
       }
+      TCP(const long long td = clock64(); pr_wo += td - tc;)
       asm volatile("bar.sync 3, 512;" ::: "memory");
+      TCP(pr_bar2 += clock64() - td;)
     }
+#ifdef GOSLAM_TC_PROBE
+    if (pr_on)
+      printf("[tc probe etid=%d] total %lld | tile loop %lld (of which tm_full wait %lld) | bar1 %lld | write-out %lld | bar2 %lld\n",
+             etid, clock64() - pr_t0, pr_tiles, pr_wait, pr_bar1, pr_wo, pr_bar2);
+#endif
   }
 
   tc_fence_before();
@@ -502,8 +637,8 @@ EncodeTiledFn get_encode_fn() {
 
 // launch the tensor-core kernel on K-major (pre-scaled) operands: f1t/f2t = [F1|F2, hw, 128]
 int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_t* ii,
-              const int64_t* jj, int rig, const int* out_slot, __half* const* levels, int num_levels,
-              int N, int h, int w, cudaStream_t st) {
+              const int64_t* jj, int rig, const int* out_slot, int tiled, __half* const* levels,
+              int num_levels, int N, int h, int w, cudaStream_t st) {
   const int hw = h * w;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return GOSLAM_ELAUNCH;
@@ -534,6 +669,10 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
   p.n_mt = gs_cdiv(hw, kBM); p.n_yb = gs_cdiv(h, kPY); p.n_xb = gs_cdiv(w, kPX);
   p.n_items = N * p.n_mt * p.n_yb;
   p.ii = ii; p.jj = jj; p.rig = rig; p.out_slot = out_slot;
+  p.tiled = tiled ? 1 : 0;
+  p.w4_0 = gs_cdiv(w, 4); p.h4_0 = gs_cdiv(h, 4);
+  p.w4_1 = gs_cdiv(w >> 1, 4); p.h4_1 = gs_cdiv(h >> 1, 4);
+  p.pitch2 = (p.n_xb * 16 + 31) / 32 * 32; p.pitch3 = 32;
   p.aligned = (w % 16 == 0 && h % 8 == 0) ? 1 : 0;
   { const char* e = getenv("GOSLAM_TC_EXPERIMENT"); p.experiment = e ? atoi(e) : 0; }
   static bool attr = false;
@@ -566,7 +705,7 @@ int build_tc(const __half* f1, const __half* f2, __half* const* levels, int num_
   to_kmajor_kernel<<<tg, 256, 0, st>>>(f1, f1t, hw);
   to_kmajor_kernel<<<tg, 256, 0, st>>>(f2, f2t, hw);
   GS_CHECK_LAUNCH();
-  return launch_tc(f1t, N, f2t, N, nullptr, nullptr, 1, nullptr, levels, num_levels, N, h, w, st);
+  return launch_tc(f1t, N, f2t, N, nullptr, nullptr, 1, nullptr, 0, levels, num_levels, N, h, w, st);
 }
 
 }  // namespace
@@ -591,21 +730,35 @@ int goslam_fmaps_to_kmajor(const void* fmaps, void* out, int F, int D, int h, in
 int goslam_corr_build_indexed(const void* fmaps_kmajor, int F, int rig, const int64_t* ii,
                               const int64_t* jj, void* const* levels, int num_levels, int N, int D,
                               int h, int w, void* stream) {
-  return goslam_corr_pool_build(fmaps_kmajor, F, rig, ii, jj, nullptr, levels, num_levels, N, D, h, w,
-                                stream);
+  return goslam_corr_pool_build(fmaps_kmajor, F, rig, ii, jj, nullptr, GOSLAM_LAYOUT_ROWMAJOR, levels,
+                                num_levels, N, D, h, w, stream);
+}
+
+size_t goslam_corr_level_plane_elems(int level, int layout, int h, int w) {
+  if (level < 0 || level > 3 || h <= 0 || w <= 0) return 0;
+  const int hl = h >> level, wl = w >> level;
+  if (hl <= 0 || wl <= 0) return 0;
+  if (layout == GOSLAM_LAYOUT_TILED) {
+    if (level < 2) return (size_t)gs_cdiv(hl, 4) * gs_cdiv(wl, 4) * 16;
+    // levels 2 / 3: one padded piece per 8-row band of level 0 (2 rows / 1 row of the level)
+    const int n_yb = gs_cdiv(h, kPY), n_xb = gs_cdiv(w, kPX);
+    return level == 2 ? (size_t)n_yb * ((n_xb * 8 + 15) / 16 * 16) : (size_t)n_yb * 16;
+  }
+  return (size_t)hl * wl;
 }
 
 int goslam_corr_pool_build(const void* fmaps_kmajor, int F, int rig, const int64_t* ii,
-                           const int64_t* jj, const int* slots, void* const* levels, int num_levels,
-                           int N, int D, int h, int w, void* stream) {
+                           const int64_t* jj, const int* slots, int layout, void* const* levels,
+                           int num_levels, int N, int D, int h, int w, void* stream) {
+  if (layout != GOSLAM_LAYOUT_ROWMAJOR && layout != GOSLAM_LAYOUT_TILED) return GOSLAM_EINVAL;
   if (N < 0 || F <= 0 || rig < 1 || D != kD || h <= 0 || w <= 0 || num_levels < 1 || num_levels > 4)
     return GOSLAM_EINVAL;
   if ((h >> (num_levels - 1)) <= 0 || (w >> (num_levels - 1)) <= 0) return GOSLAM_EINVAL;
   if (w > kMaxXB * kPX) return GOSLAM_EINVAL;
   if (N == 0) return GOSLAM_OK;
   const __half* f = reinterpret_cast<const __half*>(fmaps_kmajor);
-  return launch_tc(f, F, f, F, ii, jj, rig, slots, reinterpret_cast<__half* const*>(levels), num_levels,
-                   N, h, w, (cudaStream_t)stream);
+  return launch_tc(f, F, f, F, ii, jj, rig, slots, layout == GOSLAM_LAYOUT_TILED,
+                   reinterpret_cast<__half* const*>(levels), num_levels, N, h, w, (cudaStream_t)stream);
 }
 
 int goslam_corr_build(const void* fmap1, const void* fmap2, void* const* levels, int num_levels,

@@ -39,6 +39,11 @@ struct LookupArgs {
   int N, hw1, radius;
   const int* slot;       // optional edge -> volume slot table (CorrPool); nullptr = identity
   int cap;               // slots in the volume allocation (N when slot == nullptr)
+  int w4[kMaxLevels];    // > 0: the level is stored as 4x4 tiles, w4 tiles per tile-row (f16 only)
+  long long plane[kMaxLevels];   // elements per source-pixel plane
+  // otherwise row y starts at element (y >> rsh) * pitch + (y & rsh) * wrow   (rsh in {0, 1};
+  // reference layout: rsh = 0, pitch = w2)
+  int rsh[kMaxLevels], pitch[kMaxLevels], wrow[kMaxLevels];
 };
 
 // ---- row fetch: 8 consecutive elements starting at absolute element index e0 ----------
@@ -83,8 +88,32 @@ __device__ __forceinline__ void fetch_row8_h(const __half* __restrict__ base, lo
   w[3] = __funnelshift_r(u3, u4, sh);
 }
 
+// Tiled level (4x4-element tiles, tile-row-major): the 8 taps of window row y1 starting at column
+// x1 are sub-row (y1 & 3) of tiles tx0, tx0+1, tx0+2 of tile-row (y1 >> 2): three aligned 8-byte
+// loads, re-aligned in registers.  Tiles outside [0, w4) read as zero.
+__device__ __forceinline__ void fetch_row8_tiled_h(const __half* __restrict__ plane, int y1, int x1,
+                                                   int w4, uint32_t (&w)[4]) {
+  const int ty = y1 >> 2, r = y1 & 3;
+  const int tx0 = x1 >> 2;                    // floor, also for negative x1
+  const int a = x1 & 3;
+  const uint2* rowp = reinterpret_cast<const uint2*>(plane + ((size_t)ty * w4) * 16 + r * 4);
+  uint2 t[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int tx = tx0 + i;
+    t[i] = (tx >= 0 && tx < w4 && (i < 2 || a != 0)) ? __ldg(rowp + (size_t)tx * 4) : make_uint2(0u, 0u);
+  }
+  const uint32_t v0 = t[0].x, v1 = t[0].y, v2 = t[1].x, v3 = t[1].y, v4 = t[2].x, v5 = t[2].y;
+  const bool q = (a & 2) != 0;
+  const uint32_t u0 = q ? v1 : v0, u1 = q ? v2 : v1, u2 = q ? v3 : v2, u3 = q ? v4 : v3, u4 = q ? v5 : v4;
+  const uint32_t sh = (a & 1) * 16;
+  w[0] = __funnelshift_r(u0, u1, sh);
+  w[1] = __funnelshift_r(u1, u2, sh);
+  w[2] = __funnelshift_r(u2, u3, sh);
+  w[3] = __funnelshift_r(u3, u4, sh);
+}
+
 __device__ __forceinline__ __half2 u2h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-__device__ __forceinline__ uint32_t h22u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
 // zero the taps whose column x1+t is outside [0,w2)
 __device__ __forceinline__ void mask_cols_h(uint32_t (&w)[4], int x1, int w2) {
@@ -102,7 +131,8 @@ __device__ __forceinline__ void mask_cols_h(uint32_t (&w)[4], int x1, int w2) {
 // ------------------------------------------------------------------------------------
 template <int R>
 __device__ __forceinline__ void lookup_pass_h(const __half* __restrict__ vol, long long total,
-                                              long long plane_base, int h2, int w2, float x0,
+                                              long long plane_base, int h2, int w2, int w4, int rsh,
+                                              int pitch, int wrow, float x0,
                                               float y0, int row, bool active, __half* stage,
                                               int stage_ld, int px_in_tile) {
   constexpr int RD = 2 * R + 1;
@@ -114,7 +144,8 @@ __device__ __forceinline__ void lookup_pass_h(const __half* __restrict__ vol, lo
 
   uint32_t own[4] = {0, 0, 0, 0};
   if (active && y1 >= 0 && y1 < h2 && x1 > -8 && x1 < w2) {
-    fetch_row8_h(vol, plane_base + (long long)y1 * w2 + x1, total, own);
+    if (w4 > 0) fetch_row8_tiled_h(vol + plane_base, y1, x1, w4, own);
+    else fetch_row8_h(vol, plane_base + (long long)(y1 >> rsh) * pitch + (y1 & rsh) * wrow + x1, total, own);
     mask_cols_h(own, x1, w2);
   }
   uint32_t dn[4];
@@ -220,7 +251,7 @@ corr_lookup_kernel(const LookupArgs a) {
 
   for (int lvl = 0; lvl < a.num_levels; ++lvl) {
     const int h2 = a.h2[lvl], w2 = a.w2[lvl];
-    const long long plane = (long long)h2 * w2;
+    const long long plane = a.plane[lvl];
     const long long total = (long long)a.cap * a.hw1 * plane;
     const T* vol = reinterpret_cast<const T*>(a.vol[lvl]);
     const float sc = a.inv_scale[lvl];
@@ -229,7 +260,8 @@ corr_lookup_kernel(const LookupArgs a) {
       const int k = k0 + ps * 32 + pslot;
       const long long pbase = ((long long)nv * a.hw1 + k) * plane;
       if constexpr (sizeof(T) == 2) {
-        lookup_pass_h<R>(reinterpret_cast<const __half*>(vol), total, pbase, h2, w2, cx[ps] * sc,
+        lookup_pass_h<R>(reinterpret_cast<const __half*>(vol), total, pbase, h2, w2, a.w4[lvl], a.rsh[lvl],
+                         a.pitch[lvl], a.wrow[lvl], cx[ps] * sc,
                          cy[ps] * sc, lane8, act[ps], reinterpret_cast<__half*>(stage), LD,
                          ps * 32 + pslot);
       } else {
@@ -270,6 +302,7 @@ int goslam_corr_index_forward(const void* volume, int dtype, const float* coords
   if (N == 0) return GOSLAM_OK;
   LookupArgs a{};
   a.vol[0] = volume; a.h2[0] = h2; a.w2[0] = w2; a.inv_scale[0] = 1.0f;
+  a.w4[0] = 0; a.plane[0] = (long long)h2 * w2; a.rsh[0] = 0; a.pitch[0] = w2; a.wrow[0] = w2;
   a.num_levels = 1; a.coords = coords; a.interleaved = 0; a.out = corr;
   a.N = N; a.hw1 = h1 * w1; a.radius = radius; a.slot = nullptr; a.cap = N;
   if (dtype == GOSLAM_F16) return launch_lookup<__half>(a, (cudaStream_t)stream);
@@ -280,15 +313,17 @@ int goslam_corr_index_forward(const void* volume, int dtype, const float* coords
 int goslam_corr_pyramid_lookup(const void* const* pyramid, int dtype, int num_levels,
                                const float* coords_hw2, void* out, int N, int h1, int w1, int h2,
                                int w2, int radius, void* stream) {
-  return goslam_corr_pool_lookup(pyramid, dtype, num_levels, nullptr, N, coords_hw2, out, N, h1, w1,
-                                 h2, w2, radius, stream);
+  return goslam_corr_pool_lookup(pyramid, dtype, num_levels, nullptr, N, GOSLAM_LAYOUT_ROWMAJOR, coords_hw2,
+                                 out, N, h1, w1, h2, w2, radius, stream);
 }
 
 int goslam_corr_pool_lookup(const void* const* pyramid, int dtype, int num_levels, const int* slots,
-                            int capacity, const float* coords_hw2, void* out, int N, int h1, int w1,
-                            int h2, int w2, int radius, void* stream) {
+                            int capacity, int layout, const float* coords_hw2, void* out, int N, int h1,
+                            int w1, int h2, int w2, int radius, void* stream) {
   if (N < 0 || h1 <= 0 || w1 <= 0 || num_levels < 1 || num_levels > kMaxLevels || capacity < N)
     return GOSLAM_EINVAL;
+  if (layout != GOSLAM_LAYOUT_ROWMAJOR && layout != GOSLAM_LAYOUT_TILED) return GOSLAM_EINVAL;
+  if (layout == GOSLAM_LAYOUT_TILED && dtype != GOSLAM_F16) return GOSLAM_EINVAL;
   if (N == 0) return GOSLAM_OK;
   LookupArgs a{};
   for (int i = 0; i < num_levels; ++i) {
@@ -296,6 +331,14 @@ int goslam_corr_pool_lookup(const void* const* pyramid, int dtype, int num_level
     a.h2[i] = h2 >> i; a.w2[i] = w2 >> i;          // floor, as F.avg_pool2d(2,2) produces
     a.inv_scale[i] = 1.0f / (float)(1 << i);       // coords / 2**i (exact)
     if (a.h2[i] <= 0 || a.w2[i] <= 0) return GOSLAM_EINVAL;
+    a.plane[i] = (long long)goslam_corr_level_plane_elems(i, layout, h2, w2);
+    a.w4[i] = 0; a.rsh[i] = 0; a.pitch[i] = a.w2[i]; a.wrow[i] = a.w2[i];
+    if (layout == GOSLAM_LAYOUT_TILED) {
+      const int n_xb = gs_cdiv(w2, 16);
+      if (i < 2) a.w4[i] = gs_cdiv(a.w2[i], 4);
+      else if (i == 2) { a.rsh[i] = 1; a.wrow[i] = n_xb * 4; a.pitch[i] = (n_xb * 8 + 15) / 16 * 16; }
+      else { a.pitch[i] = 16; a.wrow[i] = 16; }
+    }
   }
   a.num_levels = num_levels; a.coords = coords_hw2; a.interleaved = 1; a.out = out;
   a.N = N; a.hw1 = h1 * w1; a.radius = radius; a.slot = slots; a.cap = capacity;

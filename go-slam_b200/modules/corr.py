@@ -34,11 +34,53 @@ class CorrPool:
     one.  The build and lookup kernels follow the table on the device
     (goslam_corr_pool_build / goslam_corr_pool_lookup)."""
 
-    def __init__(self, capacity, ht, wd, num_levels=4, device="cuda"):
+    ROWMAJOR, TILED = 0, 1
+
+    def __init__(self, capacity, ht, wd, num_levels=4, device="cuda", layout="tiled"):
+        """layout "tiled" (default): levels 0/1 as 4x4-element tiles (one 32-byte sector each),
+        private to the build and lookup kernels — nothing else in GO-SLAM reads the pyramid
+        (include/goslam_b200.h, GOSLAM_LAYOUT_TILED); "rowmajor": the reference's layout."""
         self.capacity, self.ht, self.wd, self.num_levels = int(capacity), ht, wd, num_levels
-        self.levels = [torch.empty((capacity, ht, wd, ht >> i, wd >> i), dtype=torch.float16, device=device)
+        self.layout = {"tiled": self.TILED, "rowmajor": self.ROWMAJOR}[layout]
+        self.plane_elems = [self._plane_elems(i) for i in range(num_levels)]
+        self.levels = [torch.empty((self.capacity, ht * wd, self.plane_elems[i]), dtype=torch.float16, device=device)
                        for i in range(num_levels)]
         self._free = list(range(self.capacity - 1, -1, -1))     # stack; slot 0 is handed out first
+        self._iota = torch.arange(self.capacity, dtype=torch.int32, device=device)
+
+    def slot_table(self, slots):
+        """device int32 table for a list of slot ids (a view of a resident iota when the ids are a
+        consecutive run — the common case — so that no host->device copy is needed)."""
+        n = len(slots)
+        if n and slots[-1] - slots[0] == n - 1 and all(slots[i + 1] == slots[i] + 1 for i in range(n - 1)):
+            return self._iota[slots[0]:slots[0] + n]
+        return torch.tensor(slots, dtype=torch.int32, device=self._iota.device)
+
+    def _plane_elems(self, i):
+        hl, wl = self.ht >> i, self.wd >> i
+        if self.layout == self.TILED:                             # == goslam_corr_level_plane_elems
+            if i < 2:
+                return ((hl + 3) // 4) * ((wl + 3) // 4) * 16
+            n_yb, n_xb = (self.ht + 7) // 8, (self.wd + 15) // 16
+            return n_yb * ((n_xb * 8 + 15) // 16 * 16) if i == 2 else n_yb * 16
+        return hl * wl
+
+    def level_rowmajor(self, i, slots=None):
+        """level i as [n, ht, wd, ht>>i, wd>>i] (a gathered, de-tiled copy; tests / debugging)."""
+        lvl = self.levels[i] if slots is None else self.levels[i][slots]
+        hl, wl = self.ht >> i, self.wd >> i
+        n = lvl.shape[0]
+        if self.layout == self.TILED and i < 2:
+            h4, w4 = (hl + 3) // 4, (wl + 3) // 4
+            lvl = lvl.view(n, self.ht, self.wd, h4, w4, 4, 4).permute(0, 1, 2, 3, 5, 4, 6)
+            return lvl.reshape(n, self.ht, self.wd, 4 * h4, 4 * w4)[..., :hl, :wl].contiguous()
+        if self.layout == self.TILED:
+            n_yb, n_xb = (self.ht + 7) // 8, (self.wd + 15) // 16
+            if i == 2:          # per band: 2 rows of n_xb*4 columns, padded to a multiple of 16 elements
+                lvl = lvl.view(n, self.ht, self.wd, n_yb, -1)[..., :2 * n_xb * 4]
+                return lvl.reshape(n, self.ht, self.wd, 2 * n_yb, n_xb * 4)[..., :hl, :wl].contiguous()
+            return lvl.view(n, self.ht, self.wd, n_yb, 16)[..., :hl, :wl].contiguous()
+        return lvl.view(n, self.ht, self.wd, hl, wl)
 
     @property
     def free_slots(self):
@@ -106,11 +148,11 @@ class CorrBlock:
                 raise RuntimeError("CorrBlock.from_video: pool shape mismatch")
             self.pool = pool
             self._slots_host = pool.alloc(N)
-            self.slots = torch.tensor(self._slots_host, dtype=torch.int32, device=dev)
+            self.slots = pool.slot_table(self._slots_host)
             with torch.cuda.device(dev):
                 rc = _lib.load().goslam_corr_pool_build(
                     _lib.ptr(fmaps_kmajor), F, int(rig), _lib.ptr(ii), _lib.ptr(jj), _lib.ptr(self.slots),
-                    _ptr_array(pool.levels), num_levels, N, 128, ht, wd, _lib.stream_ptr())
+                    pool.layout, _ptr_array(pool.levels), num_levels, N, 128, ht, wd, _lib.stream_ptr())
             _lib.check(rc, "corr_pool_build")
             return self
         levels = [torch.empty((N, ht, wd, ht >> i, wd >> i), dtype=torch.float16, device=dev)
@@ -154,7 +196,7 @@ class CorrBlock:
         with torch.cuda.device(dev):
             rc = _lib.load().goslam_corr_pool_lookup(
                 _ptr_array(pool.levels), 1, self.num_levels, _lib.ptr(self.slots), pool.capacity,
-                _lib.ptr(coords), _lib.ptr(out), N, ht, wd, pool.ht, pool.wd, int(self.radius),
+                pool.layout, _lib.ptr(coords), _lib.ptr(out), N, ht, wd, pool.ht, pool.wd, int(self.radius),
                 _lib.stream_ptr())
         _lib.check(rc, "corr_pool_lookup")
         return out
@@ -183,7 +225,7 @@ class CorrBlock:
                 raise RuntimeError("CorrBlock[index]: a pooled block cannot hold one slot twice")
             self.pool.release(s for i, s in enumerate(self._slots_host) if i not in kept)
             self._slots_host = [self._slots_host[i] for i in keep]
-            self.slots = torch.tensor(self._slots_host, dtype=torch.int32, device=self.slots.device)
+            self.slots = self.pool.slot_table(self._slots_host)
             return self
         for i in range(self.num_levels):
             self.corr_pyramid[i] = self.corr_pyramid[i][index]
@@ -206,7 +248,7 @@ class CorrBlock:
         if self.pool is None:
             return self.corr_pyramid
         idx = self.slots.long()
-        return [lvl[idx] for lvl in self.pool.levels]
+        return [self.pool.level_rowmajor(i, idx) for i in range(self.num_levels)]
 
     @staticmethod
     def corr(fmap1, fmap2):

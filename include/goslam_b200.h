@@ -85,13 +85,25 @@ int goslam_corr_build_indexed(const void* fmaps_kmajor, int F, int rig, const in
  * CorrBlock.cat / CorrBlock.__getitem__ (src/modules/corr.py:55-65, hit on every add_factors /
  * rm_factors, src/factor_graph.py:114,149) an edit of the slot table instead of a copy of the
  * whole pyramid.  slots == NULL means identity (slot e = edge e).
- *   levels[L]: pool buffers, level i dims [capacity,h,w,h>>i,w>>i] f16. */
+ *   levels[L]: pool buffers, f16.
+ *
+ * layout: GOSLAM_LAYOUT_ROWMAJOR = the reference's [slot,h,w,h>>i,w>>i];
+ *         GOSLAM_LAYOUT_TILED    = levels 0 and 1 stored as 4x4-element (32-byte = one DRAM sector)
+ *         tiles, tile-row-major inside each source pixel's plane, planes padded with zeros to whole
+ *         tiles; levels 2 and 3 row-major.  Nothing in the reference outside CorrBlock reads the
+ *         pyramid, so its layout is private to build + lookup: the tiled form turns the build's
+ *         per-thread output into one 128-byte run and cuts the sectors an 8x8 lookup window touches
+ *         from ~11.5 to ~7.6.  goslam_corr_level_plane_elems gives the per-source-pixel plane size
+ *         (f16 elements) of a level: buffer i holds capacity * h*w * plane_elems(i) elements. */
+#define GOSLAM_LAYOUT_ROWMAJOR 0
+#define GOSLAM_LAYOUT_TILED 1
+size_t goslam_corr_level_plane_elems(int level, int layout, int h, int w);
 int goslam_corr_pool_build(const void* fmaps_kmajor, int F, int rig, const int64_t* ii,
-                           const int64_t* jj, const int* slots, void* const* levels, int num_levels,
-                           int N, int D, int h, int w, void* stream);
+                           const int64_t* jj, const int* slots, int layout, void* const* levels,
+                           int num_levels, int N, int D, int h, int w, void* stream);
 int goslam_corr_pool_lookup(const void* const* pyramid, int dtype, int num_levels, const int* slots,
-                            int capacity, const float* coords_hw2, void* out, int N, int h1, int w1,
-                            int h2, int w2, int radius, void* stream);
+                            int capacity, int layout, const float* coords_hw2, void* out, int N,
+                            int h1, int w1, int h2, int w2, int radius, void* stream);
 /* fp32 variant used by the CPU-shaped config (fmaps f32, volume f32); SIMT only. */
 int goslam_corr_build_f32(const float* fmap1, const float* fmap2, float* const* levels,
                           int num_levels, int N, int D, int h, int w, void* stream);

@@ -141,17 +141,19 @@ def test_corr_block_from_video_matches_gathered_build():
             assert torch.equal(x, y)
 
 
-def test_corr_pool_add_remove_matches_cat_and_mask():
+@pytest.mark.parametrize("layout", ["tiled", "rowmajor"])
+@pytest.mark.parametrize("hw", [(24, 32), (30, 40), (22, 26)])
+def test_corr_pool_add_remove_matches_cat_and_mask(layout, hw):
     """FactorGraph's add_factors / rm_factors sequence (src/factor_graph.py:114,149) on a slot pool:
     cat() and [mask] edit the slot table only, and the pooled lookup equals the lookup on a
     pyramid that was really concatenated / masked, bit for bit."""
     from goslam_b200.modules import CorrBlock
     from goslam_b200.modules.corr import CorrPool, fmaps_to_kmajor
     g = torch.Generator().manual_seed(16)
-    h, w = 24, 32
+    h, w = hw
     fmaps = torch.randn(6, 1, 128, h, w, generator=g).half().to(dev())
     km = fmaps_to_kmajor(fmaps)
-    pool = CorrPool(10, h, w, device=dev())
+    pool = CorrPool(10, h, w, device=dev(), layout=layout)
     ptrs = [lvl.data_ptr() for lvl in pool.levels]
 
     def edges(pairs):
@@ -160,7 +162,12 @@ def test_corr_pool_add_remove_matches_cat_and_mask():
 
     def coords_for(n):
         base = torch.stack(torch.meshgrid(torch.arange(w).float(), torch.arange(h).float(), indexing="xy"), -1)
-        return (base[None, None] + 3 * torch.randn(1, n, h, w, 2, generator=g)).to(dev())
+        c = base[None, None] + 3 * torch.randn(1, n, h, w, 2, generator=g)
+        c[0, :, 0, :3] = torch.tensor([-5.5, 2.25])           # windows hanging over every border
+        c[0, :, 1, :3] = torch.tensor([w + 1.5, h - 2.0])
+        c[0, :, 2, :3] = torch.tensor([w / 2.0, -3.75])
+        c[0, :, 3, :3] = torch.tensor([1.0, h + 2.5])
+        return c.to(dev())
 
     i1, j1 = edges([(0, 1), (1, 0), (1, 2), (2, 1)])
     i2, j2 = edges([(2, 3), (3, 2), (0, 3)])

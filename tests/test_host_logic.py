@@ -1,4 +1,5 @@
 """CPU tests of the host-side mirror of the reference interface (no kernels are launched)."""
+import os
 import sys
 
 import numpy as np
@@ -128,8 +129,22 @@ def test_synthetic_graph_matches_reference_neighbourhood_rule():
 def test_corr_pool_slot_bookkeeping():
     """CorrPool is host-side bookkeeping only: allocation order, release, exhaustion."""
     from goslam_b200.modules.corr import CorrPool
-    pool = CorrPool(5, 8, 8, num_levels=2, device="cpu")
-    assert [tuple(l.shape) for l in pool.levels] == [(5, 8, 8, 8, 8), (5, 8, 8, 4, 4)]
+    pool = CorrPool(5, 8, 8, num_levels=2, device="cpu", layout="rowmajor")
+    assert [tuple(l.shape) for l in pool.levels] == [(5, 64, 64), (5, 64, 16)]
+    # tiled planes are padded to whole 4x4 tiles on levels 0/1 (same formula as the C helper)
+    tiled = CorrPool(2, 30, 40, num_levels=4, device="cpu")
+    assert tiled.plane_elems == [8 * 10 * 16, 4 * 5 * 16, 4 * 32, 4 * 16]      # 4 bands, 3 x-blocks
+    from goslam_b200 import _lib
+    if os.path.exists(_lib.lib_path()):
+        lib = _lib.load(build_if_missing=False)
+        assert [lib.goslam_corr_level_plane_elems(i, 1, 30, 40) for i in range(4)] == tiled.plane_elems
+    # de-tiling is the inverse of the kernel's tile order
+    lvl = tiled.levels[1]
+    lvl.copy_(torch.arange(lvl.numel(), dtype=torch.float32).reshape(lvl.shape) % 1024)
+    rm = tiled.level_rowmajor(1)
+    assert rm.shape == (2, 30, 40, 15, 20)
+    y, x = 6, 13                      # element (y, x) lives in tile (1, 3), position (2, 1)
+    assert rm[1, 7, 9, y, x] == lvl[1, 7 * 40 + 9, ((1 * 5) + 3) * 16 + 2 * 4 + 1]
     a = pool.alloc(3)
     assert a == [0, 1, 2] and pool.free_slots == 2
     pool.release([1])

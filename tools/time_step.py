@@ -28,7 +28,7 @@ def t(fn, n=50, warm=5):
 
 
 km = fmaps_to_kmajor(d["fmaps"][:bench.NUM_KF])
-corr = CorrBlock.from_video(km, ii, jj, bench.HT, bench.WD)
+corr = win.build(km)
 coords, _ = droid_backends.reproject(d["poses"], d["disps"], d["intrinsics"], ii, jj, want_valid=False)
 
 
@@ -39,9 +39,9 @@ def ba(iters, motion_only=False):
 
 
 print("kmajor(8 frames)      %8.1f us" % t(lambda: fmaps_to_kmajor(d["fmaps"][:bench.NUM_KF])))
-print("corr build (36 edges) %8.1f us" % t(lambda: CorrBlock.from_video(km, ii, jj, bench.HT, bench.WD)))
+print("corr build (36 edges) %8.1f us" % t(lambda: win.build(km)))
 print("reproject             %8.1f us" % t(lambda: droid_backends.reproject(d["poses"], d["disps"], d["intrinsics"], ii, jj, want_valid=False)))
-print("lookup (4 levels)     %8.1f us" % t(lambda: corr(coords)))
+print("lookup (4 levels)     %8.1f us" % t(lambda: win.corr(coords)))
 print("state reset (2 copies)%8.1f us" % t(lambda: (d["poses"].copy_(win.poses0), d["disps"].copy_(win.disps0))))
 for it in (1, 2, 3):
     print("ba iters=%d            %8.1f us" % (it, t(lambda: ba(it))))
