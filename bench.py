@@ -414,10 +414,16 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
+        # probe with 2 edges / 1 iteration, then size the real sample for ~15 s of CPU work (the whole
+        # step when the host is fast enough: 36 edges, 3 iterations, nothing extrapolated)
         full, spent = cpu_reference_step(sc, 2, 1)
+        n_e = int(min(36, max(2, 2 * 15.0 / max(spent, 1e-3))))
+        n_it = BA_ITERS if n_e == 36 else 1
+        full, spent = cpu_reference_step(sc, n_e, n_it)
         line["cpu_baseline"] = {"value": 1.0 / full, "unit": "updates/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": "corr build+pyramid+lookup on 2/36 edges + 1/3 BA iterations "
-                                          "(%.1f s of CPU work), extrapolated to the full step" % spent}
+                                "sample": "corr build+pyramid+lookup on %d/36 edges + %d/3 BA iterations "
+                                          "(%.1f s of CPU work)%s" % (n_e, n_it, spent, "" if n_e == 36 else
+                                                                      ", extrapolated linearly to the full step")}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

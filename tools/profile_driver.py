@@ -20,13 +20,14 @@ def main():
     win = bench.Window(sc, dev)
     d = win.d
     ii, jj = d["ii"], d["jj"]
-    f1, f2 = d["fmaps"][ii, 0][None].contiguous(), d["fmaps"][jj, 0][None].contiguous()
-    corr = CorrBlock(f1, f2)
+    from goslam_b200.modules.corr import fmaps_to_kmajor
+    km = fmaps_to_kmajor(d["fmaps"][:bench.NUM_KF])
+    corr = win.build(km)                       # tiled slot pool, video-level indexed build (the bench path)
     coords, _ = droid_backends.reproject(d["poses"], d["disps"], d["intrinsics"], ii, jj, want_valid=False)
     torch.cuda.synchronize()
     for _ in range(reps):
         if what in ("build", "all"):
-            corr = CorrBlock(f1, f2)
+            corr = win.build(km)
         if what in ("lookup", "all"):
             corr(coords)
         if what in ("ba", "all"):
