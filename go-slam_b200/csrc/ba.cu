@@ -190,15 +190,16 @@ struct BaIn {
 // One (frame slot k, kTP-pixel tile) unit; blockDim.x == kTP.  poses / disps are deliberately
 // NOT __restrict__: the single-kernel path below rewrites them between iterations.
 __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, const BaWs& ws,
-                                               int motion_only, int k, int tile) {
+                                               int motion_only, int k, int wt) {
   const float* poses = in.poses; const float* disps = in.disps;
   const float* __restrict__ intr = in.intr; const float* __restrict__ disps_sens = in.disps_sens;
   const float* __restrict__ targets = in.targets; const float* __restrict__ weights = in.weights;
   const float* __restrict__ eta = in.eta; const int eta_rows = in.eta_rows;
   const int f = ws.kx[k];
-  const int px = tile * kTP + threadIdx.x;
+  // wt = 32-pixel warp tile of the frame (no block-level cooperation anywhere below)
+  const int lane = threadIdx.x & 31;
+  const int px = wt * 32 + lane;
   const bool act = px < d.hw;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   const float fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3];
   const float u = (float)(px % d.wd), v = (float)(px / d.wd);
@@ -297,7 +298,7 @@ __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, 
     // one partial per warp: no block barrier anywhere in the linearisation
     const float tot = warp_transpose_reduce32(val, lane);
     if (lane < kNRed)
-      ws.part[(((size_t)e * ws.ntiles + tile) * (kTP / 32) + warp) * kNRed + lane] = tot;
+      ws.part[((size_t)e * ws.ntiles * (kTP / 32) + wt) * kNRed + lane] = tot;
 
     if (!motion_only) {
       float Ee[6], Eii[6];
@@ -333,7 +334,7 @@ __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, 
 __global__ void __launch_bounds__(kTP)
 ba_linearize_kernel(BaIn in, BaDims d, BaWs ws, int motion_only) {
   if ((int)blockIdx.y >= ws.counts[0]) return;
-  linearize_tile(in, d, ws, motion_only, blockIdx.y, blockIdx.x);
+  linearize_tile(in, d, ws, motion_only, blockIdx.y, blockIdx.x * (kTP / 32) + (threadIdx.x >> 5));
 }
 
 // ------------------------------------------------------------------------------------
@@ -856,10 +857,10 @@ ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __re
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ void backsub_tile(float* disps, const BaDims& d, const BaWs& ws,
                                              int owner_lo, int owner_hi, float* dz_out, int k,
-                                             int tile) {
+                                             int wt) {
   const int f = ws.kx[k];
   if (f < owner_lo || f >= owner_hi) return;
-  const int px = tile * kTP + threadIdx.x;
+  const int px = wt * 32 + (threadIdx.x & 31);
   if (px >= d.hw) return;
   float acc = 0.f;
   // own pose entry E_i: pose index f - t0, skipped when <= 0 (reference quirk) or >= P
@@ -890,7 +891,7 @@ __device__ __forceinline__ void backsub_tile(float* disps, const BaDims& d, cons
 __global__ void __launch_bounds__(kTP)
 ba_backsub_kernel(float* disps, BaDims d, BaWs ws, int owner_lo, int owner_hi, float* dz_out) {
   if ((int)blockIdx.y >= ws.counts[0]) return;
-  backsub_tile(disps, d, ws, owner_lo, owner_hi, dz_out, blockIdx.y, blockIdx.x);
+  backsub_tile(disps, d, ws, owner_lo, owner_hi, dz_out, blockIdx.y, blockIdx.x * (kTP / 32) + (threadIdx.x >> 5));
 }
 
 // ------------------------------------------------------------------------------------
@@ -933,17 +934,22 @@ ba_persistent_kernel(float* poses, float* disps, BaIn in, BaDims d, BaWs ws, int
   __shared__ long long probe[8];
 #endif
   const int M = ws.counts[0];
-  const int units = M * ws.ntiles;
+  // linearise / back-substitute unit = (frame slot, 32-pixel warp tile), one per WARP.  Units are dealt
+  // warp-major (unit u -> block u % G, warp u / G) so that a partial last round leaves every SM with
+  // the same number of busy warps instead of some blocks with four and others with none.
+  const int nwt = ws.ntiles * (kTP / 32);
+  const int units = M * nwt;
+  const int ufirst = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, ustep = (kTP / 32) * gridDim.x;
   const size_t nsys = (size_t)d.n * d.n + d.n;
   for (int it = 0; it < iterations; ++it) {
     BA_PROBE(0);
 #ifdef GOSLAM_BA_PROBE
     const long long tl0 = clock64();
 #endif
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int k = u / ws.ntiles, tile = u - k * ws.ntiles;
-      if (it > 0 && !motion_only) backsub_tile(disps, d, ws, 0, d.num, dz_out, k, tile);
-      linearize_tile(in, d, ws, motion_only, k, tile);
+    for (int u = ufirst; u < units; u += ustep) {
+      const int k = u / nwt, wt = u - k * nwt;
+      if (it > 0 && !motion_only) backsub_tile(disps, d, ws, 0, d.num, dz_out, k, wt);
+      linearize_tile(in, d, ws, motion_only, k, wt);
     }
 #ifdef GOSLAM_BA_PROBE
     if (threadIdx.x == 0 && blockIdx.x < 1024) g_phase_cycles[0][blockIdx.x] = (int)(clock64() - tl0);
@@ -992,9 +998,9 @@ ba_persistent_kernel(float* poses, float* disps, BaIn in, BaDims d, BaWs ws, int
 #endif
   }
   if (!motion_only)
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int k = u / ws.ntiles, tile = u - k * ws.ntiles;
-      backsub_tile(disps, d, ws, 0, d.num, dz_out, k, tile);
+    for (int u = ufirst; u < units; u += ustep) {
+      const int k = u / nwt, wt = u - k * nwt;
+      backsub_tile(disps, d, ws, 0, d.num, dz_out, k, wt);
     }
 }
 

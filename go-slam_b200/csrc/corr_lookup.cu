@@ -275,9 +275,18 @@ corr_lookup_kernel(const LookupArgs a) {
     T* outp = reinterpret_cast<T*>(a.out) +
               ((size_t)n * a.num_levels * CH + (size_t)lvl * CH) * a.hw1 + k0;
     const int npx = min(kTile, a.hw1 - k0);
-    for (int idx = threadIdx.x; idx < CH * kTile; idx += kThreadsL) {
-      const int c = idx / kTile, p = idx % kTile;
-      if (p < npx) outp[(size_t)c * a.hw1 + p] = stage[c * LD + p];
+    if (sizeof(T) == 2 && (a.hw1 & 7) == 0) {
+      // 16-byte pieces: channel rows start 16-byte aligned in both the stage (LD*2 = 144 B) and the output
+      for (int idx = threadIdx.x; idx < CH * (kTile / 8); idx += kThreadsL) {
+        const int c = idx / (kTile / 8), p = (idx % (kTile / 8)) * 8;
+        if (p < npx)
+          *reinterpret_cast<uint4*>(outp + (size_t)c * a.hw1 + p) = *reinterpret_cast<const uint4*>(stage + c * LD + p);
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < CH * kTile; idx += kThreadsL) {
+        const int c = idx / kTile, p = idx % kTile;
+        if (p < npx) outp[(size_t)c * a.hw1 + p] = stage[c * LD + p];
+      }
     }
     __syncthreads();
   }
