@@ -27,6 +27,14 @@
 namespace {
 
 constexpr int kLevels = 16;
+// code-size knobs (the kernel body is ~60 KB of SASS; ncu shows warps starved on instruction fetch)
+#ifndef GOSLAM_NEUS_KUNROLL
+#define GOSLAM_NEUS_KUNROLL 8
+#endif
+#ifndef GOSLAM_NEUS_HUNROLL
+#define GOSLAM_NEUS_HUNROLL 1
+#endif
+constexpr int kNeusKUnroll = GOSLAM_NEUS_KUNROLL, kNeusHUnroll = GOSLAM_NEUS_HUNROLL;
 #ifndef GOSLAM_NEUS_THREADS
 #define GOSLAM_NEUS_THREADS 384
 #endif
@@ -108,7 +116,7 @@ __device__ __forceinline__ void warp_layer(const __half* in, const __half* W,
       for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.f;
   const int lr = lane & 15, lc = (lane >> 4) * 8;       // ldmatrix.x4 A addressing
   const int br = lane & 7, bc = ((lane >> 3) & 1) * 8;  // ldmatrix.x2 B addressing
-#pragma unroll
+#pragma unroll kNeusKUnroll
   for (int kt = 0; kt < KT; ++kt) {
     unsigned a[2][4];
 #pragma unroll
@@ -182,7 +190,8 @@ __constant__ LevelConst c_lvl[kLevels];
 
 // sin(x) for |x| up to a few hundred: 2-term Cody-Waite reduction by 2*pi, then the SFU.
 __device__ __forceinline__ float fast_sin(float x) {
-  const float k = rintf(x * 0.15915494309189535f);
+  // rint via the 1.5*2^23 magic constant (exact for |v| < 2^22; the conversion unit is quarter rate)
+  const float k = __fsub_rn(__fadd_rn(x * 0.15915494309189535f, 12582912.0f), 12582912.0f);
   float r = fmaf(-k, 6.28125f, x);
   r = fmaf(-k, 1.9353071795864769e-3f, r);
   return __sinf(r);
@@ -190,8 +199,7 @@ __device__ __forceinline__ float fast_sin(float x) {
 
 __device__ __forceinline__ unsigned h2_as_u32(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
 
-template <bool HASHED>
-__device__ __forceinline__ void encode_level(int l, const __half2* __restrict__ table,
+__device__ __forceinline__ void encode_level(int l, const bool HASHED, const __half2* __restrict__ table,
                                              const float (&x01)[3], const float* gyv,
                                              __half2& enc, float (&genc)[3]) {
   const LevelConst L = c_lvl[l];
@@ -200,18 +208,23 @@ __device__ __forceinline__ void encode_level(int l, const __half2* __restrict__ 
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float pos = fmaf(L.scale, x01[c], 0.5f);
-    const float fl = floorf(pos);
-    pg[c] = (unsigned)(int)fl;
+    // floor of a float in [0, 2^23) without the quarter-rate conversion unit: adding 2^23 with
+    // round-toward-zero drops the fraction, the integer is then the low mantissa bits (exact)
+    const float t = __fadd_rz(pos, 8388608.0f);
+    const float fl = t - 8388608.0f;
+    pg[c] = __float_as_uint(t) & 0x7FFFFFu;
     fr[c] = pos - fl;
   }
   unsigned idx[8];
   if (HASHED) {
-    const unsigned hx0 = pg[0], hx1 = pg[0] + 1u;
-    const unsigned hy0 = pg[1] * 2654435761u, hy1 = hy0 + 2654435761u;
-    const unsigned hz0 = pg[2] * 805459861u, hz1 = hz0 + 805459861u;
+    // (a ^ b ^ c) & m == (a & m) ^ (b & m) ^ (c & m): mask the six components once, one LOP3 per corner
+    const unsigned hx0 = pg[0] & 0x7FFFFu, hx1 = (pg[0] + 1u) & 0x7FFFFu;
+    const unsigned hy = pg[1] * 2654435761u, hz = pg[2] * 805459861u;
+    const unsigned hy0 = hy & 0x7FFFFu, hy1 = (hy + 2654435761u) & 0x7FFFFu;
+    const unsigned hz0 = hz & 0x7FFFFu, hz1 = (hz + 805459861u) & 0x7FFFFu;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      idx[q] = (((q & 1) ? hx1 : hx0) ^ ((q & 2) ? hy1 : hy0) ^ ((q & 4) ? hz1 : hz0)) & 0x7FFFFu;
+      idx[q] = ((q & 1) ? hx1 : hx0) ^ ((q & 2) ? hy1 : hy0) ^ ((q & 4) ? hz1 : hz0);
   } else {
     // dense level: tcnn's `index % size`.  pos = x*scale + 0.5 reaches res-1+0.5, so the +1
     // corner can index one past the last row/plane and wraps; index < 2*size always, so the
@@ -223,10 +236,15 @@ __device__ __forceinline__ void encode_level(int l, const __half2* __restrict__ 
       idx[q] = i >= L.size ? i - L.size : i;
     }
   }
-  const __half2* lvl = table + L.offset;
+  // level base as an integer so that each gather address is ONE wide multiply-add (idx * 4 + base)
+  const unsigned long long lvl = reinterpret_cast<unsigned long long>(table) + (unsigned long long)L.offset * 4ull;
   __half2 v[8];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) v[q] = __ldg(lvl + idx[q]);
+  for (int q = 0; q < 8; ++q) {
+    unsigned long long addr;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(addr) : "r"(idx[q]), "l"(lvl));
+    v[q] = __ldg(reinterpret_cast<const __half2*>(addr));
+  }
 
   const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
   __half2 r = __float2half2_rn(0.f);
@@ -360,16 +378,10 @@ neus_forward_kernel(const NeusArgs a) {
           dscale[c] = (raw >= -1.0f && raw <= 1.0f) ? 2.0f / (b1 - b0) : 0.0f;
           x01[c] = __fdiv_rn(__fadd_rn(xn[c], 1.0f), 2.0f);
         }
-#pragma unroll 1
-        for (int l = 0; l < kDenseLevels; ++l) {
+#pragma unroll kNeusHUnroll
+        for (int l = 0; l < kLevels; ++l) {                 // one copy of the gather/interpolation code
           __half2 e;
-          encode_level<false>(l, table, x01, sm.gy, e, genc);
-          encrow[l] = e;
-        }
-#pragma unroll 2
-        for (int l = kDenseLevels; l < kLevels; ++l) {
-          __half2 e;
-          encode_level<true>(l, table, x01, sm.gy, e, genc);
+          encode_level(l, l >= kDenseLevels, table, x01, sm.gy, e, genc);
           encrow[l] = e;
         }
       } else {
@@ -464,21 +476,31 @@ neus_forward_kernel(const NeusArgs a) {
 
       // ---- MLP input row: [sin(p B)(33) | normal(3) | feat(31) | 1-padding(13)] ----
       {
-        float row[kIn];
+        // the first 32 embedding columns in a rolled loop (4 per trip: the kernel is instruction-
+        // fetch sensitive, see kNeusHUnroll), column 32 with the static tail of the row
+        __half* rowh = sl.actA + lane * kInPad;                            // 176-byte rows: 16-B aligned
+#pragma unroll 1
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float sn[4];
 #pragma unroll
-        for (int j = 0; j < 33; ++j) {
-          const float arg = pt[0] * sm.colB[j] + pt[1] * sm.colB[33 + j] + pt[2] * sm.colB[66 + j];
-          row[j] = fast_sin(arg);
+          for (int u = 0; u < 4; ++u) {
+            const int j = 4 * j4 + u;
+            sn[u] = fast_sin(pt[0] * sm.colB[j] + pt[1] * sm.colB[33 + j] + pt[2] * sm.colB[66 + j]);
+          }
+          *reinterpret_cast<uint2*>(rowh + 4 * j4) =
+              make_uint2(h2_as_u32(__floats2half2_rn(sn[0], sn[1])), h2_as_u32(__floats2half2_rn(sn[2], sn[3])));
         }
+        float row[kIn - 32];                                               // columns 32 .. 79
+        row[0] = fast_sin(pt[0] * sm.colB[32] + pt[1] * sm.colB[65] + pt[2] * sm.colB[98]);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) row[33 + c] = g3[c];
+        for (int c = 0; c < 3; ++c) row[1 + c] = g3[c];
 #pragma unroll
-        for (int i = 0; i < 31; ++i) row[36 + i] = inb ? out[1 + i] : 0.f;
+        for (int i = 0; i < 31; ++i) row[4 + i] = inb ? out[1 + i] : 0.f;
 #pragma unroll
-        for (int i = 67; i < kIn; ++i) row[i] = 1.0f;
-        uint4* rowA = reinterpret_cast<uint4*>(sl.actA + lane * kInPad);   // 176-byte rows: 16-B aligned
+        for (int i = 35; i < kIn - 32; ++i) row[i] = 1.0f;
+        uint4* rowA = reinterpret_cast<uint4*>(rowh + 32);
 #pragma unroll
-        for (int v8 = 0; v8 < kIn / 8; ++v8) {
+        for (int v8 = 0; v8 < (kIn - 32) / 8; ++v8) {
           uint4 u;
           u.x = h2_as_u32(__floats2half2_rn(row[8 * v8 + 0], row[8 * v8 + 1]));
           u.y = h2_as_u32(__floats2half2_rn(row[8 * v8 + 2], row[8 * v8 + 3]));
