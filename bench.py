@@ -271,20 +271,32 @@ def cpu_reference_step(sc, n_corr_edges=4, ba_iters=1):
     return full, (t2 - t0)
 
 
+def cpu_sample_plan(sc, budget_s):
+    """(edges, BA iterations) of the CPU sample: the whole step when it fits `budget_s` seconds on this
+    host, otherwise as many of the 36 edges (+ 1 of the 3 iterations) as fit; probed warm."""
+    cpu_reference_step(sc, 2, 1)                     # thread pools, allocator
+    est_full, _ = cpu_reference_step(sc, 2, 1)
+    if est_full <= budget_s:
+        return 36, BA_ITERS
+    return max(2, int(36 * budget_s / est_full)), 1
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
     sc = make_window(43)
+    n_e, n_it = cpu_sample_plan(sc, 150.0 / max(1, args.steps + args.warmup))
     for _ in range(max(args.warmup, 0)):
-        cpu_reference_step(sc, 2, 1)
+        cpu_reference_step(sc, n_e, n_it)
     ts = []
     for _ in range(args.steps):
-        full, _ = cpu_reference_step(sc, 2, 1)
+        full, _ = cpu_reference_step(sc, n_e, n_it)
         ts.append(full)
     ms = 1e3 * float(np.mean(ts))
     val = 1e3 / ms                # the host's cores are the same whatever N is: its N windows run one after another
-    sample = "per step: corr build+pyramid+lookup on 2/36 edges and 1/3 BA iterations (numpy/torch CPU port of the reference kernels), extrapolated linearly to the full step"
+    sample = ("per step: corr build+pyramid+lookup on %d/36 edges and %d/3 BA iterations (numpy/torch CPU port of the "
+              "reference kernels)%s" % (n_e, n_it, "" if n_e == 36 else ", extrapolated linearly to the full step"))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -414,11 +426,9 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        # probe with 2 edges / 1 iteration, then size the real sample for ~15 s of CPU work (the whole
-        # step when the host is fast enough: 36 edges, 3 iterations, nothing extrapolated)
-        full, spent = cpu_reference_step(sc, 2, 1)
-        n_e = int(min(36, max(2, 2 * 15.0 / max(spent, 1e-3))))
-        n_it = BA_ITERS if n_e == 36 else 1
+        # the whole step (36 edges, 3 iterations, nothing extrapolated) when the host does it in <= 20 s,
+        # else a proportional sample
+        n_e, n_it = cpu_sample_plan(sc, 20.0)
         full, spent = cpu_reference_step(sc, n_e, n_it)
         line["cpu_baseline"] = {"value": 1.0 / full, "unit": "updates/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": "corr build+pyramid+lookup on %d/36 edges + %d/3 BA iterations "
