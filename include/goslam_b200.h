@@ -260,6 +260,22 @@ int goslam_sample_z(const float* rays_o, const float* rays_d, const float* bound
 int goslam_cvx_upsample(const float* data, const void* mask, int mask_dtype, float* out, int B,
                         int ht, int wd, int dim, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Factor-graph edge selection — FactorGraph.add_proximity_factors (src/factor_graph.py:384-450;
+ * every keyframe, src/frontend.py:58) without the per-candidate device->host syncs of its Python
+ * loops.  dist [(t-t0)*(t-t1)] f32 = DepthVideo.distance over the meshgrid of (t0..t-1) x (t1..t-1)
+ * (goslam_frame_distance), ii_old/jj_old [n_old] = edges the graph already holds (active, bad,
+ * inactive).  Writes the reference's edge list, in its order, to es_i/es_j [cap] (int64) and the
+ * number of edges to *num_edges (device int).  Greedy NMS stops once more than max_factors edges
+ * are listed; ties in distance are taken in index order.
+ *   cap >= edges of the local window + max(0, max_factors + 2) is always enough.
+ *   workspace: goslam_proximity_workspace_bytes(t0, t1, t). */
+size_t goslam_proximity_workspace_bytes(int t0, int t1, int t);
+int goslam_proximity_edges(const float* dist, int t0, int t1, int t, int rad, int nms, float thresh,
+                           int max_factors, int stereo, const int64_t* ii_old, const int64_t* jj_old,
+                           int n_old, int64_t* es_i, int64_t* es_j, int cap, int* num_edges,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* Training-only entry points of the reference module are exported for ABI completeness
  * and return GOSLAM_EUNSUPPORTED (inference path is torch.no_grad, src/slam.py:45). */
 int goslam_corr_index_backward(void);

@@ -14,6 +14,7 @@ What each fixture pins:
     neus.npz          InstantNeuS.forward (9 outputs)             src/InstantNeuS.py:295-370
     render_z.npz      Renderer.render_batch_ray z-sampling        src/render.py:99-171
     cvx_upsample.npz  cvx_upsample (f32 and f16 masks)            src/droid_net.py:9-23
+    proximity.npz     FactorGraph.add_proximity_factors edges     src/factor_graph.py:384-450
 Run:  python tests/golden/make_golden.py      (writes next to this file)
 """
 import importlib
@@ -265,11 +266,44 @@ def gen_cvx_upsample():
     np.savez_compressed(os.path.join(HERE, "cvx_upsample.npz"), **out)
 
 
+def gen_proximity():
+    """FactorGraph.add_proximity_factors (src/factor_graph.py:384-450) itself, with a stub video whose
+    distance() returns a prepared matrix; the edges handed to add_factors are the golden output."""
+    fg_mod = ref_import("src.factor_graph")
+    rng = np.random.default_rng(21)
+    cases = []
+    for (t0, t1, t, rad, nms, thresh, maxf, stereo, n_old) in [
+            (7, 0, 12, 2, 2, 16.0, 48, False, 6), (0, 0, 9, 2, 2, 16.0, 60, False, 0),
+            (10, 3, 22, 3, 1, 20.0, 40, True, 9), (4, 0, 10, 2, 2, 12.0, 14, False, 3)]:
+        ilen, jlen = t - t0, t - t1
+        dist = (rng.random(ilen * jlen) * 40).astype(np.float32)
+        dist[rng.random(ilen * jlen) < 0.1] = 150.0
+        old = rng.integers(0, t, size=(n_old, 2)).astype(np.int64)
+        cap = {}
+        g = fg_mod.FactorGraph.__new__(fg_mod.FactorGraph)
+        g.device = "cpu"
+        g.max_factors = maxf
+        g.ii, g.jj = torch.from_numpy(old[:, 0].copy()), torch.from_numpy(old[:, 1].copy())
+        g.ii_bad = g.jj_bad = g.ii_inac = g.jj_inac = torch.zeros(0, dtype=torch.long)
+        g.video = types.SimpleNamespace(counter=types.SimpleNamespace(value=t), stereo=stereo,
+                                        distance=lambda ii, jj, beta, _d=dist: torch.from_numpy(_d.copy()))
+        g.add_factors = lambda ii, jj, remove=False, _c=cap: _c.update(ii=ii.numpy().copy(), jj=jj.numpy().copy())
+        g.add_proximity_factors(t0, t1, rad=rad, nms=nms, thresh=thresh, remove=False)
+        cases.append(dict(params=np.array([t0, t1, t, rad, nms, maxf, int(stereo)], np.int64), thresh=np.float32(thresh),
+                          dist=dist, old=old, es=np.stack([cap["ii"], cap["jj"]], 1)))
+    out = {}
+    for n, c in enumerate(cases):
+        for k, v in c.items():
+            out["c%d_%s" % (n, k)] = v
+    out["n_cases"] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(HERE, "proximity.npz"), **out)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("needs /root/reference (build container only)")
     install_stubs()
-    which = sys.argv[1:] or ["corr_block", "reproject", "ba_torch", "neus", "render_z", "cvx_upsample"]
+    which = sys.argv[1:] or ["corr_block", "reproject", "ba_torch", "neus", "render_z", "cvx_upsample", "proximity"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)

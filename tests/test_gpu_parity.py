@@ -509,3 +509,53 @@ def test_cvx_upsample_golden_from_reference():
         np.testing.assert_allclose(droid_net.cvx_upsample(data, mask).cpu().numpy(), gold[tag + "_out_f32"], rtol=2e-6, atol=2e-7)
         np.testing.assert_allclose(droid_net.cvx_upsample(data, mask.half()).cpu().numpy(), gold[tag + "_out_f16mask"],
                                    rtol=0, atol=2.0 ** -11 * 1.2)
+
+
+# ------------------------------------------------------------------------------ graph bookkeeping
+def _prox_case(rng, t0, t1, t, n_old, frac_big=0.1, ties=False):
+    ilen, jlen = t - t0, t - t1
+    dist = (rng.random(ilen * jlen) * 40).astype(np.float32)
+    if ties:
+        dist = np.round(dist)                               # many equal distances
+    dist[rng.random(ilen * jlen) < frac_big] = 150.0
+    old = rng.integers(0, t, size=(n_old, 2)).astype(np.int64)
+    return dist, old
+
+
+@pytest.mark.parametrize("case", [
+    dict(t0=7, t1=0, t=12, rad=2, nms=2, thresh=16.0, maxf=48, stereo=False, n_old=6),
+    dict(t0=0, t1=0, t=9, rad=2, nms=2, thresh=16.0, maxf=60, stereo=False, n_old=0),
+    dict(t0=10, t1=3, t=22, rad=3, nms=1, thresh=20.0, maxf=40, stereo=True, n_old=9),
+    dict(t0=4, t1=0, t=10, rad=2, nms=2, thresh=12.0, maxf=14, stereo=False, n_old=3),
+    dict(t0=0, t1=0, t=120, rad=2, nms=2, thresh=16.0, maxf=1200, stereo=False, n_old=300),   # global-BA sized
+    dict(t0=5, t1=9, t=30, rad=2, nms=2, thresh=25.0, maxf=200, stereo=True, n_old=20),       # t1 > t0: negative columns
+    dict(t0=3, t1=0, t=14, rad=2, nms=3, thresh=30.0, maxf=-1, stereo=False, n_old=0),        # max_factors = -1
+    dict(t0=2, t1=0, t=40, rad=1, nms=0, thresh=18.0, maxf=500, stereo=False, n_old=10, ties=True),
+])
+def test_proximity_edges_match_reference_loops(case):
+    """goslam_proximity_edges == the reference's Python loops (oracle, itself pinned to the reference method):
+    same edges in the same order — edge-index parity, bit-exact."""
+    from goslam_b200 import graph
+    from oracle import graph_oracle
+    c = dict(case)
+    rng = np.random.default_rng(c["t"] * 31 + c["t0"])
+    dist, old = _prox_case(rng, c["t0"], c["t1"], c["t"], c["n_old"], ties=c.pop("ties", False))
+    want = graph_oracle.proximity_edges(dist, c["t0"], c["t1"], c["t"], c["rad"], c["nms"], c["thresh"], c["maxf"],
+                                        c["stereo"], old[:, 0], old[:, 1])
+    ii, jj = graph.proximity_edges(torch.from_numpy(dist).to(dev()), c["t0"], c["t1"], c["t"], c["rad"], c["nms"],
+                                   c["thresh"], c["maxf"], c["stereo"], torch.from_numpy(old[:, 0]).to(dev()),
+                                   torch.from_numpy(old[:, 1]).to(dev()))
+    got = torch.stack([ii, jj], 1).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
+def test_proximity_edges_golden_from_reference_method():
+    from goslam_b200 import graph
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "proximity.npz"))
+    for n in range(int(g["n_cases"])):
+        t0, t1, t, rad, nms, maxf, st = [int(x) for x in g["c%d_params" % n]]
+        old = g["c%d_old" % n]
+        ii, jj = graph.proximity_edges(torch.from_numpy(g["c%d_dist" % n]).to(dev()), t0, t1, t, rad, nms,
+                                       float(g["c%d_thresh" % n]), maxf, bool(st),
+                                       torch.from_numpy(old[:, 0].copy()).to(dev()), torch.from_numpy(old[:, 1].copy()).to(dev()))
+        np.testing.assert_array_equal(torch.stack([ii, jj], 1).cpu().numpy(), g["c%d_es" % n])

@@ -198,3 +198,16 @@ def test_cvx_upsample_oracle_matches_reference_function():
         np.testing.assert_allclose(upsample_oracle.cvx_upsample(data, mask).numpy(), g[tag + "_out_f32"], rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(upsample_oracle.cvx_upsample(data, mask.half()).numpy(), g[tag + "_out_f16mask"],
                                    rtol=1e-6, atol=1e-7)
+
+
+def test_proximity_edges_oracle_matches_reference_method():
+    """oracle/graph_oracle.py against the edges FactorGraph.add_proximity_factors itself produced
+    (src/factor_graph.py:384-450, run by tests/golden/make_golden.py with a stub video)."""
+    from oracle import graph_oracle
+    g = _load("proximity.npz")
+    for n in range(int(g["n_cases"])):
+        t0, t1, t, rad, nms, maxf, st = [int(x) for x in g["c%d_params" % n]]
+        old = g["c%d_old" % n]
+        es = graph_oracle.proximity_edges(g["c%d_dist" % n], t0, t1, t, rad, nms, float(g["c%d_thresh" % n]), maxf,
+                                          bool(st), old[:, 0], old[:, 1])
+        np.testing.assert_array_equal(es, g["c%d_es" % n])
