@@ -24,8 +24,8 @@ __device__ __forceinline__ unsigned g_f2ord(float f) {      // order-preserving,
 
 struct ProxArgs {
   const float* dist; const int64_t* ii_old; const int64_t* jj_old; int n_old;
-  int t0, t1, t, rad, nms, max_factors, stereo;
-  float thresh;
+  int t0, t1, t, rad, nms, max_factors, stereo, jfloor;
+  float thresh, dmax;
   float* dm;                    // [ilen*jlen] working copy
   unsigned long long* keys;     // [pow2 >= candidates]
   int* counters;                // [0] candidates, [1] edges written
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kGT) proximity_kernel(const ProxArgs a) {
     float v = a.dist[k];
     const int i = a.t0 + k / jlen, j = a.t1 + k % jlen;
     if (i - a.rad < j) v = inf;
-    if (v > 100.0f) v = inf;
+    if (v > a.dmax) v = inf;
     a.dm[k] = v;
   }
   if (tid == 0) { a.counters[0] = 0; a.counters[1] = 0; }
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kGT) proximity_kernel(const ProxArgs a) {
   // ---- C: local-window edges (:412-425); their positions in `es` are known in closed form ----
   for (int i = a.t0 + tid; i < a.t; i += kGT) {
     int off = 0;
-    for (int q = a.t0; q < i; ++q) off += (a.stereo ? 1 : 0) + 2 * (q - max(q - a.rad, 0));
+    for (int q = a.t0; q < i; ++q) off += (a.stereo ? 1 : 0) + 2 * (q - min(q, max(q - a.rad, a.jfloor)));
     const int di = i - a.t0;
     if (a.stereo) {
       if (off < a.cap) { a.es_i[off] = i; a.es_j[off] = i; }
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kGT) proximity_kernel(const ProxArgs a) {
       if (dj < 0) dj += jlen;
       a.dm[di * jlen + dj] = inf;
     }
-    for (int j = max(i - a.rad, 0); j < i; ++j) {
+    for (int j = max(i - a.rad, a.jfloor); j < i; ++j) {
       if (off + 1 < a.cap) { a.es_i[off] = i; a.es_j[off] = j; a.es_i[off + 1] = j; a.es_j[off + 1] = i; }
       off += 2;
       const int dj = j - a.t1;
@@ -157,15 +157,16 @@ size_t goslam_proximity_workspace_bytes(int t0, int t1, int t) {
 }
 
 int goslam_proximity_edges(const float* dist, int t0, int t1, int t, int rad, int nms, float thresh,
-                           int max_factors, int stereo, const int64_t* ii_old, const int64_t* jj_old,
+                           float dmax, int jfloor, int max_factors, int stereo, const int64_t* ii_old,
+                           const int64_t* jj_old,
                            int n_old, int64_t* es_i, int64_t* es_j, int cap, int* num_edges,
                            void* workspace, size_t workspace_bytes, void* stream) {
-  if (t <= t0 || t <= t1 || t0 < 0 || t1 < 0 || rad < 0 || nms < 0 || n_old < 0 || cap < 0)
+  if (t <= t0 || t <= t1 || t0 < 0 || t1 < 0 || rad < 0 || nms < 0 || n_old < 0 || cap < 0 || jfloor < 0)
     return GOSLAM_EINVAL;
   const int ilen = t - t0, jlen = t - t1;
   if ((long long)ilen * jlen > (1 << 24)) return GOSLAM_EINVAL;
   // the reference would raise IndexError for a column index below -jlen (src/factor_graph.py:423)
-  const int jmin = (t0 - rad > 0 ? t0 - rad : 0);
+  const int jmin = (t0 - rad > jfloor ? t0 - rad : jfloor);
   if (rad > 0 && jmin - t1 < -jlen) return GOSLAM_EINVAL;
   if (stereo && t0 - t1 < -jlen) return GOSLAM_EINVAL;
   const size_t need = goslam_proximity_workspace_bytes(t0, t1, t);
@@ -176,7 +177,7 @@ int goslam_proximity_edges(const float* dist, int t0, int t1, int t, int rad, in
   ProxArgs a{};
   a.dist = dist; a.ii_old = ii_old; a.jj_old = jj_old; a.n_old = n_old;
   a.t0 = t0; a.t1 = t1; a.t = t; a.rad = rad; a.nms = nms; a.max_factors = max_factors; a.stereo = stereo ? 1 : 0;
-  a.thresh = thresh;
+  a.thresh = thresh; a.dmax = dmax; a.jfloor = jfloor;
   char* w = reinterpret_cast<char*>(workspace);
   a.dm = reinterpret_cast<float*>(w);
   a.keys = reinterpret_cast<unsigned long long*>(w + gs_align(n * sizeof(float)));

@@ -15,6 +15,7 @@ What each fixture pins:
     render_z.npz      Renderer.render_batch_ray z-sampling        src/render.py:99-171
     cvx_upsample.npz  cvx_upsample (f32 and f16 masks)            src/droid_net.py:9-23
     proximity.npz     FactorGraph.add_proximity_factors edges     src/factor_graph.py:384-450
+    backend_edges.npz Backend.ba edge selection (loop=False)      src/backend.py:25-99
 Run:  python tests/golden/make_golden.py      (writes next to this file)
 """
 import importlib
@@ -299,11 +300,39 @@ def gen_proximity():
     np.savez_compressed(os.path.join(HERE, "proximity.npz"), **out)
 
 
+def gen_backend_edges():
+    """Backend.ba (src/backend.py:25-128) with loop=False and stubbed graph/video: the edges handed to
+    graph.add_factors are the golden output (None when it returns early)."""
+    be_mod = ref_import("src.backend")
+    rng = np.random.default_rng(33)
+    out, n = {}, 0
+    for (ts, te, radius, nms, thresh, maxf, stereo) in [(0, 14, 2, 2, 18.0, 96, False), (3, 25, 3, 1, 25.0, 80, True),
+                                                       (0, 3, 2, 2, 10.0, 20, False), (5, 30, 1, 2, 15.0, 30, False)]:
+        ilen = te - ts
+        dist = (rng.random(ilen * ilen) * 40).astype(np.float32)
+        cap = {}
+        b = be_mod.Backend.__new__(be_mod.Backend)
+        b.beta, b.device = 0.75, "cpu"
+        b.video = types.SimpleNamespace(stereo=stereo, dirty=torch.zeros(te + 1, dtype=torch.bool),
+                                        distance=lambda ii, jj, beta, _d=dist: torch.from_numpy(_d.copy()))
+        graph = types.SimpleNamespace(ii=[], update_lowmem=lambda **k: None, clear_edges=lambda: None,
+                                      add_factors=lambda ii, jj, remove=False, _c=cap: _c.update(ii=ii.numpy().copy(), jj=jj.numpy().copy()))
+        b.ba(ts, te, 4, graph, nms, radius, thresh, maxf)
+        out["b%d_params" % n] = np.array([ts, te, radius, nms, maxf, int(stereo)], np.int64)
+        out["b%d_thresh" % n] = np.float32(thresh)
+        out["b%d_dist" % n] = dist
+        out["b%d_es" % n] = np.stack([cap["ii"], cap["jj"]], 1) if cap else np.zeros((0, 2), np.int64)
+        out["b%d_early" % n] = np.int64(0 if cap else 1)
+        n += 1
+    out["n_cases"] = np.int64(n)
+    np.savez_compressed(os.path.join(HERE, "backend_edges.npz"), **out)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("needs /root/reference (build container only)")
     install_stubs()
-    which = sys.argv[1:] or ["corr_block", "reproject", "ba_torch", "neus", "render_z", "cvx_upsample", "proximity"]
+    which = sys.argv[1:] or ["corr_block", "reproject", "ba_torch", "neus", "render_z", "cvx_upsample", "proximity", "backend_edges"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)

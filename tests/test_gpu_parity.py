@@ -559,3 +559,25 @@ def test_proximity_edges_golden_from_reference_method():
                                        float(g["c%d_thresh" % n]), maxf, bool(st),
                                        torch.from_numpy(old[:, 0].copy()).to(dev()), torch.from_numpy(old[:, 1].copy()).to(dev()))
         np.testing.assert_array_equal(torch.stack([ii, jj], 1).cpu().numpy(), g["c%d_es" % n])
+
+
+def test_backend_edges_golden_and_oracle():
+    """Backend.ba's edge selection (loop=False): device == the reference method (golden) == the oracle,
+    including the early return with fewer than 3 edges."""
+    from goslam_b200 import graph
+    from oracle import graph_oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "backend_edges.npz"))
+    for n in range(int(g["n_cases"])):
+        ts, te, rad, nms, maxf, st = [int(x) for x in g["b%d_params" % n]]
+        got = graph.backend_edges(torch.from_numpy(g["b%d_dist" % n]).to(dev()), ts, te, rad, nms,
+                                  float(g["b%d_thresh" % n]), maxf, bool(st))
+        if int(g["b%d_early" % n]):
+            assert got is None
+        else:
+            np.testing.assert_array_equal(torch.stack(got, 1).cpu().numpy(), g["b%d_es" % n])
+    rng = np.random.default_rng(8)
+    dist = (rng.random(90 * 90) * 50).astype(np.float32)
+    want = graph_oracle.backend_edges(dist, 10, 100, 2, 2, 22.0, 700, False)
+    got = graph.backend_edges(torch.from_numpy(dist).to(dev()), 10, 100, 2, 2, 22.0, 700, False)
+    np.testing.assert_array_equal(torch.stack(got, 1).cpu().numpy(), want)
+    assert graph.backend_edges(torch.from_numpy(dist[:1]).to(dev()), 4, 5, 2, 2, 22.0, 10, False) is None

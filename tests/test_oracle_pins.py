@@ -211,3 +211,16 @@ def test_proximity_edges_oracle_matches_reference_method():
         es = graph_oracle.proximity_edges(g["c%d_dist" % n], t0, t1, t, rad, nms, float(g["c%d_thresh" % n]), maxf,
                                           bool(st), old[:, 0], old[:, 1])
         np.testing.assert_array_equal(es, g["c%d_es" % n])
+
+
+def test_backend_edges_oracle_matches_reference_method():
+    """oracle/graph_oracle.backend_edges against Backend.ba's own edge list (src/backend.py:25-99, loop=False)."""
+    from oracle import graph_oracle
+    g = _load("backend_edges.npz")
+    for n in range(int(g["n_cases"])):
+        ts, te, rad, nms, maxf, st = [int(x) for x in g["b%d_params" % n]]
+        es = graph_oracle.backend_edges(g["b%d_dist" % n], ts, te, rad, nms, float(g["b%d_thresh" % n]), maxf, bool(st))
+        if int(g["b%d_early" % n]):
+            assert es is None
+        else:
+            np.testing.assert_array_equal(es, g["b%d_es" % n])
