@@ -193,6 +193,7 @@ struct TcParams {
   int aligned;                // w % 16 == 0 && h % 8 == 0: every store is a whole aligned sector run
   int experiment;             // profiling only: 1 = no output writes
   int bulk;                   // tiled: pooled levels leave through bulk (TMA) stores, asynchronously
+  int pingpong;               // tiled: the two epilogue groups take turns in their level-0 store sections
 };
 
 // ---- packed fp16 rows live in registers as uint32 pairs (lo = even column) ----
@@ -360,6 +361,8 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
     const int h1 = p.h >> 1, w1 = p.w >> 1, h2 = p.h >> 2, w2 = p.w >> 2, h3 = p.h >> 3, w3 = p.w >> 3;
     const bool wr = p.experiment != 1;
     int tph = 0, tile = 0;
+    // ordered store sections (ping-pong): named barrier 4+g = "group g may store"; 256 waiters + 256 arrivers
+    if (p.pingpong && group == 1) asm volatile("bar.arrive 4, 512;" ::: "memory");
 #ifdef GOSLAM_TC_PROBE
     long long pr_wait = 0, pr_tiles = 0, pr_bar1 = 0, pr_wo = 0, pr_bar2 = 0, pr_t0 = clock64();
     const bool pr_on = (etid == 0 || etid == 256) && blockIdx.x == 0;
@@ -408,6 +411,10 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
           __syncwarp();
           if (lane == 0) mbar_arrive(&tm_empty[ts]);
           const int ty = 2 * yb + half;
+          if (p.pingpong) {
+            if (group == 0) asm volatile("bar.sync 4, 512;" ::: "memory");
+            else asm volatile("bar.sync 5, 512;" ::: "memory");
+          }
           if (src_ok && ty < p.h4_0) {
             unsigned char* dst = reinterpret_cast<unsigned char*>(p.lvl[0]) +
                                  ((plane_id * p.h4_0 + ty) * p.w4_0 + xb * 4) * 32LL;
@@ -418,6 +425,10 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                              "r"(hr[0][2 * t]), "r"(hr[0][2 * t + 1]), "r"(hr[1][2 * t]), "r"(hr[1][2 * t + 1]),
                              "r"(hr[2][2 * t]), "r"(hr[2][2 * t + 1]), "r"(hr[3][2 * t]), "r"(hr[3][2 * t + 1])
                              : "memory");
+          }
+          if (p.pingpong) {                          // the other group's turn
+            if (group == 0) asm volatile("bar.arrive 5, 512;" ::: "memory");
+            else asm volatile("bar.arrive 4, 512;" ::: "memory");
           }
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
@@ -721,6 +732,7 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
   // experiment switch: measured 278 us with bulk stores vs 273 us with plain stores on config 2 — the
   // limit is past the SM (L2 / fabric), so the TMA path is off by default
   { const char* e = getenv("GOSLAM_TC_BULK"); p.bulk = (p.tiled && e && atoi(e) == 1) ? 1 : 0; }
+  { const char* e = getenv("GOSLAM_TC_PINGPONG"); p.pingpong = (p.tiled && e && atoi(e) == 1) ? 1 : 0; }
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(corr_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
