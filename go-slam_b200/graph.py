@@ -62,3 +62,16 @@ def proximity_edges(dist, t0, t1, t, rad, nms, thresh, max_factors, stereo, ii_o
     _lib.check(rc, "proximity_edges")
     n = int(num.item())            # the one host sync (the reference builds its edge tensor on the host here)
     return es_i[:n], es_j[:n]
+
+
+def filter_repeated_edges(ii, jj, ii_active, jj_active, ii_inactive, jj_inactive):
+    """FactorGraph.__filter_repeated_edges (src/factor_graph.py:44-54): drop the candidate edges the
+    graph already holds (active or inactive), keeping the order of the rest.  The reference builds a
+    Python set with two .item() syncs per stored edge and tests every candidate against it; here it is
+    a key comparison on the device (key = i * 2^32 + j), the only sync being the boolean compaction."""
+    dev = ii.device
+    key = (ii.long() << 32) | jj.long()
+    old = torch.cat([(ii_active.to(dev).long() << 32) | jj_active.to(dev).long(),
+                     (ii_inactive.to(dev).long() << 32) | jj_inactive.to(dev).long()])
+    keep = ~torch.isin(key, old)
+    return ii[keep], jj[keep]

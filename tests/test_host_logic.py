@@ -153,3 +153,19 @@ def test_corr_pool_slot_bookkeeping():
         pool.alloc(2)
     pool.release([0, 2, 1, 3])
     assert pool.free_slots == 5 and sorted(pool.alloc(5)) == [0, 1, 2, 3, 4]
+
+
+def test_filter_repeated_edges_matches_python_set():
+    """graph.filter_repeated_edges is device-agnostic torch plumbing: check it on CPU tensors against
+    the reference's Python-set formulation (src/factor_graph.py:44-54)."""
+    from goslam_b200 import graph
+    from oracle import graph_oracle
+    g = torch.Generator().manual_seed(4)
+    ii, jj = torch.randint(0, 12, (60,), generator=g), torch.randint(0, 12, (60,), generator=g)
+    ia, ja = torch.randint(0, 12, (25,), generator=g), torch.randint(0, 12, (25,), generator=g)
+    ib, jb = torch.randint(0, 12, (10,), generator=g), torch.randint(0, 12, (10,), generator=g)
+    got = graph.filter_repeated_edges(ii, jj, ia, ja, ib, jb)
+    want = graph_oracle.filter_repeated_edges(ii.numpy(), jj.numpy(), ia.numpy(), ja.numpy(), ib.numpy(), jb.numpy())
+    assert got[0].tolist() == want[0].tolist() and got[1].tolist() == want[1].tolist()
+    e = torch.zeros(0, dtype=torch.long)
+    assert graph.filter_repeated_edges(ii, jj, e, e, e, e)[0].tolist() == ii.tolist()
