@@ -581,3 +581,35 @@ def test_backend_edges_golden_and_oracle():
     got = graph.backend_edges(torch.from_numpy(dist).to(dev()), 10, 100, 2, 2, 22.0, 700, False)
     np.testing.assert_array_equal(torch.stack(got, 1).cpu().numpy(), want)
     assert graph.backend_edges(torch.from_numpy(dist[:1]).to(dev()), 4, 5, 2, 2, 22.0, 10, False) is None
+
+
+# ------------------------------------------------------------------------------ degenerate inputs
+def test_degenerate_inputs_do_not_crash():
+    """empty edge lists / ray batches and all-masked graphs go through every entry point cleanly."""
+    from goslam_b200 import droid_backends, graph, render
+    from goslam_b200.modules import CorrBlock
+    from goslam_b200.modules.corr import CorrPool, fmaps_to_kmajor
+    sc, targets, weights, eta = _ba_case(num_kf=5, ht=9, wd=13, rgbd=True)
+    e = torch.zeros(0, dtype=torch.long, device=dev())
+    poses, disps = sc["poses"].clone().to(dev()), sc["disps"].clone().to(dev())
+    # BA with no edges: the damped system is diagonal with a zero right-hand side -> zero pose step, and the
+    # depth update is the pure sensor-prior step
+    dx, dz, status = droid_backends.ba(poses, disps, sc["intrinsics"][0].to(dev()).contiguous(), sc["disps_sens"].to(dev()),
+                                       torch.zeros(0, 2, 9, 13, device=dev()), torch.zeros(0, 2, 9, 13, device=dev()),
+                                       eta[:4].to(dev()).contiguous(), e, e, 1, 5, 2, 1e-4, 0.1, False, return_status=True)
+    assert status.cpu().tolist() == [0, 0] and float(dx.abs().max()) == 0.0
+    assert torch.equal(poses.cpu(), sc["poses"]) and torch.isfinite(disps).all()
+    # correlation: empty blocks
+    fm = torch.randn(3, 1, 128, 16, 16).half().to(dev())
+    km = fmaps_to_kmajor(fm)
+    pool = CorrPool(4, 16, 16, device=dev())
+    blk = CorrBlock.from_video(km, e, e, 16, 16, pool=pool)
+    assert blk(torch.zeros(1, 0, 16, 16, 2, device=dev())).shape == (1, 0, 196, 16, 16) and pool.free_slots == 4
+    assert droid_backends.frame_distance(poses, disps, sc["intrinsics"][0].to(dev()).contiguous(), e, e, 0.3).numel() == 0
+    # renderer: empty ray batch
+    z, d = render.sample_z(torch.zeros(0, 3, device=dev()), torch.zeros(0, 3, device=dev()),
+                           torch.tensor([[-1.0, 1.0]] * 3), torch.zeros(0, device=dev()), 24, 48)
+    assert z.shape == (0, 72) and d.shape == (0, 72)
+    # graph: nothing below the threshold -> only the local-window edges
+    ii, jj = graph.proximity_edges(torch.full((36,), 1e9, device=dev()), 0, 0, 6, 2, 2, 16.0, 48, False, e, e)
+    assert ii.numel() == graph.local_edge_count(0, 6, 2, False)
