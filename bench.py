@@ -142,13 +142,14 @@ class Window:
         self.corr = CorrBlock.from_video(km, self.d["ii"], self.d["jj"], HT, WD, pool=self.pool)
         return self.corr
 
-    def step(self):
+    def step(self, reset=True):
         from goslam_b200 import droid_backends
         from goslam_b200.modules import CorrBlock
         from goslam_b200.modules.corr import fmaps_to_kmajor
         d = self.d
-        d["poses"].copy_(self.poses0)           # restart from the same state every step
-        d["disps"].copy_(self.disps0)
+        if reset:                               # device-resident loop: restart from the same state every step
+            d["poses"].copy_(self.poses0)       # (the end-to-end loop gets fresh inputs from the host instead)
+            d["disps"].copy_(self.disps0)
         ii, jj = d["ii"], d["jj"]
         # FactorGraph.add_factors' volume, video-level: K-major re-layout of the window's feature
         # maps (per keyframe, redone every step here) + on-device edge -> frame indexing
@@ -169,10 +170,25 @@ class Window:
         of a double buffer, so the transfer of update i+1 overlaps the kernels of update i (each
         step still waits for ITS inputs and its result is read back)."""
         if not hasattr(self, "_e2e"):
-            self._e2e = dict(copy=torch.cuda.Stream(self.dev), bufs=[None, None], ready=[None, None],
-                             done=[None, None], parity=0)
+            # all inputs of a step live in ONE pinned host block and one device block per buffer half:
+            # one H2D copy per step instead of ten (the end-to-end loop is otherwise host-bound)
+            offs, total = {}, 0
+            for k in self.E2E_KEYS:
+                offs[k] = total
+                total += (self.host[k].numel() * self.host[k].element_size() + 255) // 256 * 256
+            packed = torch.empty(total, dtype=torch.uint8).pin_memory()
+
+            def views(block):
+                return {k: block[offs[k]:offs[k] + self.host[k].numel() * self.host[k].element_size()]
+                        .view(self.host[k].dtype).view(self.host[k].shape) for k in self.E2E_KEYS}
+            hv = views(packed)
+            for k in self.E2E_KEYS:
+                hv[k].copy_(self.host[k])
+            self._e2e = dict(copy=torch.cuda.Stream(self.dev), bufs=[None, None], blocks=[None, None], packed=packed,
+                             ready=[None, None], done=[None, None], parity=0)
             for b in range(2):
-                self._e2e["bufs"][b] = {k: torch.empty_like(self.d[k]) for k in self.E2E_KEYS}
+                self._e2e["blocks"][b] = torch.empty(total, dtype=torch.uint8, device=self.dev)
+                self._e2e["bufs"][b] = views(self._e2e["blocks"][b])
         st = self._e2e
         cur = st["parity"]
         main = torch.cuda.current_stream(self.dev)
@@ -181,10 +197,8 @@ class Window:
         main.wait_event(st["ready"][cur])
         for k in self.E2E_KEYS:
             self.d[k] = st["bufs"][cur][k]
-        self.poses0.copy_(self.d["poses"])
-        self.disps0.copy_(self.d["disps"])
         self._prefetch(cur ^ 1)                           # next update's inputs, overlapped
-        self.step()
+        self.step(reset=False)
         out_pinned[0].copy_(self.d["poses"], non_blocking=True)
         out_pinned[1].copy_(self.d["disps"], non_blocking=True)
         st["done"][cur] = torch.cuda.Event()
@@ -196,8 +210,7 @@ class Window:
         with torch.cuda.stream(st["copy"]):
             if st["done"][b] is not None:                 # buffer b must not be in use by an older step
                 st["copy"].wait_event(st["done"][b])
-            for k in self.E2E_KEYS:
-                st["bufs"][b][k].copy_(self.host[k], non_blocking=True)
+            st["blocks"][b].copy_(st["packed"], non_blocking=True)
             st["ready"][b] = torch.cuda.Event()
             st["ready"][b].record(st["copy"])
 
