@@ -418,13 +418,13 @@ def main():
         renderer = render_mod.Renderer(rcfg, None, types.SimpleNamespace(H=512, W=512, fx=460.8, fy=460.8, cx=256.0, cy=256.0))
         gt_depth = 0.5 + 2.5 * torch.rand(RAYS, generator=torch.Generator().manual_seed(43 + rank))
         hp = [rays[0].pin_memory(), rays[1].pin_memory(), gt_depth.pin_memory()]
-        keep = {}
+        keep = {"color": torch.empty(RAYS, 3).pin_memory(), "depth": torch.empty(RAYS, 1).pin_memory()}
 
         def render_e2e():
             ro, rdir, gd = [x.to(dev, non_blocking=True) for x in hp]
             out = renderer.render_batch_ray(ro, rdir, net, None, device=dev, gt_depth=gd)
             for k in ("color", "depth"):
-                keep[k] = out[k].to("cpu", non_blocking=True)
+                keep[k].copy_(out[k].reshape(keep[k].shape), non_blocking=True)
         ms_re = max_over_ranks(time_gpu(render_e2e, max(5, args.steps // 2), 3, barrier), world)
         rbytes = RAYS * (512.0 * SAMPLES + 1216.0)
         line["render"] = {"metric": "rendered Mrays/s", "value": world * RAYS / ms_r / 1e3, "unit": "Mrays/s",
