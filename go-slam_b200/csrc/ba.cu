@@ -95,9 +95,14 @@ size_t ba_layout(const BaDims& d, void* base, size_t cap, BaWs* ws) {
 // prefix sum over a presence bitmap (frame order == sorted order, as torch::_unique gives).
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-ba_prep_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, BaDims d, BaWs ws) {
+ba_prep_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, BaDims d, BaWs ws, int zero) {
   extern __shared__ int sm[];          // [num] scratch
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (zero) {                          // single-kernel driver: reduced system and grid-barrier counter start at 0
+    const size_t nsys = (size_t)d.n * d.n + d.n;
+    for (size_t i = tid; i < nsys; i += nt) ws.sys[i] = 0.0;
+    if (tid == 0) ws.counts[3] = 0;
+  }
   int* present = sm;
   for (int f = tid; f < d.num; f += nt) present[f] = (f >= d.t0 && f < d.t1) ? 1 : 0;
   __syncthreads();
@@ -941,6 +946,10 @@ ba_persistent_kernel(float* poses, float* disps, BaIn in, BaDims d, BaWs ws, int
   const int units = M * nwt;
   const int ufirst = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, ustep = (kTP / 32) * gridDim.x;
   const size_t nsys = (size_t)d.n * d.n + d.n;
+  if (dz_out) {                      // rows of frames without a depth update stay 0 (first written after 3 barriers)
+    const size_t ndz = (size_t)d.num * d.hw;
+    for (size_t i = (size_t)blockIdx.x * kTP + threadIdx.x; i < ndz; i += (size_t)gridDim.x * kTP) dz_out[i] = 0.f;
+  }
   for (int it = 0; it < iterations; ++it) {
     BA_PROBE(0);
 #ifdef GOSLAM_BA_PROBE
@@ -1021,7 +1030,7 @@ int launch_phase1(const float* poses, const float* disps, const float* intr,
                   const BaDims& d, const BaWs& ws, int motion_only, bool prep, cudaStream_t st) {
   const BaIn in{poses, disps, intr, disps_sens, targets, weights, eta, eta_rows, ii, jj};
   if (prep) {
-    ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws);
+    ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws, 0);
     GS_CHECK_LAUNCH();
   }
   cudaMemsetAsync(ws.sys, 0, ((size_t)d.n * d.n + d.n) * sizeof(double), st);
@@ -1099,7 +1108,6 @@ int goslam_ba(float* poses, float* disps, const float* intrinsics, const float* 
   const size_t need = ba_layout(d, workspace, workspace_bytes, &ws);
   if (workspace == nullptr || need > workspace_bytes) return GOSLAM_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dz_out) cudaMemsetAsync(dz_out, 0, (size_t)num * d.hw * sizeof(float), st);
   static const bool multi_kernel = [] {
     const char* e = getenv("GOSLAM_BA_MULTIKERNEL");
     return e && e[0] == '1';
@@ -1120,11 +1128,11 @@ int goslam_ba(float* poses, float* disps, const float* intrinsics, const float* 
       blocks_per_sm = (!coop || occ < 1) ? 0 : (occ > want ? want : occ);
     }
     if (blocks_per_sm > 0) {
-      ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws);
+      // two launches per call: the table kernel (which also zeroes the reduced system and the barrier
+      // counter) and the cooperative kernel (which zeroes dz_out itself)
+      ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws, 1);
       GS_CHECK_LAUNCH();
       unsigned* barrier = reinterpret_cast<unsigned*>(ws.counts + 3);
-      cudaMemsetAsync(barrier, 0, sizeof(unsigned), st);
-      cudaMemsetAsync(ws.sys, 0, ((size_t)d.n * d.n + d.n) * sizeof(double), st);
       BaIn in{poses, disps, intrinsics, disps_sens, targets, weights, eta, eta_rows, ii, jj};
       BaDims dd = d;
       BaWs wsv = ws;
@@ -1136,6 +1144,7 @@ int goslam_ba(float* poses, float* disps, const float* intrinsics, const float* 
       return GOSLAM_OK;
     }
   }
+  if (dz_out) cudaMemsetAsync(dz_out, 0, (size_t)num * d.hw * sizeof(float), st);
   for (int it = 0; it < iterations; ++it) {
     int rc = launch_phase1(poses, disps, intrinsics, disps_sens, targets, weights, eta, eta_rows,
                            ii, jj, d, ws, motion_only, it == 0, st);
