@@ -652,14 +652,30 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
 // `fmap / 4.0` on the half tensor (src/modules/corr.py:71-72): exact for normal values.
 __global__ void __launch_bounds__(256)
 to_kmajor_kernel(const __half* __restrict__ in, __half* __restrict__ out, int hw) {
-  __shared__ __half tile[kD][64 + 2];
+  __shared__ __align__(16) __half tile[kD][64 + 2];
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * 64;
   const __half* src = in + (size_t)n * kD * hw;
   const __half q = __float2half_rn(0.25f);
-  for (int idx = threadIdx.x; idx < kD * 64; idx += 256) {
-    const int k = idx / 64, pp = idx % 64;
-    tile[k][pp] = (p0 + pp < hw) ? __hmul(src[(size_t)k * hw + p0 + pp], q) : __half(0.f);
+  if ((hw & 7) == 0 && p0 + 64 <= hw) {
+    // 16-byte loads (8 pixels of one channel), scaled as half2, stored as 4 words
+    const __half2 q2 = __half2half2(q);
+    for (int idx = threadIdx.x; idx < kD * 8; idx += 256) {
+      const int k = idx >> 3, pp = (idx & 7) * 8;
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)k * hw + p0 + pp));
+      __half2* h = reinterpret_cast<__half2*>(&v);
+      uint32_t* dstw = reinterpret_cast<uint32_t*>(&tile[k][pp]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __half2 r = __hmul2(h[u], q2);
+        dstw[u] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < kD * 64; idx += 256) {
+      const int k = idx / 64, pp = idx % 64;
+      tile[k][pp] = (p0 + pp < hw) ? __hmul(src[(size_t)k * hw + p0 + pp], q) : __half(0.f);
+    }
   }
   __syncthreads();
   __half* dst = out + ((size_t)n * hw + p0) * kD;
