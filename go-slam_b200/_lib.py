@@ -70,7 +70,7 @@ SIGNATURES = {
     "goslam_sample_z": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "goslam_cvx_upsample": (c_int, [c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_void_p]),
     "goslam_proximity_workspace_bytes": (c_size_t, [c_int] * 3),
-    "goslam_proximity_edges": (c_int, [c_void_p] + [c_int] * 5 + [c_float, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
+    "goslam_proximity_edges": (c_int, [c_void_p] + [c_int] * 5 + [c_float, c_float, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                                                c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                                                c_size_t, c_void_p]),
     "goslam_corr_index_backward": (c_int, []),

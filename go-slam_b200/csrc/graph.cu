@@ -24,7 +24,7 @@ __device__ __forceinline__ unsigned g_f2ord(float f) {      // order-preserving,
 
 struct ProxArgs {
   const float* dist; const int64_t* ii_old; const int64_t* jj_old; int n_old;
-  int t0, t1, t, rad, nms, max_factors, stereo, jfloor;
+  int t0, t1, t, rad, nms, max_factors, stereo, jfloor, loop;
   float thresh, dmax;
   float* dm;                    // [ilen*jlen] working copy
   unsigned long long* keys;     // [pow2 >= candidates]
@@ -128,11 +128,30 @@ __global__ void __launch_bounds__(kGT) proximity_kernel(const ProxArgs a) {
       const int di = k / jlen, dj = k % jlen;
       if (dmv[k] > a.thresh) continue;                  // suppressed meanwhile
       if (n_es > a.max_factors) break;
-      if (tid == 0 && n_es + 1 < a.cap) {
+      if (a.loop) {
+        // loop-closure candidates (src/backend.py:81-91): the 3x3 neighbourhood of (i, j) votes with the RAW
+        // distances; if more than half of the 9 cells are below the threshold, every such cell off the
+        // diagonal becomes an edge, in row-major (si, sj) order
         const int i = a.t0 + di, j = a.t1 + dj;
-        a.es_i[n_es] = i; a.es_j[n_es] = j; a.es_i[n_es + 1] = j; a.es_j[n_es + 1] = i;
+        const int si = i - 1 + tid / 3, sj = j - 1 + tid % 3;
+        const bool in_rng = tid < 9 && si >= max(i - 1, a.t0) && si < min(i + 2, a.t) &&
+                            sj >= max(j - 1, a.t1) && sj < min(j + 2, a.t);
+        const bool vote = in_rng && a.dist[(si - a.t0) * jlen + (sj - a.t1)] <= a.thresh;
+        const unsigned votes = __ballot_sync(0xffffffffu, vote);
+        if (__popc(votes) > 4) {                       // int(9 * 0.5) = 4
+          const bool take = vote && si != sj;
+          const unsigned takes = __ballot_sync(0xffffffffu, take);
+          const int pos = n_es + __popc(takes & ((1u << tid) - 1u));
+          if (take && pos < a.cap) { a.es_i[pos] = si; a.es_j[pos] = sj; }
+          n_es += __popc(takes);
+        }
+      } else {
+        if (tid == 0 && n_es + 1 < a.cap) {
+          const int i = a.t0 + di, j = a.t1 + dj;
+          a.es_i[n_es] = i; a.es_j[n_es] = j; a.es_i[n_es + 1] = j; a.es_j[n_es + 1] = i;
+        }
+        n_es += 2;
       }
-      n_es += 2;
       int r0, r1, c0, c1;
       box_bounds(di, dj, a.nms, ilen, jlen, r0, r1, c0, c1);
       const int bw = c1 - c0, cells = (r1 - r0) * bw;
@@ -157,8 +176,8 @@ size_t goslam_proximity_workspace_bytes(int t0, int t1, int t) {
 }
 
 int goslam_proximity_edges(const float* dist, int t0, int t1, int t, int rad, int nms, float thresh,
-                           float dmax, int jfloor, int max_factors, int stereo, const int64_t* ii_old,
-                           const int64_t* jj_old,
+                           float dmax, int jfloor, int loop, int max_factors, int stereo,
+                           const int64_t* ii_old, const int64_t* jj_old,
                            int n_old, int64_t* es_i, int64_t* es_j, int cap, int* num_edges,
                            void* workspace, size_t workspace_bytes, void* stream) {
   if (t <= t0 || t <= t1 || t0 < 0 || t1 < 0 || rad < 0 || nms < 0 || n_old < 0 || cap < 0 || jfloor < 0)
@@ -177,7 +196,7 @@ int goslam_proximity_edges(const float* dist, int t0, int t1, int t, int rad, in
   ProxArgs a{};
   a.dist = dist; a.ii_old = ii_old; a.jj_old = jj_old; a.n_old = n_old;
   a.t0 = t0; a.t1 = t1; a.t = t; a.rad = rad; a.nms = nms; a.max_factors = max_factors; a.stereo = stereo ? 1 : 0;
-  a.thresh = thresh; a.dmax = dmax; a.jfloor = jfloor;
+  a.thresh = thresh; a.dmax = dmax; a.jfloor = jfloor; a.loop = loop ? 1 : 0;
   char* w = reinterpret_cast<char*>(workspace);
   a.dm = reinterpret_cast<float*>(w);
   a.keys = reinterpret_cast<unsigned long long*>(w + gs_align(n * sizeof(float)));

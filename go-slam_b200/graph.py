@@ -24,17 +24,20 @@ def local_edge_count(t0, t, rad, stereo, jfloor=0):
     return sum((1 if stereo else 0) + 2 * (i - min(i, max(i - rad, jfloor))) for i in range(t0, t))
 
 
-def backend_edges(dist, t_start, t_end, radius, nms, thresh, max_factors, stereo):
-    """Backend.ba's edge selection without loop closure (src/backend.py:25-99, the dense global BA):
-    returns the (ii, jj) it hands to graph.add_factors — or None where the reference returns early
-    (fewer than 3 edges, :96-97)."""
+def backend_edges(dist, t_start, t_end, radius, nms, thresh, max_factors, stereo, t_start_loop=None, loop=False):
+    """Backend.ba's edge selection (src/backend.py:25-99; dense global BA, and loop-closure BA with
+    loop=True): returns the (ii, jj) it hands to graph.add_factors — or None where the reference returns
+    early (fewer than 3 edges, :96-97).  dist = video.distance over (t_start_loop..t_end) x (t_start..t_end)."""
+    if t_start_loop is None or not loop:
+        t_start_loop = t_start
     empty = torch.zeros(0, dtype=torch.long, device=dist.device)
-    ii, jj = proximity_edges(dist, t_start, t_start, t_end, radius, nms, thresh, max_factors, stereo, empty, empty,
-                             dmax=thresh, jfloor=t_start)
+    ii, jj = proximity_edges(dist, t_start_loop, t_start, t_end, radius, nms, thresh, max_factors,
+                             stereo and not loop, empty, empty, dmax=thresh, jfloor=t_start_loop, loop=loop)
     return None if ii.numel() < 3 else (ii, jj)
 
 
-def proximity_edges(dist, t0, t1, t, rad, nms, thresh, max_factors, stereo, ii_old, jj_old, dmax=100.0, jfloor=0):
+def proximity_edges(dist, t0, t1, t, rad, nms, thresh, max_factors, stereo, ii_old, jj_old, dmax=100.0, jfloor=0,
+                    loop=False):
     if not dist.is_cuda:
         raise RuntimeError("proximity_edges: CUDA tensors required (no CPU fallback)")
     dev = dist.device
@@ -44,7 +47,7 @@ def proximity_edges(dist, t0, t1, t, rad, nms, thresh, max_factors, stereo, ii_o
     io = ii_old.to(dev).long().contiguous()
     jo = jj_old.to(dev).long().contiguous()
     mf = int(math.floor(float(max_factors)))
-    cap = local_edge_count(t0, t, rad, stereo, jfloor) + max(0, mf + 2) + 2
+    cap = local_edge_count(t0, t, rad, stereo, jfloor) + max(0, mf + 2) + 10
     es_i = torch.empty(cap, dtype=torch.int64, device=dev)
     es_j = torch.empty(cap, dtype=torch.int64, device=dev)
     num = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -55,7 +58,7 @@ def proximity_edges(dist, t0, t1, t, rad, nms, thresh, max_factors, stereo, ii_o
             raise RuntimeError("proximity_edges: empty window (t0=%d t1=%d t=%d)" % (t0, t1, t))
         ws = _workspace(nbytes, dev)
         rc = lib.goslam_proximity_edges(_lib.ptr(d), int(t0), int(t1), int(t), int(rad), int(nms), float(thresh),
-                                        float(dmax), int(jfloor), mf,
+                                        float(dmax), int(jfloor), int(bool(loop)), mf,
                                         int(bool(stereo)), _lib.ptr(io), _lib.ptr(jo), int(io.numel()),
                                         _lib.ptr(es_i), _lib.ptr(es_j), cap, _lib.ptr(num), _lib.ptr(ws),
                                         ctypes.c_size_t(ws.numel()), _lib.stream_ptr())

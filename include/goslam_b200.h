@@ -271,14 +271,18 @@ int goslam_cvx_upsample(const float* data, const void* mask, int mask_dtype, flo
  * dmax / jfloor select the variant: add_proximity_factors masks d > 100 and starts the local window
  * at max(i - rad, 0) (dmax = 100, jfloor = 0); Backend.ba without loop closure (src/backend.py:25-99)
  * masks d > thresh, starts it at max(i - radius, t_start) and holds no previous edges
- * (dmax = thresh, jfloor = t0 = t1 = t_start, n_old = 0).
- *   cap >= edges of the local window + max(0, max_factors + 2) is always enough.
+ * (dmax = thresh, jfloor = t0 = t1 = t_start, n_old = 0).  loop != 0 is Backend.ba's loop-closure mode
+ * (src/backend.py:81-91; t0 = t_start_loop, t1 = t_start, jfloor = t_start_loop, stereo ignored by the
+ * caller): an accepted candidate contributes the cells of its 3x3 neighbourhood whose RAW distance is
+ * below thresh (off-diagonal ones, row-major) when more than 4 of the 9 are.
+ *   cap >= edges of the local window + max(0, max_factors + 2) (+ 8 in loop mode) is always enough.
  *   workspace: goslam_proximity_workspace_bytes(t0, t1, t). */
 size_t goslam_proximity_workspace_bytes(int t0, int t1, int t);
 int goslam_proximity_edges(const float* dist, int t0, int t1, int t, int rad, int nms, float thresh,
-                           float dmax, int jfloor, int max_factors, int stereo, const int64_t* ii_old,
-                           const int64_t* jj_old, int n_old, int64_t* es_i, int64_t* es_j, int cap,
-                           int* num_edges, void* workspace, size_t workspace_bytes, void* stream);
+                           float dmax, int jfloor, int loop, int max_factors, int stereo,
+                           const int64_t* ii_old, const int64_t* jj_old, int n_old, int64_t* es_i,
+                           int64_t* es_j, int cap, int* num_edges, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* Training-only entry points of the reference module are exported for ABI completeness
  * and return GOSLAM_EUNSUPPORTED (inference path is torch.no_grad, src/slam.py:45). */

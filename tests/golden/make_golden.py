@@ -306,10 +306,15 @@ def gen_backend_edges():
     be_mod = ref_import("src.backend")
     rng = np.random.default_rng(33)
     out, n = {}, 0
-    for (ts, te, radius, nms, thresh, maxf, stereo) in [(0, 14, 2, 2, 18.0, 96, False), (3, 25, 3, 1, 25.0, 80, True),
-                                                       (0, 3, 2, 2, 10.0, 20, False), (5, 30, 1, 2, 15.0, 30, False)]:
-        ilen = te - ts
-        dist = (rng.random(ilen * ilen) * 40).astype(np.float32)
+    for (ts, te, radius, nms, thresh, maxf, stereo, tsl, loop) in [
+            (0, 14, 2, 2, 18.0, 96, False, None, False), (3, 25, 3, 1, 25.0, 80, True, None, False),
+            (0, 3, 2, 2, 10.0, 20, False, None, False), (5, 30, 1, 2, 15.0, 30, False, None, False),
+            (0, 40, 2, 2, 22.0, 300, False, 25, True), (2, 30, 3, 1, 30.0, 120, True, 18, True)]:
+        ilen = te - (tsl if loop else ts)
+        jlen = te - ts
+        dist = (rng.random(ilen * jlen) * 40).astype(np.float32)
+        if loop:                                   # smooth field so that 3x3 neighbourhoods agree often enough
+            dist = (dist.reshape(ilen, jlen) * 0.25 + 30.0 * np.abs(np.sin(np.arange(ilen)[:, None] * 0.4 + np.arange(jlen)[None] * 0.3))).astype(np.float32).reshape(-1)
         cap = {}
         b = be_mod.Backend.__new__(be_mod.Backend)
         b.beta, b.device = 0.75, "cpu"
@@ -317,8 +322,8 @@ def gen_backend_edges():
                                         distance=lambda ii, jj, beta, _d=dist: torch.from_numpy(_d.copy()))
         graph = types.SimpleNamespace(ii=[], update_lowmem=lambda **k: None, clear_edges=lambda: None,
                                       add_factors=lambda ii, jj, remove=False, _c=cap: _c.update(ii=ii.numpy().copy(), jj=jj.numpy().copy()))
-        b.ba(ts, te, 4, graph, nms, radius, thresh, maxf)
-        out["b%d_params" % n] = np.array([ts, te, radius, nms, maxf, int(stereo)], np.int64)
+        b.ba(ts, te, 4, graph, nms, radius, thresh, maxf, t_start_loop=tsl, loop=loop)
+        out["b%d_params" % n] = np.array([ts, te, radius, nms, maxf, int(stereo), -1 if tsl is None else tsl, int(loop)], np.int64)
         out["b%d_thresh" % n] = np.float32(thresh)
         out["b%d_dist" % n] = dist
         out["b%d_es" % n] = np.stack([cap["ii"], cap["jj"]], 1) if cap else np.zeros((0, 2), np.int64)

@@ -562,15 +562,15 @@ def test_proximity_edges_golden_from_reference_method():
 
 
 def test_backend_edges_golden_and_oracle():
-    """Backend.ba's edge selection (loop=False): device == the reference method (golden) == the oracle,
+    """Backend.ba's edge selection (dense and loop-closure modes): device == the reference method (golden) == the oracle,
     including the early return with fewer than 3 edges."""
     from goslam_b200 import graph
     from oracle import graph_oracle
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "backend_edges.npz"))
     for n in range(int(g["n_cases"])):
-        ts, te, rad, nms, maxf, st = [int(x) for x in g["b%d_params" % n]]
+        ts, te, rad, nms, maxf, st, tsl, loop = [int(x) for x in g["b%d_params" % n]]
         got = graph.backend_edges(torch.from_numpy(g["b%d_dist" % n]).to(dev()), ts, te, rad, nms,
-                                  float(g["b%d_thresh" % n]), maxf, bool(st))
+                                  float(g["b%d_thresh" % n]), maxf, bool(st), None if tsl < 0 else tsl, bool(loop))
         if int(g["b%d_early" % n]):
             assert got is None
         else:
@@ -581,6 +581,12 @@ def test_backend_edges_golden_and_oracle():
     got = graph.backend_edges(torch.from_numpy(dist).to(dev()), 10, 100, 2, 2, 22.0, 700, False)
     np.testing.assert_array_equal(torch.stack(got, 1).cpu().numpy(), want)
     assert graph.backend_edges(torch.from_numpy(dist[:1]).to(dev()), 4, 5, 2, 2, 22.0, 10, False) is None
+    # loop-closure mode on a larger smooth field
+    ilen, jlen = 60, 100
+    field = (rng.random((ilen, jlen)) * 8 + 30.0 * np.abs(np.sin(np.arange(ilen)[:, None] * 0.3 + np.arange(jlen)[None] * 0.2))).astype(np.float32)
+    want = graph_oracle.backend_edges(field.reshape(-1), 0, 100, 2, 2, 20.0, 900, False, 40, True)
+    got = graph.backend_edges(torch.from_numpy(field.reshape(-1)).to(dev()), 0, 100, 2, 2, 20.0, 900, False, 40, True)
+    np.testing.assert_array_equal(torch.stack(got, 1).cpu().numpy(), want)
 
 
 # ------------------------------------------------------------------------------ degenerate inputs

@@ -214,12 +214,13 @@ def test_proximity_edges_oracle_matches_reference_method():
 
 
 def test_backend_edges_oracle_matches_reference_method():
-    """oracle/graph_oracle.backend_edges against Backend.ba's own edge list (src/backend.py:25-99, loop=False)."""
+    """oracle/graph_oracle.backend_edges against Backend.ba's own edge list (src/backend.py:25-99; dense and loop-closure modes)."""
     from oracle import graph_oracle
     g = _load("backend_edges.npz")
     for n in range(int(g["n_cases"])):
-        ts, te, rad, nms, maxf, st = [int(x) for x in g["b%d_params" % n]]
-        es = graph_oracle.backend_edges(g["b%d_dist" % n], ts, te, rad, nms, float(g["b%d_thresh" % n]), maxf, bool(st))
+        ts, te, rad, nms, maxf, st, tsl, loop = [int(x) for x in g["b%d_params" % n]]
+        es = graph_oracle.backend_edges(g["b%d_dist" % n], ts, te, rad, nms, float(g["b%d_thresh" % n]), maxf, bool(st),
+                                        None if tsl < 0 else tsl, bool(loop))
         if int(g["b%d_early" % n]):
             assert es is None
         else:
