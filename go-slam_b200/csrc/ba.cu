@@ -20,6 +20,12 @@
 //   * The reduced camera system is accumulated and solved in float64 on the device
 //     (the reference converts fp32 blocks to float64 and solves on the CPU).
 //
+//   * Small windows (6P <= 96, every local window): ALL Gauss-Newton iterations of a call run in
+//     ONE cooperative kernel (ba_persistent_kernel) — linearise | grid barrier | reduced system |
+//     grid barrier | solve (block 0) | grid barrier, with the depth back-substitution of iteration
+//     i fused into the linearisation of iteration i+1; larger systems and the multi-GPU split
+//     form (goslam_ba_phase1/2) run the same device functions as separate launches.
+//
 // Reference quirks kept on purpose: the first optimised pose is skipped in the depth
 // back-substitution (`ix <= 0`, :1105); C/b_z use the stereo edge's weight before it is
 // zeroed (:320-323); stereo baseline (-0.1,0,0) (:219-229); MIN_DEPTH 0.25 (:26);
