@@ -275,44 +275,43 @@ def fmaps_to_kmajor(fmaps, out=None):
 
 
 class AltCorrBlock:
+    """Windowed correlation without a volume (global BA / `update_lowmem`): same constructor and call
+    signature as src/modules/corr.py:97-145.  `pyramid[l]` = NHWC feature maps of level l, pre-scaled by
+    1/4 and 2x2 average-pooled l times, shape [B, N, H >> l, W >> l, C]."""
+
     def __init__(self, fmaps, num_levels=4, radius=3):
-        self.num_levels = num_levels
-        self.radius = radius
-        B, N, C, H, W = fmaps.shape
-        fmaps = fmaps.view(B * N, C, H, W) / 4.0
+        self.num_levels, self.radius = num_levels, radius
+        b, n, c, h, w = fmaps.shape
+        level = fmaps.reshape(b * n, c, h, w) * 0.25            # exact power-of-two scaling, == fmaps / 4.0
         self.pyramid = []
-        for i in range(self.num_levels):
-            sz = (B, N, H // 2 ** i, W // 2 ** i, C)
-            fmap_lvl = fmaps.permute(0, 2, 3, 1).contiguous()
-            self.pyramid.append(fmap_lvl.view(*sz))
-            fmaps = F.avg_pool2d(fmaps, kernel_size=2, stride=2)
+        for lvl in range(num_levels):
+            nhwc = level.permute(0, 2, 3, 1).contiguous()
+            self.pyramid.append(nhwc.view(b, n, h >> lvl, w >> lvl, c))
+            if lvl + 1 < num_levels:
+                level = F.avg_pool2d(level, kernel_size=2, stride=2)
 
     def corr_fn(self, coords, ii, jj):
-        B, N, H, W, S, _ = coords.shape
-        coords = coords.permute(0, 1, 4, 2, 3, 5)
-        corr_list = []
-        for i in range(self.num_levels):
-            fmap1_i = self.pyramid[0][:, ii]
-            fmap2_i = self.pyramid[i][:, jj]
-            coords_i = (coords / 2 ** i).reshape(B * N, S, H, W, 2).contiguous()
-            fmap1_i = fmap1_i.reshape((B * N,) + fmap1_i.shape[2:])
-            fmap2_i = fmap2_i.reshape((B * N,) + fmap2_i.shape[2:])
-            corr, = altcorr_forward(fmap1_i.float().contiguous(), fmap2_i.float().contiguous(),
-                                    coords_i, self.radius)
-            corr = corr.view(B, N, S, -1, H, W).permute(0, 1, 3, 4, 5, 2)
-            corr_list.append(corr)
-        return torch.cat(corr_list, dim=2)
+        """reference-shaped path: one altcorr_forward per level on gathered fp32 maps
+        (coords [B, N, H, W, S, 2] -> [B, N, L*(2r+1)^2, H, W, S])."""
+        b, n, h, w, s, _ = coords.shape
+        pts = coords.permute(0, 1, 4, 2, 3, 5)
+        src = self.pyramid[0][:, ii]
+        src = src.reshape((b * n,) + tuple(src.shape[2:])).float().contiguous()
+        per_level = []
+        for lvl, maps in enumerate(self.pyramid):
+            tgt = maps[:, jj]
+            tgt = tgt.reshape((b * n,) + tuple(tgt.shape[2:])).float().contiguous()
+            pts_l = (pts / float(1 << lvl)).reshape(b * n, s, h, w, 2).contiguous()
+            corr, = altcorr_forward(src, tgt, pts_l, self.radius)
+            per_level.append(corr.view(b, n, s, -1, h, w).permute(0, 1, 3, 4, 5, 2))
+        return torch.cat(per_level, dim=2)
 
     def __call__(self, coords, ii, jj):
-        if len(coords.shape) == 5 and coords.is_cuda and self.pyramid[0].dtype == torch.float16:
-            return self._fused(coords, ii, jj)
-        squeeze_output = len(coords.shape) == 5
-        if squeeze_output:
-            coords = coords.unsqueeze(dim=-2)
-        corr = self.corr_fn(coords, ii, jj)
-        if squeeze_output:
-            corr = corr.squeeze(dim=-1)
-        return corr.contiguous()
+        if coords.dim() == 5:
+            if coords.is_cuda and self.pyramid[0].dtype == torch.float16:
+                return self._fused(coords, ii, jj)            # one launch, all levels, tensor cores
+            return self.corr_fn(coords.unsqueeze(-2), ii, jj).squeeze(-1).contiguous()
+        return self.corr_fn(coords, ii, jj).contiguous()
 
     def _fused(self, coords, ii, jj):
         """one launch for all levels, feature maps indexed per edge on the device."""
