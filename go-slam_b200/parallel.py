@@ -112,3 +112,34 @@ def sharded_ba(backend, disps, targets, weights, eta_by_frame, ii, jj, iteration
                 if b > a:
                     dist.broadcast(disps[a:b], src=dist.get_global_rank(group, r) if group else r, group=group)
     return dx
+
+
+def sharded_pairs(fn, ii, jj, group=None):
+    """Embarrassingly parallel per-pair work (DepthVideo.distance over K frame pairs):
+    the pair list is split evenly and contiguously over the ranks, each rank evaluates `fn(ii_part,
+    jj_part) -> [k]` on its slice, and ONE all-gather of K floats rebuilds the replicated result.
+    `fn` is droid_backends.frame_distance bound to the replicated poses / disps on GPUs (any callable
+    with that contract in the gloo tests)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    K = int(ii.shape[0])
+    per = (K + world - 1) // world
+    lo, hi = min(K, rank * per), min(K, (rank + 1) * per)
+    part = fn(ii[lo:hi].contiguous(), jj[lo:hi].contiguous()) if hi > lo else ii.new_zeros(0, dtype=torch.float32)
+    padded = torch.zeros(per, dtype=torch.float32, device=part.device)
+    padded[:hi - lo] = part.float()
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)
+    return torch.cat(gathered)[:K]
+
+
+def sharded_distance(poses, disps, intrinsics, ii, jj, beta=0.3, bidirectional=True, group=None):
+    """DepthVideo.distance (src/depth_video.py:219-255) with the pair list sharded over the ranks."""
+    from . import droid_backends
+
+    def one_way(a, b):
+        return droid_backends.frame_distance(poses, disps, intrinsics, a, b, beta)
+
+    if not bidirectional:
+        return sharded_pairs(one_way, ii, jj, group)
+    return sharded_pairs(lambda a, b: 0.5 * (one_way(a, b) + one_way(b, a)), ii, jj, group)

@@ -95,3 +95,48 @@ def test_sharded_ba_two_ranks_equals_single_process(tmp_path):
     np.testing.assert_allclose(got["poses"].numpy(), rp, rtol=0, atol=2e-6)
     np.testing.assert_allclose(got["disps"].numpy(), rd, rtol=0, atol=2e-6)
     np.testing.assert_allclose(got["dx"].numpy(), rdx, rtol=0, atol=2e-6)
+
+
+def _pairs_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from goslam_b200 import parallel
+    from oracle import geom_oracle
+    from goslam_b200 import synthetic
+    sc, _ = synthetic.make_scene(num_kf=6, ht=8, wd=10, seed=11, rgbd=True, with_fmaps=False)
+    ii, jj = torch.meshgrid(torch.arange(6), torch.arange(6), indexing="ij")
+    ii, jj = ii.reshape(-1)[:31], jj.reshape(-1)[:31]            # 31 pairs: uneven split over 2 ranks
+
+    def fn(a, b):
+        return torch.from_numpy(geom_oracle.frame_distance(sc["poses"].numpy(), sc["disps"].numpy(),
+                                                           sc["intrinsics"][0].numpy(), a.numpy(), b.numpy(), 0.3))
+    got = parallel.sharded_pairs(fn, ii, jj)
+    if rank == 0:
+        out.put(got.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_pair_distance_gloo_world2():
+    """frame-distance pair list split over 2 ranks + one all-gather == the unsharded evaluation."""
+    sys.path.insert(0, ROOT)
+    from goslam_b200 import synthetic
+    from oracle import geom_oracle
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_pairs_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sc, _ = synthetic.make_scene(num_kf=6, ht=8, wd=10, seed=11, rgbd=True, with_fmaps=False)
+    ii, jj = torch.meshgrid(torch.arange(6), torch.arange(6), indexing="ij")
+    ii, jj = ii.reshape(-1)[:31], jj.reshape(-1)[:31]
+    want = geom_oracle.frame_distance(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"][0].numpy(),
+                                      ii.numpy(), jj.numpy(), 0.3)
+    np.testing.assert_array_equal(got, want.astype(np.float32))
