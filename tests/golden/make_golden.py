@@ -15,6 +15,7 @@ What each fixture pins:
     render_z.npz      Renderer.render_batch_ray z-sampling        src/render.py:99-171
     cvx_upsample.npz  cvx_upsample (f32 and f16 masks)            src/droid_net.py:9-23
     proximity.npz     FactorGraph.add_proximity_factors edges     src/factor_graph.py:384-450
+    altcorr_pyramid.npz AltCorrBlock.__init__ pyramid            src/modules/corr.py:97-111
     backend_edges.npz Backend.ba edge selection (loop=False)      src/backend.py:25-99
 Run:  python tests/golden/make_golden.py      (writes next to this file)
 """
@@ -333,11 +334,23 @@ def gen_backend_edges():
     np.savez_compressed(os.path.join(HERE, "backend_edges.npz"), **out)
 
 
+def gen_altcorr_pyramid():
+    """AltCorrBlock.__init__ (src/modules/corr.py:97-111): the /4-scaled, average-pooled NHWC pyramid."""
+    corr_mod = ref_import("src.modules.corr")
+    g = torch.Generator().manual_seed(12)
+    fm = torch.randn(1, 3, 128, 10, 12, generator=g).half()
+    blk = corr_mod.AltCorrBlock(fm)
+    out = {"fmaps": fm.numpy()}
+    for i, lvl in enumerate(blk.pyramid):
+        out["level%d" % i] = lvl.numpy()
+    np.savez_compressed(os.path.join(HERE, "altcorr_pyramid.npz"), **out)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("needs /root/reference (build container only)")
     install_stubs()
-    which = sys.argv[1:] or ["corr_block", "reproject", "ba_torch", "neus", "render_z", "cvx_upsample", "proximity", "backend_edges"]
+    which = sys.argv[1:] or ["corr_block", "reproject", "ba_torch", "neus", "render_z", "cvx_upsample", "proximity", "backend_edges", "altcorr_pyramid"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)

@@ -225,3 +225,14 @@ def test_backend_edges_oracle_matches_reference_method():
             assert es is None
         else:
             np.testing.assert_array_equal(es, g["b%d_es" % n])
+
+
+def test_altcorr_block_pyramid_matches_reference_constructor():
+    """goslam_b200.modules.AltCorrBlock.__init__ is torch-only: its pyramid must equal the reference
+    constructor's (src/modules/corr.py:97-111) bit for bit."""
+    from goslam_b200.modules.corr import AltCorrBlock
+    g = _load("altcorr_pyramid.npz")
+    blk = AltCorrBlock(torch.from_numpy(g["fmaps"]))
+    assert len(blk.pyramid) == 4
+    for i, lvl in enumerate(blk.pyramid):
+        assert torch.equal(lvl, torch.from_numpy(g["level%d" % i]))
