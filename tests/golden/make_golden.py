@@ -338,7 +338,7 @@ def gen_altcorr_pyramid():
     """AltCorrBlock.__init__ (src/modules/corr.py:97-111): the /4-scaled, average-pooled NHWC pyramid."""
     corr_mod = ref_import("src.modules.corr")
     g = torch.Generator().manual_seed(12)
-    fm = torch.randn(1, 3, 128, 10, 12, generator=g).half()
+    fm = torch.randn(1, 3, 128, 16, 24, generator=g).half()   # the reference pools once more than it needs: h >= 16
     blk = corr_mod.AltCorrBlock(fm)
     out = {"fmaps": fm.numpy()}
     for i, lvl in enumerate(blk.pyramid):
