@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -87,3 +89,22 @@ def test_hashgrid_layout_matches_oracle(lib):
     assert offs[:-1] == [2 * m["offset"] for m in metas]
     for s, m in zip(scales, metas):
         assert abs(s - float(m["scale"])) <= 1e-6 * s
+
+
+def test_header_is_plain_c_and_library_links_without_torch(tmp_path):
+    """compile tests/c/abi_smoke.c as C99 against include/goslam_b200.h, link it to libgoslam_b200.so only,
+    run it: host-only helpers answer, argument validation returns before any CUDA call."""
+    import shutil
+    import subprocess
+    from goslam_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None or not os.path.exists(_lib.lib_path()):
+        pytest.skip("gcc or the built library is missing")
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(_lib.lib_path())
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", libdir, "-lgoslam_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "abi smoke ok" in out.stdout
