@@ -334,6 +334,26 @@ def gen_backend_edges():
     np.savez_compressed(os.path.join(HERE, "backend_edges.npz"), **out)
 
 
+def gen_altcorr_block():
+    """AltCorrBlock.__call__ plumbing (src/modules/corr.py:113-145) with the oracle standing in for the
+    CUDA op: pins the gather / per-level scaling / channel layout of the reference class."""
+    def alt_fwd(f1, f2, coords, r):
+        return [torch.from_numpy(corr_oracle.altcorr_forward(f1.numpy(), f2.numpy(), coords.numpy(), r))]
+    sys.modules["droid_backends"].altcorr_forward = alt_fwd
+    corr_mod = ref_import("src.modules.corr")
+    g = torch.Generator().manual_seed(13)
+    h, w = 16, 24
+    fm = torch.randn(1, 4, 128, h, w, generator=g)
+    ii, jj = torch.tensor([0, 3, 2]), torch.tensor([1, 0, 3])
+    base = torch.stack(torch.meshgrid(torch.arange(w).float(), torch.arange(h).float(), indexing="xy"), -1)
+    coords = base[None, None].repeat(1, 3, 1, 1, 1) + 2 * torch.randn(1, 3, h, w, 2, generator=g)
+    out5 = corr_mod.AltCorrBlock(fm)(coords, ii, jj)
+    c6 = coords.unsqueeze(-2).repeat(1, 1, 1, 1, 2, 1) + torch.tensor([0.0, 0.5]).view(1, 1, 1, 1, 2, 1)
+    out6 = corr_mod.AltCorrBlock(fm)(c6, ii, jj)
+    np.savez_compressed(os.path.join(HERE, "altcorr_block.npz"), fmaps=fm.numpy(), ii=ii.numpy(), jj=jj.numpy(),
+                        coords=coords.numpy(), coords6=c6.numpy(), out5=out5[:, :, ::7].numpy(), out6=out6[:, :, ::7].numpy())
+
+
 def gen_altcorr_pyramid():
     """AltCorrBlock.__init__ (src/modules/corr.py:97-111): the /4-scaled, average-pooled NHWC pyramid."""
     corr_mod = ref_import("src.modules.corr")
@@ -350,7 +370,7 @@ if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("needs /root/reference (build container only)")
     install_stubs()
-    which = sys.argv[1:] or ["corr_block", "reproject", "ba_torch", "neus", "render_z", "cvx_upsample", "proximity", "backend_edges", "altcorr_pyramid"]
+    which = sys.argv[1:] or ["corr_block", "reproject", "ba_torch", "neus", "render_z", "cvx_upsample", "proximity", "backend_edges", "altcorr_pyramid", "altcorr_block"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)
