@@ -276,7 +276,10 @@ def gen_proximity():
     cases = []
     for (t0, t1, t, rad, nms, thresh, maxf, stereo, n_old) in [
             (7, 0, 12, 2, 2, 16.0, 48, False, 6), (0, 0, 9, 2, 2, 16.0, 60, False, 0),
-            (10, 3, 22, 3, 1, 20.0, 40, True, 9), (4, 0, 10, 2, 2, 12.0, 14, False, 3)]:
+            (10, 3, 22, 3, 1, 20.0, 40, True, 9), (4, 0, 10, 2, 2, 12.0, 14, False, 3),
+            (5, 9, 30, 2, 2, 25.0, 200, True, 20),       # t1 > t0: negative column indices wrap (Python semantics)
+            (6, 8, 20, 3, 2, 30.0, 90, False, 5), (0, 0, 40, 2, 2, 14.0, 400, False, 60),
+            (3, 0, 14, 2, 3, 30.0, -1, False, 0)]:
         ilen, jlen = t - t0, t - t1
         dist = (rng.random(ilen * jlen) * 40).astype(np.float32)
         dist[rng.random(ilen * jlen) < 0.1] = 150.0
