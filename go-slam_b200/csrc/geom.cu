@@ -37,14 +37,12 @@ __device__ __forceinline__ float tree256(float v, float* s) {
   return r;  // valid in thread 0
 }
 
-__global__ void __launch_bounds__(kThreads)
-frame_distance_kernel(const float* __restrict__ poses, const float* __restrict__ disps,
-                      const float* __restrict__ intr, const int64_t* __restrict__ ii,
-                      const int64_t* __restrict__ jj, float* __restrict__ dist,
-                      int ht, int wd, float beta) {
-  __shared__ float red[kThreads];
-  const int ix = (int)ii[blockIdx.x];
-  const int jx = (int)jj[blockIdx.x];
+// distance of the ordered pair (ix -> jx); the value is valid in thread 0.  NOT inlined: the one-way and the
+// bidirectional kernel must run the very same instruction sequence (FMA contraction included) so that
+// 0.5 * (d_ij + d_ji) is bit-identical in both forms.
+__device__ __noinline__ float pair_distance(const float* __restrict__ poses, const float* __restrict__ disps,
+                                               const float* __restrict__ intr, int ix, int jx, int ht, int wd,
+                                               float beta, float* red) {
   const float fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3];
 
   // NB: no stereo special case here — the reference calls relSE3 unconditionally.
@@ -93,8 +91,31 @@ frame_distance_kernel(const float* __restrict__ poses, const float* __restrict__
   const float a = tree256(accum, red);
   const float t = tree256(total, red);
   const float w = tree256(valid, red);
-  if (threadIdx.x == 0)
-    dist[blockIdx.x] = (w / (t + 1e-8f) < 0.75f) ? 1000.0f : a / w;
+  return (w / (t + 1e-8f) < 0.75f) ? 1000.0f : a / w;
+}
+
+__global__ void __launch_bounds__(kThreads)
+frame_distance_kernel(const float* __restrict__ poses, const float* __restrict__ disps,
+                      const float* __restrict__ intr, const int64_t* __restrict__ ii,
+                      const int64_t* __restrict__ jj, float* __restrict__ dist,
+                      int ht, int wd, float beta) {
+  __shared__ float red[kThreads];
+  const float d = pair_distance(poses, disps, intr, (int)ii[blockIdx.x], (int)jj[blockIdx.x], ht, wd, beta, red);
+  if (threadIdx.x == 0) dist[blockIdx.x] = d;
+}
+
+// DepthVideo.distance(bidirectional=True) (src/depth_video.py:233-245): 0.5 * (d(i->j) + d(j->i)) in one
+// launch; each direction keeps the reduction tree above, so the result equals the two-launch form bit for bit.
+__global__ void __launch_bounds__(kThreads)
+frame_distance_bidir_kernel(const float* __restrict__ poses, const float* __restrict__ disps,
+                            const float* __restrict__ intr, const int64_t* __restrict__ ii,
+                            const int64_t* __restrict__ jj, float* __restrict__ dist,
+                            int ht, int wd, float beta) {
+  __shared__ float red[kThreads];
+  const int ix = (int)ii[blockIdx.x], jx = (int)jj[blockIdx.x];
+  const float d1 = pair_distance(poses, disps, intr, ix, jx, ht, wd, beta, red);
+  const float d2 = pair_distance(poses, disps, intr, jx, ix, ht, wd, beta, red);
+  if (threadIdx.x == 0) dist[blockIdx.x] = __fmul_rn(0.5f, __fadd_rn(d1, d2));
 }
 
 // ---------------------------------------------------------------------------------
@@ -260,6 +281,17 @@ int goslam_frame_distance(const float* poses, const float* disps, const float* i
   if (K == 0) return GOSLAM_OK;
   frame_distance_kernel<<<K, kThreads, 0, (cudaStream_t)stream>>>(poses, disps, intrinsics, ii,
                                                                   jj, dist, ht, wd, beta);
+  GS_CHECK_LAUNCH();
+  return GOSLAM_OK;
+}
+
+int goslam_frame_distance_bidir(const float* poses, const float* disps, const float* intrinsics,
+                                const int64_t* ii, const int64_t* jj, float* dist, int K, int ht, int wd,
+                                float beta, void* stream) {
+  if (K < 0 || ht <= 0 || wd <= 0) return GOSLAM_EINVAL;
+  if (K == 0) return GOSLAM_OK;
+  frame_distance_bidir_kernel<<<K, kThreads, 0, (cudaStream_t)stream>>>(poses, disps, intrinsics, ii, jj, dist, ht,
+                                                                        wd, beta);
   GS_CHECK_LAUNCH();
   return GOSLAM_OK;
 }

@@ -115,6 +115,22 @@ def frame_distance(poses, disps, intrinsics, ii, jj, beta):
     return dist
 
 
+def frame_distance_bidirectional(poses, disps, intrinsics, ii, jj, beta):
+    """Not in the reference module: DepthVideo.distance(bidirectional=True) (src/depth_video.py:233-245)
+    = 0.5 * (frame_distance(ii, jj) + frame_distance(jj, ii)) in one launch, bit-identical to that form."""
+    _contig(poses=poses, disps=disps, intrinsics=intrinsics, ii=ii, jj=jj)
+    _need_cuda(poses, disps, intrinsics, ii, jj)
+    K = ii.shape[0]
+    ht, wd = disps.shape[1], disps.shape[2]
+    dist = torch.empty((K,), dtype=torch.float32, device=poses.device)
+    with torch.cuda.device(poses.device):
+        rc = _lib.load().goslam_frame_distance_bidir(
+            _lib.ptr(poses), _lib.ptr(disps), _lib.ptr(intrinsics), _lib.ptr(ii), _lib.ptr(jj),
+            _lib.ptr(dist), K, ht, wd, float(beta), _lib.stream_ptr())
+    _lib.check(rc, "frame_distance_bidir")
+    return dist
+
+
 def projmap(poses, disps, intrinsics, ii, jj):
     """src/lib/droid.cpp:139-144 -> [coords(N,h,w,3), valid(N,h,w,1)]."""
     _contig(poses=poses, disps=disps, intrinsics=intrinsics, ii=ii, jj=jj)

@@ -142,4 +142,5 @@ def sharded_distance(poses, disps, intrinsics, ii, jj, beta=0.3, bidirectional=T
 
     if not bidirectional:
         return sharded_pairs(one_way, ii, jj, group)
-    return sharded_pairs(lambda a, b: 0.5 * (one_way(a, b) + one_way(b, a)), ii, jj, group)
+    return sharded_pairs(lambda a, b: droid_backends.frame_distance_bidirectional(poses, disps, intrinsics, a, b, beta),
+                         ii, jj, group)

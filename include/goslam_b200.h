@@ -138,6 +138,11 @@ int goslam_altcorr_pyramid(const void* const* pyramid, int num_levels, const flo
 int goslam_frame_distance(const float* poses, const float* disps, const float* intrinsics,
                           const int64_t* ii, const int64_t* jj, float* dist,
                           int K, int ht, int wd, float beta, void* stream);
+/* DepthVideo.distance(bidirectional=True) (src/depth_video.py:233-245): 0.5 * (d(i->j) + d(j->i)) in one
+ * launch instead of two launches and two elementwise kernels; bit-identical to that form. */
+int goslam_frame_distance_bidir(const float* poses, const float* disps, const float* intrinsics,
+                                const int64_t* ii, const int64_t* jj, float* dist, int K, int ht,
+                                int wd, float beta, void* stream);
 /* projmap (src/lib/droid_kernels.cu:427-516,1463-1488): coords [K,ht,wd,3] (3rd
  * component left zero, as the reference does), valid [K,ht,wd,1]. */
 int goslam_projmap(const float* poses, const float* disps, const float* intrinsics,

@@ -271,6 +271,19 @@ def test_frame_distance(size):
         assert (np.argsort(got, kind="stable") == np.argsort(ref, kind="stable")).mean() > 0.95
 
 
+def test_frame_distance_bidirectional_equals_two_launches():
+    """goslam_frame_distance_bidir == 0.5 * (d(ii,jj) + d(jj,ii)) of the one-way kernel, bit for bit."""
+    from goslam_b200 import droid_backends
+    sc, _ = _scene(7, 30, 40, seed=3, with_fmaps=False)
+    poses, disps, intr = _to_dev(sc, "poses", "disps", "intrinsics")
+    ii, jj = torch.meshgrid(torch.arange(7), torch.arange(7), indexing="ij")
+    ii, jj = ii.reshape(-1).to(dev()), jj.reshape(-1).to(dev())
+    d1 = droid_backends.frame_distance(poses, disps, intr[0].contiguous(), ii, jj, 0.3)
+    d2 = droid_backends.frame_distance(poses, disps, intr[0].contiguous(), jj, ii, 0.3)
+    both = droid_backends.frame_distance_bidirectional(poses, disps, intr[0].contiguous(), ii, jj, 0.3)
+    assert torch.equal(both, 0.5 * (d1 + d2))
+
+
 def test_projmap_iproj_depth_filter_reproject():
     from goslam_b200 import droid_backends
     sc, g = _scene(7, 12, 16, with_fmaps=False)
