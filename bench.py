@@ -112,11 +112,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------ workload
 def make_window(seed):
     from goslam_b200 import synthetic
-    from oracle import geom_oracle   # only used to seed targets (setup, not the timed path)
     sc, g = synthetic.make_scene(num_kf=NUM_KF, ht=HT, wd=WD, seed=seed, rgbd=True)
-    coords, _ = geom_oracle.reproject(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"].numpy(),
-                                      sc["ii"].numpy(), sc["jj"].numpy())
-    targets, weights, eta = synthetic.make_update(sc, torch.from_numpy(coords[0]), g, noise=0.5)
+    coords = synthetic.true_reprojection(sc)          # plain-torch setup helper (targets = reprojection + noise)
+    targets, weights, eta = synthetic.make_update(sc, coords[0], g, noise=0.5)
     sc.update(targets=targets, weights=weights, eta=eta)
     return sc
 

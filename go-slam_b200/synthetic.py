@@ -85,6 +85,40 @@ def make_scene(num_kf=8, ht=40, wd=80, seed=43, rgbd=True, buffer=None, fx=None,
     return scene, g
 
 
+def true_reprojection(scene):
+    """Where every source pixel of every edge lands in its target frame, in plain torch — the seed of the
+    synthetic flow targets (setup helper for bench / tools; same model as DepthVideo.reproject:
+    G_ij = G_j G_i^-1, fixed stereo baseline for i == j, pinhole projection).  Returns [1, N, ht, wd, 2]."""
+    poses, disps, K = scene["poses"].float(), scene["disps"].float(), scene["intrinsics"].float()
+    ii, jj = scene["ii"].long(), scene["jj"].long()
+    N = ii.numel()
+    _, ht, wd = disps.shape
+    qi, qj = poses[ii, 3:].T, poses[jj, 3:].T                      # [4, N]
+    q = _qmul(qj, qi * torch.tensor([-1.0, -1.0, -1.0, 1.0])[:, None])
+    t = poses[jj, :3].T - _vrot(q, poses[ii, :3].T)                # [3, N]
+    same = (ii == jj)
+    q = torch.where(same[None], torch.tensor([0.0, 0.0, 0.0, 1.0])[:, None], q)
+    t = torch.where(same[None], torch.tensor([-0.1, 0.0, 0.0])[:, None], t)
+    v, u = torch.meshgrid(torch.arange(ht).float(), torch.arange(wd).float(), indexing="ij")
+    Ki, Kj = K[ii], K[jj]                                          # [N, 4]
+    X = torch.stack([(u[None] - Ki[:, 2, None, None]) / Ki[:, 0, None, None],
+                     (v[None] - Ki[:, 3, None, None]) / Ki[:, 1, None, None],
+                     torch.ones(N, ht, wd)], 0)                    # [3, N, ht, wd]
+    X1 = _vrot(q[:, :, None, None], X) + t[:, :, None, None] * disps[ii][None]
+    Z = torch.where(X1[2] < 0.1, torch.ones(()), X1[2])
+    x = Kj[:, 0, None, None] * (X1[0] / Z) + Kj[:, 2, None, None]
+    y = Kj[:, 1, None, None] * (X1[1] / Z) + Kj[:, 3, None, None]
+    return torch.stack([x, y], -1)[None]
+
+
+def _vrot(q, v):
+    """rotate v [3, ...] by quaternions q [4, ...] (x, y, z, w), broadcasting."""
+    qv = q[:3]
+    uv = 2 * torch.stack([qv[1] * v[2] - qv[2] * v[1], qv[2] * v[0] - qv[0] * v[2], qv[0] * v[1] - qv[1] * v[0]])
+    return v + q[3] * uv + torch.stack([qv[1] * uv[2] - qv[2] * uv[1], qv[2] * uv[0] - qv[0] * uv[2],
+                                        qv[0] * uv[1] - qv[1] * uv[0]])
+
+
 def make_update(scene, coords, g, noise=0.5, oob_frac=0.0):
     """targets / weights / eta like the update operator would emit (src/factor_graph.py:212-241):
     target = reprojection + N(0, noise px); weight ~ U(0,1); eta = 0.2*damping + 1e-7."""

@@ -169,3 +169,14 @@ def test_filter_repeated_edges_matches_python_set():
     assert got[0].tolist() == want[0].tolist() and got[1].tolist() == want[1].tolist()
     e = torch.zeros(0, dtype=torch.long)
     assert graph.filter_repeated_edges(ii, jj, e, e, e, e)[0].tolist() == ii.tolist()
+
+
+def test_synthetic_true_reprojection_matches_oracle():
+    """the plain-torch setup helper that seeds bench.py's flow targets == the oracle's DepthVideo.reproject
+    (incl. the stereo baseline for i == j)."""
+    from goslam_b200 import synthetic
+    for kw in (dict(num_kf=6, ht=12, wd=16, seed=43), dict(num_kf=5, ht=9, wd=13, seed=2, stereo_edges=3)):
+        sc, _ = synthetic.make_scene(rgbd=True, with_fmaps=False, **kw)
+        ref, _ = geom_oracle.reproject(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"].numpy(),
+                                       sc["ii"].numpy(), sc["jj"].numpy())
+        np.testing.assert_allclose(synthetic.true_reprojection(sc).numpy(), ref, rtol=1e-6, atol=1e-5)

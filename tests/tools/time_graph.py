@@ -1,6 +1,6 @@
 """proximity-edge selection: device kernel vs the reference-shaped Python loops (oracle, CPU)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch

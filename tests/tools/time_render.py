@@ -1,6 +1,6 @@
 """in-stream timing of the renderer pieces: z-sampling kernel, marcher on bench rays vs sampled rays."""
 import os, sys, types
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 import bench

@@ -15,12 +15,10 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     from goslam_b200 import droid_backends, parallel, synthetic
-    from oracle import geom_oracle
     num_kf, ht, wd = 16, 40, 80
     sc, g = synthetic.make_scene(num_kf=num_kf, ht=ht, wd=wd, seed=9, rgbd=True, with_fmaps=False)
-    coords, _ = geom_oracle.reproject(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"].numpy(),
-                                      sc["ii"].numpy(), sc["jj"].numpy())
-    tg, wg, eta = synthetic.make_update(sc, torch.from_numpy(coords[0]), g, noise=0.6)
+    coords = synthetic.true_reprojection(sc)
+    tg, wg, eta = synthetic.make_update(sc, coords[0], g, noise=0.6)
     t0, t1, iters = 1, num_kf, 3
     kx = torch.unique(torch.cat([torch.arange(t0, t1), sc["ii"]]))
     eta_f = torch.zeros(num_kf, ht, wd)
