@@ -66,6 +66,17 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, fn)).read()
                 assert "import oracle" not in src and "from oracle" not in src, os.path.join(dp, fn)
+    # developer tools never touch the oracle either, and bench.py only inside its CPU-baseline leg
+    top = os.path.dirname(root)
+    for fn in os.listdir(os.path.join(top, "tools")):
+        if fn.endswith(".py"):
+            src = open(os.path.join(top, "tools", fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+    bench_src = open(os.path.join(top, "bench.py")).read()
+    uses = [i for i in range(len(bench_src)) if bench_src.startswith("from oracle", i)]
+    start = bench_src.index("def cpu_reference_step")
+    end = bench_src.index("\ndef ", start + 10)
+    assert uses and all(start < i < end for i in uses)
 
 
 def _rand_se3(n, seed):
