@@ -32,8 +32,8 @@
 // damping diag += ep + lm*diag (:1197); failed factorisation => dx = 0 (:1207-1210).
 #include "common.cuh"
 #include "se3.cuh"
-#include <cstdlib>
 #include <cstdio>
+#include <mutex>
 
 namespace {
 
@@ -45,7 +45,7 @@ struct BaWs {
   // graph tables (built once per call by ba_prep_kernel)
   int* slot_of_frame;  // [num]   slot in kx or -1
   int* kx;             // [num]   frame id of slot
-  int* counts;         // [4]     M, total_entries, total_pairs, unused
+  int* counts;         // [8]     M, total_entries, total_pairs, grid-barrier counter, bad-argument flag
   int* row_ptr;        // [num+1] CSR over frame id: edges with ii == frame
   int* edge_idx;       // [N]
   int* entry_ptr;      // [num+1] per slot: Schur entries
@@ -75,7 +75,7 @@ size_t ba_layout(const BaDims& d, void* base, size_t cap, BaWs* ws) {
   BaWs w{};
   w.slot_of_frame = a.take<int>(d.num);
   w.kx = a.take<int>(d.num);
-  w.counts = a.take<int>(4);
+  w.counts = a.take<int>(8);
   w.row_ptr = a.take<int>(d.num + 1);
   w.edge_idx = a.take<int>(d.N > 0 ? d.N : 1);
   w.entry_ptr = a.take<int>(d.num + 1);
@@ -101,7 +101,8 @@ size_t ba_layout(const BaDims& d, void* base, size_t cap, BaWs* ws) {
 // prefix sum over a presence bitmap (frame order == sorted order, as torch::_unique gives).
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-ba_prep_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, BaDims d, BaWs ws, int zero) {
+ba_prep_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, BaDims d, BaWs ws, int zero,
+               int eta_rows) {
   extern __shared__ int sm[];          // [num] scratch
   const int tid = threadIdx.x, nt = blockDim.x;
   if (zero) {                          // single-kernel driver: reduced system and grid-barrier counter start at 0
@@ -126,6 +127,11 @@ ba_prep_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, B
       else ws.slot_of_frame[f] = -1;
     }
     ws.counts[0] = m;
+    // eta must have one row (broadcast), one row per depth slot (the reference's
+    // `damping[unique(cat(arange(t0,t1), ii))]`, src/factor_graph.py:236-238) or — negative
+    // eta_rows — one row per FRAME.  Anything else is a caller bug that the reference reports as a
+    // broadcast error (src/lib/droid_kernels.cu:1397); here the call becomes a no-op with status 2.
+    ws.counts[4] = (eta_rows == 0 || eta_rows == 1 || eta_rows == m || eta_rows == -d.num) ? 0 : 1;
   }
   __syncthreads();
   // CSR: one thread per frame scans the edge list => stable (edge-index) order
@@ -330,7 +336,7 @@ __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, 
     // depth prior where the sensor has a reading, eta-damping elsewhere (:1396-1400)
     const float ds = disps_sens[(size_t)f * d.hw + px];
     const float m = (ds > 0.f) ? 1.0f : 0.0f;
-    const int er = (eta_rows == 1) ? 0 : min(k, eta_rows - 1);
+    const int er = (eta_rows == 1) ? 0 : (eta_rows < 0 ? f : k);
     const float et = eta[(size_t)er * d.hw + px];
     C = C + m * kAlpha + (1.0f - m) * et;
     wz = wz - m * kAlpha * (di - ds);
@@ -344,7 +350,7 @@ __device__ __forceinline__ void linearize_tile(const BaIn& in, const BaDims& d, 
 
 __global__ void __launch_bounds__(kTP)
 ba_linearize_kernel(BaIn in, BaDims d, BaWs ws, int motion_only) {
-  if ((int)blockIdx.y >= ws.counts[0]) return;
+  if ((int)blockIdx.y >= ws.counts[0] || ws.counts[4]) return;
   linearize_tile(in, d, ws, motion_only, blockIdx.y, blockIdx.x * (kTP / 32) + (threadIdx.x >> 5));
 }
 
@@ -562,6 +568,7 @@ __global__ void __launch_bounds__(256)
 ba_system_kernel(const float* poses, const int64_t* __restrict__ ii,
                  const int64_t* __restrict__ jj, BaDims d, BaWs ws, int motion_only) {
   __shared__ SysSmem sm;
+  if (ws.counts[4]) return;
   system_items<256>(poses, ii, jj, d, ws, motion_only, blockIdx.x, gridDim.x, sm);
 }
 
@@ -579,6 +586,16 @@ __device__ __forceinline__ void solve_finish(float* poses, const BaDims& d, cons
     if (dx_out) dx_out[i] = val;
   }
   if (tid == 0 && status_out) *status_out = fail;
+}
+
+// eta shape mismatch (see ba_prep_kernel): zero step, status 2, state untouched
+__device__ __forceinline__ void bad_argument_step(const BaDims& d, const BaWs& ws, float* dx_out,
+                                                  int* status_out, int tid, int nt) {
+  for (int i = tid; i < d.n; i += nt) {
+    ws.dx[i] = 0.f;
+    if (dx_out) dx_out[i] = 0.f;
+  }
+  if (tid == 0 && status_out) *status_out = 2;
 }
 
 __device__ __forceinline__ void retract_poses(float* poses, const BaDims& d, const BaWs& ws, int tid,
@@ -794,6 +811,7 @@ ba_solve_warp_kernel(float* poses, BaDims d, BaWs ws, const double* sys_in, floa
                      float* dx_out, int* status_out) {
   extern __shared__ double smd[];
   __shared__ SolveSmem ss;
+  if (ws.counts[4]) { bad_argument_step(d, ws, dx_out, status_out, threadIdx.x, blockDim.x); return; }
   solve_small(poses, d, ws, sys_in, lm, ep, dx_out, status_out, smd, ss);
 }
 
@@ -805,6 +823,7 @@ ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __re
   extern __shared__ double smd[];
   __shared__ int fail;
   const int n = d.n, tid = threadIdx.x, nt = blockDim.x;
+  if (ws.counts[4]) { bad_argument_step(d, ws, dx_out, status_out, tid, nt); return; }
   double* A = use_smem ? smd : ws.chol;
   double* b = use_smem ? smd + (size_t)n * n : ws.rhs;
   if (tid == 0) fail = 0;
@@ -901,7 +920,7 @@ __device__ __forceinline__ void backsub_tile(float* disps, const BaDims& d, cons
 
 __global__ void __launch_bounds__(kTP)
 ba_backsub_kernel(float* disps, BaDims d, BaWs ws, int owner_lo, int owner_hi, float* dz_out) {
-  if ((int)blockIdx.y >= ws.counts[0]) return;
+  if ((int)blockIdx.y >= ws.counts[0] || ws.counts[4]) return;
   backsub_tile(disps, d, ws, owner_lo, owner_hi, dz_out, blockIdx.y, blockIdx.x * (kTP / 32) + (threadIdx.x >> 5));
 }
 
@@ -955,6 +974,13 @@ ba_persistent_kernel(float* poses, float* disps, BaIn in, BaDims d, BaWs ws, int
   if (dz_out) {                      // rows of frames without a depth update stay 0 (first written after 3 barriers)
     const size_t ndz = (size_t)d.num * d.hw;
     for (size_t i = (size_t)blockIdx.x * kTP + threadIdx.x; i < ndz; i += (size_t)gridDim.x * kTP) dz_out[i] = 0.f;
+  }
+  if (ws.counts[4]) {                 // uniform across the grid: nobody reaches a barrier
+    if (blockIdx.x == 0) {
+      bad_argument_step(d, ws, dx_out, nullptr, threadIdx.x, kTP);
+      if (status_out) for (int it = threadIdx.x; it < iterations; it += kTP) status_out[it] = 2;
+    }
+    return;
   }
   for (int it = 0; it < iterations; ++it) {
     BA_PROBE(0);
@@ -1029,6 +1055,47 @@ bool make_dims(int N, int num, int ht, int wd, int t0, int t1, BaDims* d) {
 
 constexpr int kSmemSolveMaxN = 160;   // (160*160 + 160) * 8 B = 206 KB of the 227 KB
 constexpr int kWarpSolveMaxN = 96;    // single-warp solve up to 16 poses
+constexpr int kMaxDevices = 64;
+
+// Function attributes (opt-in dynamic shared memory) and the occupancy of the cooperative kernel
+// are PER DEVICE: a process that runs BA on a second GPU must set them there too.  One slot per
+// device ordinal, initialised once under a mutex (the C-ABI may be called from several threads).
+struct BaDevice {
+  bool ready = false;
+  int sms = 0;
+  int blocks_per_sm = 0;      // 0: cooperative launch unavailable -> multi-kernel driver
+};
+
+void ba_persistent_kernel_attrs(BaDevice* dv, int dev) {
+  int occ = 0, coop = 0;
+  const size_t smem_max = ((size_t)kWarpSolveMaxN * kWarpSolveMaxN + 2 * kWarpSolveMaxN) * sizeof(double);
+  cudaDeviceGetAttribute(&dv->sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaFuncSetAttribute(ba_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ba_persistent_kernel, kTP, smem_max);
+  constexpr int kWant = 2;    // 2 blocks/SM measured best (profiles/r01: 1 -> 151 us, 2 -> 121 us, 3 -> 124 us)
+  dv->blocks_per_sm = (!coop || occ < 1) ? 0 : (occ > kWant ? kWant : occ);
+}
+
+const BaDevice& ba_device() {
+  static BaDevice table[kMaxDevices];
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  BaDevice& dv = table[dev];
+  if (!dv.ready) {
+    cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(((size_t)kSmemSolveMaxN * kSmemSolveMaxN + kSmemSolveMaxN) * 8));
+    cudaFuncSetAttribute(ba_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(((size_t)kWarpSolveMaxN * kWarpSolveMaxN + 2 * kWarpSolveMaxN) * 8));
+    ba_persistent_kernel_attrs(&dv, dev);
+    dv.ready = true;
+  }
+  return dv;
+}
+
 
 int launch_phase1(const float* poses, const float* disps, const float* intr,
                   const float* disps_sens, const float* targets, const float* weights,
@@ -1036,7 +1103,7 @@ int launch_phase1(const float* poses, const float* disps, const float* intr,
                   const BaDims& d, const BaWs& ws, int motion_only, bool prep, cudaStream_t st) {
   const BaIn in{poses, disps, intr, disps_sens, targets, weights, eta, eta_rows, ii, jj};
   if (prep) {
-    ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws, 0);
+    ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws, 0, motion_only ? 0 : eta_rows);
     GS_CHECK_LAUNCH();
   }
   cudaMemsetAsync(ws.sys, 0, ((size_t)d.n * d.n + d.n) * sizeof(double), st);
@@ -1058,14 +1125,8 @@ int launch_phase2(float* poses, float* disps, const double* sys_in,
                   const BaDims& d, const BaWs& ws, float lm, float ep, int motion_only,
                   int owner_lo, int owner_hi, float* dx_out, float* dz_out, int* status_out,
                   cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(((size_t)kSmemSolveMaxN * kSmemSolveMaxN + kSmemSolveMaxN) * 8));
-    cudaFuncSetAttribute(ba_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(((size_t)kWarpSolveMaxN * kWarpSolveMaxN + 2 * kWarpSolveMaxN) * 8));
-    attr_set = true;
-  }
+  const BaDevice& dv = ba_device();    // per-device function attributes are set on first use
+  (void)dv;
   if (d.n <= kWarpSolveMaxN) {
     const size_t smem = ((size_t)d.n * d.n + 2 * d.n) * sizeof(double);
     ba_solve_warp_kernel<<<1, 128, smem, st>>>(poses, d, ws, sys_in, lm, ep, dx_out, status_out);
@@ -1108,35 +1169,25 @@ int goslam_ba(float* poses, float* disps, const float* intrinsics, const float* 
               void* stream) {
   BaDims d;
   if (!make_dims(N, num, ht, wd, t0, t1, &d)) return GOSLAM_EINVAL;
-  if (!motion_only && (eta == nullptr || eta_rows < 1)) return GOSLAM_EINVAL;
+  if (!motion_only && (eta == nullptr || eta_rows == 0)) return GOSLAM_EINVAL;
   if (d.P == 0 || iterations <= 0) return GOSLAM_OK;
   BaWs ws;
   const size_t need = ba_layout(d, workspace, workspace_bytes, &ws);
   if (workspace == nullptr || need > workspace_bytes) return GOSLAM_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  static const bool multi_kernel = [] {
-    const char* e = getenv("GOSLAM_BA_MULTIKERNEL");
-    return e && e[0] == '1';
-  }();
+#ifdef GOSLAM_BA_FORCE_MULTIKERNEL      // build-time A/B switch (tools/), never in the shipped library
+  constexpr bool multi_kernel = true;
+#else
+  constexpr bool multi_kernel = false;
+#endif
   if (d.n <= kWarpSolveMaxN && !multi_kernel) {
-    static int blocks_per_sm = -1, sms = 0;
-    const size_t smem_max = ((size_t)kWarpSolveMaxN * kWarpSolveMaxN + 2 * kWarpSolveMaxN) * sizeof(double);
+    const BaDevice& dv = ba_device();
+    const int blocks_per_sm = dv.blocks_per_sm, sms = dv.sms;
     const size_t smem = ((size_t)d.n * d.n + 2 * d.n) * sizeof(double);
-    if (blocks_per_sm < 0) {
-      int dev = 0, occ = 0, coop = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-      cudaFuncSetAttribute(ba_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ba_persistent_kernel, kTP, smem_max);
-      int want = 2;
-      if (const char* e = getenv("GOSLAM_BA_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
-      blocks_per_sm = (!coop || occ < 1) ? 0 : (occ > want ? want : occ);
-    }
     if (blocks_per_sm > 0) {
       // two launches per call: the table kernel (which also zeroes the reduced system and the barrier
       // counter) and the cooperative kernel (which zeroes dz_out itself)
-      ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws, 1);
+      ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws, 1, motion_only ? 0 : eta_rows);
       GS_CHECK_LAUNCH();
       unsigned* barrier = reinterpret_cast<unsigned*>(ws.counts + 3);
       BaIn in{poses, disps, intrinsics, disps_sens, targets, weights, eta, eta_rows, ii, jj};

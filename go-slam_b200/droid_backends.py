@@ -59,9 +59,10 @@ def corr_index_forward(volume, coords, radius):
     N, h1, w1, h2, w2 = volume.shape
     rd = 2 * radius + 1
     corr = torch.empty((N, rd, rd, h1, w1), dtype=volume.dtype, device=volume.device)
+    coords_f = coords.float()          # named: a converted copy must outlive the launch
     with torch.cuda.device(volume.device):
         rc = _lib.load().goslam_corr_index_forward(
-            _lib.ptr(volume), _dtype_code(volume), _lib.ptr(coords.float()), _lib.ptr(corr),
+            _lib.ptr(volume), _dtype_code(volume), _lib.ptr(coords_f), _lib.ptr(corr),
             N, h1, w1, h2, w2, int(radius), _lib.stream_ptr())
     _lib.check(rc, "corr_index_forward")
     return [corr]
@@ -194,7 +195,7 @@ def reproject(poses, disps, intrinsics_all, ii, jj, want_valid=True):
 
 # ----------------------------------------------------------------------------- bundle adjustment
 def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj,
-       t0, t1, iterations, lm, ep, motion_only, return_status=False):
+       t0, t1, iterations, lm, ep, motion_only, return_status=False, eta_by_frame=False):
     """src/lib/droid.cpp:88-117.  In place on poses [num,7] / disps [num,ht,wd].
 
     Returns [dx (t1-t0, 6), dz].  dz is laid out [num, ht*wd] indexed by FRAME id (rows of
@@ -202,7 +203,12 @@ def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj,
     [len(unique frames), ht*wd]: producing the packed shape needs the size of a device-side
     unique(), i.e. a host sync per call, and every caller in the reference discards the
     return value (src/depth_video.py:266).  dz is None when motion_only (reference: undefined
-    tensor)."""
+    tensor).
+
+    eta: [M, ht, wd] with M = |unique([t0,t1) U ii)| rows in sorted frame order (what FactorGraph passes,
+    src/factor_graph.py:236-238), or one row.  A different row count leaves the state untouched and
+    reports status 2 (the reference raises a broadcast error there).  eta_by_frame=True (not in the
+    reference): eta is [num, ht, wd] indexed by frame id."""
     _contig(targets=targets, weights=weights, poses=poses, disps=disps, intrinsics=intrinsics,
             disps_sens=disps_sens, ii=ii, jj=jj)
     _need_cuda(poses, disps, intrinsics, disps_sens, targets, weights, ii, jj)
@@ -219,6 +225,10 @@ def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj,
     if not motion_only:
         eta_c = eta.contiguous().view(-1, ht * wd).float()
         eta_rows = int(eta_c.shape[0])
+        if eta_by_frame:
+            if eta_rows != num:
+                raise RuntimeError("ba: eta_by_frame needs one row per frame (%d), got %d" % (num, eta_rows))
+            eta_rows = -num
     dx = torch.zeros((P, 6), dtype=torch.float32, device=dev)
     dz = None if motion_only else torch.empty((num, ht * wd), dtype=torch.float32, device=dev)
     status = torch.zeros((max(int(iterations), 1),), dtype=torch.int32, device=dev)

@@ -114,13 +114,14 @@ class CorrBlock:
         f2 = fmap2.reshape(N, dim, ht, wd).contiguous()
         lib = _lib.load()
         if f1.dtype == torch.float16:
+            f2 = f2.half()             # named: a converted copy must outlive the launch
             levels = [torch.empty((N, ht, wd, ht >> i, wd >> i), dtype=torch.float16, device=dev)
                       for i in range(num_levels)]
             with torch.cuda.device(dev):
                 nbytes = lib.goslam_corr_build_workspace_bytes(N, dim, ht, wd)
                 ws = _workspace(nbytes, dev)
                 rc = lib.goslam_corr_build(
-                    _lib.ptr(f1), _lib.ptr(f2.half()), _ptr_array(levels), num_levels, N, dim, ht, wd,
+                    _lib.ptr(f1), _lib.ptr(f2), _ptr_array(levels), num_levels, N, dim, ht, wd,
                     int(impl), _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_ptr())
             _lib.check(rc, "corr_build")
         else:

@@ -41,50 +41,94 @@ def local_edges(ii, lo, hi):
 
 
 class CudaBackend:
-    """goslam_ba_phase1 / goslam_ba_phase2 on the current CUDA device."""
+    """goslam_ba_phase1 / goslam_ba_phase2 on the current CUDA device.
+
+    The backend OWNS its BA workspace: phase 2 reads what phase 1 left there (E, Q, w, the graph
+    tables), so it must not be the shared grow-only scratch other calls may reallocate in between."""
 
     def __init__(self, poses, disps, intrinsics, disps_sens, t0, t1):
         from . import _lib
-        from .droid_backends import _workspace
-        self._lib, self._workspace = _lib, _workspace
+        self._lib = _lib
         self.poses, self.disps, self.intr, self.sens = poses, disps, intrinsics, disps_sens
         self.t0, self.t1 = int(t0), int(t1)
         self.num, self.ht, self.wd = disps.shape
+        self._ws = None
+        self.N = 0
 
-    def _ws(self, N):
-        lib = self._lib.load()
-        n = lib.goslam_ba_workspace_bytes(N, self.num, self.ht, self.wd, self.t0, self.t1)
-        return self._workspace(n, self.poses.device)
+    def _workspace(self, N):
+        n = self._lib.load().goslam_ba_workspace_bytes(N, self.num, self.ht, self.wd, self.t0, self.t1)
+        if n == 0:
+            raise RuntimeError("sharded BA: invalid shapes (N=%d num=%d t0=%d t1=%d)" % (N, self.num, self.t0, self.t1))
+        if self._ws is None or self._ws.numel() < n:
+            self._ws = torch.empty(int(n), dtype=torch.uint8, device=self.poses.device)
+        return self._ws
 
     def phase1(self, targets, weights, eta_by_frame, ii, jj, motion_only):
         lib = self._lib.load()
         self.N = int(ii.shape[0])
-        ws = self._ws(self.N)
+        ws = self._workspace(self.N)
         n_sys = lib.goslam_ba_system_doubles(self.t0, self.t1)
         system = torch.empty(n_sys, dtype=torch.float64, device=self.poses.device)
-        # eta rows must follow this rank's own slot order (unique([t0,t1) U local ii))
-        kx = torch.unique(torch.cat([torch.arange(self.t0, self.t1, device=ii.device), ii]))
-        eta = eta_by_frame.view(self.num, -1)[kx].contiguous()
-        rc = lib.goslam_ba_phase1(
-            self._lib.ptr(self.poses), self._lib.ptr(self.disps), self._lib.ptr(self.intr), self._lib.ptr(self.sens),
-            self._lib.ptr(targets), self._lib.ptr(weights), self._lib.ptr(eta), int(eta.shape[0]),
-            self._lib.ptr(ii), self._lib.ptr(jj), self.N, self.num, self.ht, self.wd, self.t0, self.t1,
-            int(bool(motion_only)), self._lib.ptr(system), self._lib.ptr(ws), ctypes.c_size_t(ws.numel()),
-            self._lib.stream_ptr())
+        # eta is FRAME-indexed here ([num, ht, wd]; eta_rows == num selects that form in the kernel),
+        # so every rank reads the rows of its own frames whatever its local slot order is
+        eta = eta_by_frame.reshape(self.num, -1)
+        if not eta.is_contiguous() or eta.dtype != torch.float32:
+            eta = eta.float().contiguous()
+        with torch.cuda.device(self.poses.device):
+            rc = lib.goslam_ba_phase1(
+                self._lib.ptr(self.poses), self._lib.ptr(self.disps), self._lib.ptr(self.intr), self._lib.ptr(self.sens),
+                self._lib.ptr(targets), self._lib.ptr(weights), self._lib.ptr(eta), -int(eta.shape[0]),
+                self._lib.ptr(ii), self._lib.ptr(jj), self.N, self.num, self.ht, self.wd, self.t0, self.t1,
+                int(bool(motion_only)), self._lib.ptr(system), self._lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+                self._lib.stream_ptr())
         self._lib.check(rc, "ba_phase1")
         return system
 
-    def phase2(self, system, lm, ep, motion_only, owner_lo, owner_hi):
+    def phase2(self, system, lm, ep, motion_only, owner_lo, owner_hi, return_status=False):
         lib = self._lib.load()
-        ws = self._ws(self.N)
-        dx = torch.empty((self.t1 - self.t0, 6), dtype=torch.float32, device=self.poses.device)
-        rc = lib.goslam_ba_phase2(
-            self._lib.ptr(self.poses), self._lib.ptr(self.disps), self._lib.ptr(system), self.N, self.num,
-            self.ht, self.wd, self.t0, self.t1, float(lm), float(ep), int(bool(motion_only)),
-            int(owner_lo), int(owner_hi), self._lib.ptr(dx), None, None,
-            self._lib.ptr(ws), ctypes.c_size_t(ws.numel()), self._lib.stream_ptr())
+        ws = self._workspace(self.N)
+        dev = self.poses.device
+        dx = torch.empty((self.t1 - self.t0, 6), dtype=torch.float32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev) if return_status else None
+        with torch.cuda.device(dev):
+            rc = lib.goslam_ba_phase2(
+                self._lib.ptr(self.poses), self._lib.ptr(self.disps), self._lib.ptr(system), self.N, self.num,
+                self.ht, self.wd, self.t0, self.t1, float(lm), float(ep), int(bool(motion_only)),
+                int(owner_lo), int(owner_hi), self._lib.ptr(dx), None, self._lib.ptr(status),
+                self._lib.ptr(ws), ctypes.c_size_t(ws.numel()), self._lib.stream_ptr())
         self._lib.check(rc, "ba_phase2")
-        return dx
+        return (dx, status) if return_status else dx
+
+
+class RowExchange:
+    """Re-replication of the disparity rows each rank owns after the back-substitution: ONE
+    all-gather of [max_rows, hw] per rank (frame ranges are balanced by edge count, so they are padded
+    to the widest range) followed by one indexed copy — not one broadcast per rank."""
+
+    def __init__(self, disps, bounds, rank):
+        self.bounds, self.rank = bounds, rank
+        world = len(bounds)
+        self.hw = disps[0].numel()
+        self.max_rows = max(1, max(hi - lo for lo, hi in bounds))
+        self.send = disps.new_zeros((self.max_rows, self.hw))
+        self.recv = disps.new_zeros((world, self.max_rows, self.hw))
+        frames, src = [], []
+        for r, (lo, hi) in enumerate(bounds):
+            if r == rank:
+                continue
+            frames += list(range(lo, hi))
+            src += [r * self.max_rows + k for k in range(hi - lo)]
+        self.frames = torch.tensor(frames, dtype=torch.long, device=disps.device)
+        self.src = torch.tensor(src, dtype=torch.long, device=disps.device)
+
+    def __call__(self, disps, group=None):
+        lo, hi = self.bounds[self.rank]
+        flat = disps.view(disps.shape[0], self.hw)
+        if hi > lo:
+            self.send[:hi - lo].copy_(flat[lo:hi])
+        dist.all_gather(list(self.recv.unbind(0)), self.send, group=group)
+        if self.frames.numel():
+            flat.index_copy_(0, self.frames, self.recv.view(-1, self.hw).index_select(0, self.src))
 
 
 def sharded_ba(backend, disps, targets, weights, eta_by_frame, ii, jj, iterations, lm, ep,
@@ -93,7 +137,8 @@ def sharded_ba(backend, disps, targets, weights, eta_by_frame, ii, jj, iteration
 
     `targets` / `weights` / `ii` / `jj` are the FULL (replicated) edge list; each rank picks its
     shard.  `disps` is the replicated [num, ht, wd] tensor the backend mutates; `eta_by_frame` is
-    [num, ht, wd] (frame-indexed damping).  Returns the last dx."""
+    [num, ht, wd] (frame-indexed damping).  Per iteration: one all-reduce of the reduced camera
+    system, one all-gather of the owned disparity rows.  Returns the last dx."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     num = disps.shape[0]
@@ -102,15 +147,14 @@ def sharded_ba(backend, disps, targets, weights, eta_by_frame, ii, jj, iteration
     sel = local_edges(ii, lo, hi)
     tl, wl = targets[sel].contiguous(), weights[sel].contiguous()
     il, jl = ii[sel].contiguous(), jj[sel].contiguous()
+    exchange = None if motion_only or world == 1 else RowExchange(disps, bounds, rank)
     dx = None
     for _ in range(iterations):
         system = backend.phase1(tl, wl, eta_by_frame, il, jl, motion_only)
-        dist.all_reduce(system, op=dist.ReduceOp.SUM, group=group)        # the single exchange step
+        dist.all_reduce(system, op=dist.ReduceOp.SUM, group=group)        # exchange 1: reduced system
         dx = backend.phase2(system, lm, ep, motion_only, lo, hi)
-        if not motion_only:
-            for r, (a, b) in enumerate(bounds):                           # re-replicate owned rows
-                if b > a:
-                    dist.broadcast(disps[a:b], src=dist.get_global_rank(group, r) if group else r, group=group)
+        if exchange is not None:
+            exchange(disps, group)                                        # exchange 2: owned rows
     return dx
 
 

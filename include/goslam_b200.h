@@ -168,11 +168,17 @@ int goslam_reproject(const float* poses, const float* disps, const float* intrin
  * Dense bundle adjustment.  Replaces droid_backends.ba (src/lib/droid.cpp:88-117,
  * src/lib/droid_kernels.cu:1314-1434 + kernels :176-424,:854-1115 + the host Eigen
  * Schur/LLT :1117-1311).  poses and disps are updated IN PLACE.
- *   targets,weights [N,2,ht,wd] f32; eta [M,ht,wd] f32 with M = |unique([t0,t1) U ii)|
- *   (or a single row, broadcast); disps_sens [num,ht,wd].
+ *   targets,weights [N,2,ht,wd] f32; disps_sens [num,ht,wd].
+ *   eta [eta_rows,ht,wd] f32: eta_rows == M = |unique([t0,t1) U ii)| (rows in sorted frame order —
+ *   the reference's `damping[unique(cat(arange(t0,t1), ii))]`, src/factor_graph.py:236-238),
+ *   eta_rows == 1 (one row, broadcast) or eta_rows == -num (negative: eta is [num,ht,wd] indexed
+ *   by FRAME id — the form the sharded driver uses, where every rank has its own slot order).
+ *   Any other row count is a caller bug (the reference raises a broadcast error,
+ *   src/lib/droid_kernels.cu:1397): the call leaves poses/disps untouched, dx = 0, status 2.
  *   dx_out [t1-t0,6] (nullable), dz_out [num,ht*wd] indexed by FRAME id (nullable).
  *   status_out: device int[iterations] (nullable), 0 = solved, 1 = factorisation failed
- *   (then dx = 0 for that iteration, like src/lib/droid_kernels.cu:1207-1210).
+ *   (then dx = 0 for that iteration, like src/lib/droid_kernels.cu:1207-1210), 2 = eta row count
+ *   mismatch (see above).
  * Limits: num <= 4096 frames.
  * ---------------------------------------------------------------------------------- */
 size_t goslam_ba_workspace_bytes(int N, int num, int ht, int wd, int t0, int t1);
