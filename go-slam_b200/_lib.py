@@ -38,6 +38,7 @@ SIGNATURES = {
     "goslam_version": (c_int, []),
     "goslam_sm_arch": (c_int, []),
     "goslam_strerror": (ctypes.c_char_p, [c_int]),
+    "goslam_last_cuda_error": (ctypes.c_char_p, []),
     "goslam_corr_index_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     "goslam_corr_pyramid_lookup": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     "goslam_corr_build_workspace_bytes": (c_size_t, [c_int] * 4),
@@ -56,6 +57,7 @@ SIGNATURES = {
     "goslam_iproj": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "goslam_depth_filter": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),
     "goslam_reproject": (c_int, [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),
+    "goslam_reproject_motion": (c_int, [c_void_p] * 9 + [c_int] * 3 + [c_void_p]),
     "goslam_ba_workspace_bytes": (c_size_t, [c_int] * 6),
     "goslam_ba": (c_int, [c_void_p] * 7 + [c_int] + [c_void_p] * 2 + [c_int] * 7 +
                   [c_float, c_float, c_int] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
@@ -108,7 +110,9 @@ def load(build_if_missing=True):
 def check(rc, what):
     if rc != 0:
         msg = load().goslam_strerror(int(rc))
-        raise RuntimeError("%s failed: %s (code %d)" % (what, msg.decode() if msg else "?", rc))
+        detail = load().goslam_last_cuda_error() if int(rc) == -2 else b""
+        raise RuntimeError("%s failed: %s (code %d)%s" % (what, msg.decode() if msg else "?", rc,
+                                                          ": " + detail.decode() if detail else ""))
 
 
 def ptr(t):

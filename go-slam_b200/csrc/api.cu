@@ -1,7 +1,14 @@
 // api.cu — library identification / error strings for the C-ABI in include/goslam_b200.h.
 #include "common.cuh"
 
+static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
+void gs_note_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
+
 extern "C" {
+
+const char* goslam_last_cuda_error(void) {
+  return g_last_cuda_error == cudaSuccess ? "" : cudaGetErrorString(g_last_cuda_error);
+}
 
 int goslam_version(void) { return 100; }
 

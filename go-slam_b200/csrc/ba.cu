@@ -32,8 +32,10 @@
 // damping diag += ep + lm*diag (:1197); failed factorisation => dx = 0 (:1207-1210).
 #include "common.cuh"
 #include "se3.cuh"
+#include <algorithm>
 #include <cstdio>
 #include <mutex>
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -882,6 +884,268 @@ ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __re
 }
 
 // ------------------------------------------------------------------------------------
+// Global-BA-sized systems (96 < 6P, up to ~100 poses): ONE THREAD-BLOCK CLUSTER of kCl CTAs holds
+// the lower triangle of the reduced camera matrix in DISTRIBUTED SHARED MEMORY (6x6 pose blocks,
+// block row r lives in CTA r % kCl) and runs the same right-looking 6x6-blocked Cholesky as
+// solve_small, with hardware cluster barriers between the phases of a block column:
+//   (A) the 6x6 diagonal block is fetched from its owner (36 DSMEM loads) and factored redundantly
+//       in registers by the threads that need it; (B) every CTA solves the panel blocks of ITS rows
+//       (and its replica of the right-hand-side row: forward substitution rides along);
+//   --- cluster barrier --- (C) the block column is gathered from its owners into a local buffer
+//   (DSMEM loads, <= 9 per thread) and (D) the trailing update of the CTA's own rows runs out of local
+//   shared memory; --- cluster barrier ---.
+// Backward substitution: right-looking over block rows, each owner folding x_jb into a LOCAL vector of
+// partial sums that the next owner collects through DSMEM; one cluster barrier per block row.
+// P = 63 (config 4): 378 unknowns, 80 KB of matrix per CTA.  Replaces a single-block factorisation out
+// of global scratch that needed 5.2 ms per solve (tools/time_ba_large.py) — the reference does this
+// step on the host with Eigen SimplicialLLT (src/lib/droid_kernels.cu:1192-1213).
+// ------------------------------------------------------------------------------------
+constexpr int kCl = 8;        // portable cluster size
+constexpr int kClT = 256;     // threads per CTA
+
+__host__ __device__ inline int cl_row_off(int q, int l) {      // doubles before local block row l of CTA q
+  return 36 * (l * (q + 1) + kCl * (l * (l - 1) / 2));
+}
+inline size_t cl_rows_doubles(int P) {                         // largest per-CTA matrix slice
+  size_t mx = 0;
+  for (int q = 0; q < kCl; ++q) {
+    const int nl = (P - q + kCl - 1) / kCl;
+    if (nl > 0) mx = std::max(mx, (size_t)cl_row_off(q, nl));
+  }
+  return mx;
+}
+inline size_t cl_smem_bytes(int P) {
+  return (cl_rows_doubles(P) + 2 * (size_t)(6 * P) + (size_t)P * 36 + 36 + 16) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(kClT)
+ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restrict__ sys_in, float lm,
+                        float ep, int rows_doubles, float* dx_out, int* status_out) {
+  namespace cg = cooperative_groups;
+  extern __shared__ double smd[];
+  __shared__ int failed;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int q = (int)cluster.block_rank();
+  const int P = d.P, n = d.n, tid = threadIdx.x;
+  if (ws.counts[4]) {                                  // uniform over the cluster
+    if (q == 0) bad_argument_step(d, ws, dx_out, status_out, tid, kClT);
+    return;
+  }
+  double* rows = smd;                                  // own block rows, row l = blocks 0..r (r = q + l*kCl)
+  double* rhs = smd + rows_doubles;                    // [n]  replica of the right-hand side -> y = L^-1 b
+  double* ps = rhs + n;                                // [n]  backward substitution: local partial sums
+  double* panel = ps + n;                              // [P][36] gathered block column
+  double* dloc = panel + (size_t)P * 36;               // [36] diagonal block of the current column
+  double* xs = dloc + 36;                              // [6] + [6]
+  const int nl = (P - q + kCl - 1) / kCl;              // own block rows (may be <= 0 for tiny P)
+
+  // ---- load own rows (lower blocks incl. the diagonal one), damping on the diagonal
+  for (int l = 0; l < nl; ++l) {
+    const int r = q + l * kCl;
+    double* dst = rows + cl_row_off(q, l);
+    const int width = 6 * (r + 1);
+    for (int idx = tid; idx < 6 * width; idx += kClT) {
+      const int a = idx / width, col = idx - a * width;
+      double val = sys_in[(size_t)(6 * r + a) * n + col];
+      if (col == 6 * r + a) val += (double)ep + (double)lm * val;
+      dst[(col / 6) * 36 + a * 6 + (col % 6)] = val;
+    }
+  }
+  for (int i = tid; i < n; i += kClT) { rhs[i] = sys_in[(size_t)n * n + i]; ps[i] = 0.0; }
+  if (tid == 0) failed = 0;
+  cluster.sync();
+
+  bool bad = false;
+  for (int jb = 0; jb < P; ++jb) {
+    const int owner = jb % kCl, lo = jb / kCl;
+    // (A) diagonal block from its owner
+    if (tid < 36) {
+      const double* src = cluster.map_shared_rank(rows, owner) + cl_row_off(owner, lo) + jb * 36;
+      dloc[tid] = src[tid];
+    }
+    __syncthreads();
+    // first own block row below jb
+    const int l0 = jb < q ? 0 : (jb - q) / kCl + 1;
+    const int npan = nl > l0 ? nl - l0 : 0;
+    double l[6][6];
+    if (tid < 6 * npan || tid == 0) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) l[r][c] = dloc[r * 6 + c];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double dkk = l[k][k];
+#pragma unroll
+        for (int m = 0; m < k; ++m) dkk -= l[k][m] * l[k][m];
+        bad = bad || !(dkk > 0.0);
+        const double inv = rsqrt(dkk);
+        l[k][k] = inv;
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r) {
+          double v = l[r][k];
+#pragma unroll
+          for (int m = 0; m < k; ++m) v -= l[r][m] * l[k][m];
+          l[r][k] = v * inv;
+        }
+      }
+      // (B) panel: one scalar row of one own block per thread
+      if (tid < 6 * npan) {
+        const int lr = l0 + tid / 6, a = tid % 6;
+        double* blk = rows + cl_row_off(q, lr) + jb * 36 + a * 6;
+        double x[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) x[k] = blk[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double v = x[k];
+#pragma unroll
+          for (int m = 0; m < k; ++m) v -= x[m] * l[k][m];
+          x[k] = v * l[k][k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) blk[k] = x[k];
+      }
+      if (tid == 0) {                                 // right-hand-side row (replicated in every CTA)
+        double x[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) x[k] = rhs[6 * jb + k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double v = x[k];
+#pragma unroll
+          for (int m = 0; m < k; ++m) v -= x[m] * l[k][m];
+          x[k] = v * l[k][k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { rhs[6 * jb + k] = x[k]; xs[k] = x[k]; }
+      }
+    }
+    cluster.sync();                                   // panel blocks visible cluster-wide
+    if (q == owner && tid == 0) {                     // keep L_d (strictly lower + 1/l_kk) for the backward pass
+      double* blk = rows + cl_row_off(q, lo) + jb * 36;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) blk[r * 6 + c] = l[r][c];
+    }
+    // (C) gather the block column below the diagonal
+    {
+      const int cnt = (P - 1 - jb) * 36;
+      for (int idx = tid; idx < cnt; idx += kClT) {
+        const int c = jb + 1 + idx / 36, e = idx % 36;
+        const int oq = c % kCl;
+        const double* src = cluster.map_shared_rank(rows, oq) + cl_row_off(oq, c / kCl) + jb * 36;
+        panel[(size_t)c * 36 + e] = src[e];
+      }
+    }
+    __syncthreads();
+    // (D) trailing update of own rows: A[i,c] -= L[i,jb] L[c,jb]^T, jb < c <= i; one (c, row a) per item
+    for (int lr = l0; lr < nl; ++lr) {
+      const int r = q + lr * kCl;
+      double* rowp = rows + cl_row_off(q, lr);
+      const double* Li = rowp + jb * 36;
+      const int items = (r - jb) * 6;
+      for (int it = tid; it < items; it += kClT) {
+        const int c = jb + 1 + it / 6, a = it % 6;
+        double li[6], acc[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) li[k] = Li[a * 6 + k];
+        double* out = rowp + c * 36 + a * 6;
+        const double* Lc = panel + (size_t)c * 36;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+          double v = out[b];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) v -= li[k] * Lc[b * 6 + k];
+          acc[b] = v;
+        }
+#pragma unroll
+        for (int b = 0; b < 6; ++b) out[b] = acc[b];
+      }
+    }
+    // right-hand-side row: b[c] -= y_jb L[c,jb]^T
+    for (int it = tid; it < (P - 1 - jb) * 6; it += kClT) {
+      const int c = jb + 1 + it / 6, b = it % 6;
+      const double* Lc = panel + (size_t)c * 36 + b * 6;
+      double v = rhs[6 * c + b];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v -= xs[k] * Lc[k];
+      rhs[6 * c + b] = v;
+    }
+    cluster.sync();                                   // next diagonal block is final
+  }
+  if (bad && tid == 0) failed = 1;
+  __syncthreads();
+
+  // ---- backward substitution L^T x = y (only when the factorisation succeeded — uniform: every CTA
+  // factored the same diagonal blocks)
+  if (!failed) {
+    for (int jb = P - 1; jb >= 0; --jb) {
+      const int owner = jb % kCl, lo = jb / kCl;
+      if (q == owner) {
+        if (tid < 6) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int oq = 0; oq < kCl; ++oq) sacc += cluster.map_shared_rank(ps, oq)[6 * jb + tid];
+          xs[6 + tid] = rhs[6 * jb + tid] - sacc;
+        }
+        __syncthreads();
+        const double* Ld = rows + cl_row_off(q, lo) + jb * 36;
+        if (tid == 0) {
+          double x[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) x[k] = xs[6 + k];
+          int nf = 0;
+#pragma unroll
+          for (int k = 5; k >= 0; --k) {
+            double v = x[k];
+#pragma unroll
+            for (int m = k + 1; m < 6; ++m) v -= Ld[m * 6 + k] * x[m];
+            x[k] = v * Ld[k * 6 + k];
+            nf |= !isfinite(x[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { xs[k] = x[k]; ws.dx[6 * jb + k] = (float)x[k]; }
+          if (nf) failed = 1;
+        }
+        __syncthreads();
+        const double* rowp = rows + cl_row_off(q, lo);
+        for (int it = tid; it < jb * 6; it += kClT) {
+          const int c = it / 6, k = it % 6;
+          const double* blk = rowp + c * 36;
+          double v = ps[6 * c + k];
+#pragma unroll
+          for (int m = 0; m < 6; ++m) v += blk[m * 6 + k] * xs[m];
+          ps[6 * c + k] = v;
+        }
+      }
+      cluster.sync();
+    }
+  }
+  // ---- status, dx, retraction (CTA 0); the others stay until their flags have been read
+  if (q == 0) {
+    __shared__ int any_fail;
+    if (tid == 0) {
+      int f = 0;
+      for (int oq = 0; oq < kCl; ++oq) f |= *cluster.map_shared_rank(&failed, oq);
+      any_fail = f;
+    }
+    __syncthreads();
+    const int fail = any_fail;
+    for (int i = tid; i < n; i += kClT) {
+      const float val = fail ? 0.0f : ws.dx[i];
+      ws.dx[i] = val;
+      if (dx_out) dx_out[i] = val;
+    }
+    if (tid == 0 && status_out) *status_out = fail;
+    __syncthreads();
+    retract_poses(poses, d, ws, tid, kClT);
+  }
+  cluster.sync();
+}
+
+// ------------------------------------------------------------------------------------
 // Depth back-substitution + retraction: dz = Q (w - sum_a E_a^T dx[pose_a]), disps += dz.
 // (EvT6x1 + accum + disp_retr, :1095-1115,:1417,:933-946)
 // ------------------------------------------------------------------------------------
@@ -1056,6 +1320,7 @@ bool make_dims(int N, int num, int ht, int wd, int t0, int t1, BaDims* d) {
 constexpr int kSmemSolveMaxN = 160;   // (160*160 + 160) * 8 B = 206 KB of the 227 KB
 constexpr int kWarpSolveMaxN = 96;    // single-warp solve up to 16 poses
 constexpr int kMaxDevices = 64;
+constexpr size_t kClusterSmemMax = 226 * 1024;   // dynamic part of the 227 KB per-CTA opt-in maximum (static: a few bytes)
 
 // Function attributes (opt-in dynamic shared memory) and the occupancy of the cooperative kernel
 // are PER DEVICE: a process that runs BA on a second GPU must set them there too.  One slot per
@@ -1090,6 +1355,8 @@ const BaDevice& ba_device() {
                          (int)(((size_t)kSmemSolveMaxN * kSmemSolveMaxN + kSmemSolveMaxN) * 8));
     cudaFuncSetAttribute(ba_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(((size_t)kWarpSolveMaxN * kWarpSolveMaxN + 2 * kWarpSolveMaxN) * 8));
+    cudaFuncSetAttribute(ba_solve_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)kClusterSmemMax);
     ba_persistent_kernel_attrs(&dv, dev);
     dv.ready = true;
   }
@@ -1130,6 +1397,22 @@ int launch_phase2(float* poses, float* disps, const double* sys_in,
   if (d.n <= kWarpSolveMaxN) {
     const size_t smem = ((size_t)d.n * d.n + 2 * d.n) * sizeof(double);
     ba_solve_warp_kernel<<<1, 128, smem, st>>>(poses, d, ws, sys_in, lm, ep, dx_out, status_out);
+  } else if (cl_smem_bytes(d.P) <= kClusterSmemMax) {
+    // one 8-CTA cluster, matrix in distributed shared memory
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kCl);
+    cfg.blockDim = dim3(kClT);
+    cfg.dynamicSmemBytes = cl_smem_bytes(d.P);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int rows_doubles = (int)cl_rows_doubles(d.P);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, ba_solve_cluster_kernel, poses, d, ws, sys_in, lm, ep,
+                                              rows_doubles, dx_out, status_out);
+    if (le != cudaSuccess) { gs_note_cuda_error(le); return GOSLAM_ELAUNCH; }
   } else {
     const int use_smem = d.n <= kSmemSolveMaxN;
     const size_t smem = use_smem ? ((size_t)d.n * d.n + d.n) * sizeof(double) : 0;
@@ -1195,9 +1478,9 @@ int goslam_ba(float* poses, float* disps, const float* intrinsics, const float* 
       BaWs wsv = ws;
       void* args[] = {&poses, &disps, &in, &dd, &wsv, &iterations, &lm, &ep, &motion_only,
                       &dx_out, &dz_out, &status_out, &barrier};
-      if (cudaLaunchCooperativeKernel((const void*)ba_persistent_kernel, dim3(sms * blocks_per_sm),
-                                      dim3(kTP), args, smem, st) != cudaSuccess)
-        return GOSLAM_ELAUNCH;
+      const cudaError_t le = cudaLaunchCooperativeKernel((const void*)ba_persistent_kernel,
+                                                         dim3(sms * blocks_per_sm), dim3(kTP), args, smem, st);
+      if (le != cudaSuccess) { gs_note_cuda_error(le); return GOSLAM_ELAUNCH; }
       return GOSLAM_OK;
     }
   }

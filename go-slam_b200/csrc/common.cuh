@@ -7,10 +7,13 @@
 
 #define GS_MIN_DEPTH 0.25f   // src/lib/droid_kernels.cu:26 (CUDA side; the Python side uses 0.2)
 
+// the CUDA error behind the most recent GOSLAM_ELAUNCH of this thread (goslam_last_cuda_error)
+void gs_note_cuda_error(cudaError_t e);
+
 #define GS_CHECK_LAUNCH()                                        \
   do {                                                           \
     cudaError_t e__ = cudaGetLastError();                        \
-    if (e__ != cudaSuccess) return GOSLAM_ELAUNCH;               \
+    if (e__ != cudaSuccess) { gs_note_cuda_error(e__); return GOSLAM_ELAUNCH; } \
   } while (0)
 
 __host__ __device__ static inline int gs_cdiv(int a, int b) { return (a + b - 1) / b; }

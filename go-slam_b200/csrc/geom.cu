@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(kThreads)
 reproject_kernel(const float* __restrict__ poses, const float* __restrict__ disps,
                  const float* __restrict__ intr_all, const int64_t* __restrict__ ii,
                  const int64_t* __restrict__ jj, float* __restrict__ coords,
-                 float* __restrict__ valid, int ht, int wd) {
+                 float* __restrict__ valid, const float* __restrict__ target,
+                 float* __restrict__ motion, int ht, int wd) {
   const int e = blockIdx.y;
   const int k = blockIdx.x * kThreads + threadIdx.x;
   const int ix = (int)ii[e], jx = (int)jj[e];
@@ -182,6 +183,17 @@ reproject_kernel(const float* __restrict__ poses, const float* __restrict__ disp
   c.y = Kj[1] * (X1[1] / Z) + Kj[3];
   reinterpret_cast<float2*>(coords)[(size_t)e * ht * wd + k] = c;
   if (valid) valid[(size_t)e * ht * wd + k] = (X1[2] > 0.2f) ? 1.0f : 0.0f;
+  if (motion) {
+    // FactorGraph.update's motion features (src/factor_graph.py:204-206):
+    // cat([coords1 - coords0, target - coords1], -1).permute(0,1,4,2,3).clamp(-64, 64)
+    const float2 t = reinterpret_cast<const float2*>(target)[(size_t)e * ht * wd + k];
+    float* m = motion + (size_t)e * 4 * ht * wd + k;
+    const size_t hw = (size_t)ht * wd;
+    m[0] = fminf(fmaxf(c.x - u, -64.f), 64.f);
+    m[hw] = fminf(fmaxf(c.y - v, -64.f), 64.f);
+    m[2 * hw] = fminf(fmaxf(t.x - c.x, -64.f), 64.f);
+    m[3 * hw] = fminf(fmaxf(t.y - c.y, -64.f), 64.f);
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -315,7 +327,19 @@ int goslam_reproject(const float* poses, const float* disps, const float* intrin
   if (K == 0) return GOSLAM_OK;
   dim3 grid(gs_cdiv(ht * wd, kThreads), K);
   reproject_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(poses, disps, intrinsics_all, ii,
-                                                                jj, coords, valid, ht, wd);
+                                                                jj, coords, valid, nullptr, nullptr, ht, wd);
+  GS_CHECK_LAUNCH();
+  return GOSLAM_OK;
+}
+
+int goslam_reproject_motion(const float* poses, const float* disps, const float* intrinsics_all,
+                            const int64_t* ii, const int64_t* jj, const float* target, float* coords,
+                            float* valid, float* motion, int K, int ht, int wd, void* stream) {
+  if (K < 0 || ht <= 0 || wd <= 0 || target == nullptr || motion == nullptr) return GOSLAM_EINVAL;
+  if (K == 0) return GOSLAM_OK;
+  dim3 grid(gs_cdiv(ht * wd, kThreads), K);
+  reproject_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(poses, disps, intrinsics_all, ii,
+                                                                jj, coords, valid, target, motion, ht, wd);
   GS_CHECK_LAUNCH();
   return GOSLAM_OK;
 }

@@ -193,6 +193,25 @@ def reproject(poses, disps, intrinsics_all, ii, jj, want_valid=True):
     return coords, valid
 
 
+def reproject_motion(poses, disps, intrinsics_all, ii, jj, target):
+    """DepthVideo.reproject + FactorGraph's motion features in one launch (src/factor_graph.py:202-206):
+    returns coords1 [1,N,h,w,2] and motion [1,N,4,h,w] = clamp(cat([coords1 - coords0, target - coords1]), +-64)."""
+    _contig(poses=poses, disps=disps, intrinsics_all=intrinsics_all, ii=ii, jj=jj, target=target)
+    _need_cuda(poses, disps, intrinsics_all, ii, jj, target)
+    K = ii.shape[0]
+    ht, wd = disps.shape[1], disps.shape[2]
+    if target.dtype != torch.float32 or target.numel() != K * ht * wd * 2:
+        raise RuntimeError("reproject_motion: target must be float32 [1, N, ht, wd, 2]")
+    coords = torch.empty((1, K, ht, wd, 2), dtype=torch.float32, device=poses.device)
+    motion = torch.empty((1, K, 4, ht, wd), dtype=torch.float32, device=poses.device)
+    with torch.cuda.device(poses.device):
+        rc = _lib.load().goslam_reproject_motion(
+            _lib.ptr(poses), _lib.ptr(disps), _lib.ptr(intrinsics_all), _lib.ptr(ii), _lib.ptr(jj),
+            _lib.ptr(target), _lib.ptr(coords), None, _lib.ptr(motion), K, ht, wd, _lib.stream_ptr())
+    _lib.check(rc, "reproject_motion")
+    return coords, motion
+
+
 # ----------------------------------------------------------------------------- bundle adjustment
 def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj,
        t0, t1, iterations, lm, ep, motion_only, return_status=False, eta_by_frame=False):

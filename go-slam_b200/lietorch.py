@@ -151,6 +151,34 @@ class SE3:
     def retr(self, xi):
         return SE3.exp(xi).mul(self)
 
+    def log(self):
+        """inverse of `exp` ([..., 6] = (tau, phi)); call site: PoseTrajectoryFiller, dP.log() / dt
+        (src/trajectory_filler.py:53).  Rotation vector from the quaternion (atan2 form, sign-safe for
+        qw < 0), then tau = V(phi)^-1 t with the same closed form `exp` inverts and the same small-angle
+        switch-over (t = tau at or below theta = 1e-4 rad)."""
+        t, q = self.data[..., :3], self.data[..., 3:]
+        qv, qw = q[..., :3], q[..., 3:]
+        n2 = (qv * qv).sum(-1, keepdim=True)
+        n = n2.sqrt()
+        small = n2 < 1e-12
+        n_safe = torch.where(small, torch.ones_like(n), n)
+        # 2*atan(n/w)/n, written with atan2 so that w <= 0 (rotations beyond pi) stays continuous
+        sgn = torch.where(qw < 0, -torch.ones_like(qw), torch.ones_like(qw))
+        two_atan = torch.where(small, 2.0 / qw - (2.0 / 3.0) * n2 / (qw * qw * qw),
+                               2.0 * sgn * torch.atan2(n_safe, qw * sgn) / n_safe)
+        phi = two_atan * qv
+        th2 = (phi * phi).sum(-1, keepdim=True)
+        th = th2.sqrt()
+        big = th > 1e-4
+        th_safe = torch.where(big, th, torch.ones_like(th))
+        half = 0.5 * th_safe
+        coef = (1.0 - th_safe * torch.cos(half) / (2.0 * torch.sin(half))) / (th_safe * th_safe)
+        c1 = torch.linalg.cross(phi, t, dim=-1)
+        c2 = torch.linalg.cross(phi, c1, dim=-1)
+        # below the threshold `exp` (like expSE3, src/lib/droid_kernels.cu:160) leaves t = tau untouched
+        tau = torch.where(big, t - 0.5 * c1 + coef * c2, t)
+        return torch.cat([tau, phi], dim=-1)
+
 
 class Sim3(SE3):
     """placeholder so `isinstance(G, Sim3)` checks in projective_ops.actp resolve (never built)."""

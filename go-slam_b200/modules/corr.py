@@ -5,7 +5,7 @@ CorrBlock(fmap1, fmap2)      -> tcgen05 all-pairs build + in-epilogue 4-level py
                                 (goslam_corr_build; reference: torch.matmul + 3x avg_pool2d)
 CorrBlock.__call__(coords)   -> ONE fused 4-level radius-3 lookup (goslam_corr_pyramid_lookup;
                                 reference: 4 x corr_index_forward + torch.cat)
-AltCorrBlock(fmaps)(coords, ii, jj) -> windowed correlation per level (goslam_altcorr_forward)
+AltCorrBlock(fmaps)(coords, ii, jj) -> windowed correlation, all levels in one launch (goslam_altcorr_pyramid)
 """
 import ctypes
 
@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _lib
-from ..droid_backends import _workspace, altcorr_forward
+from ..droid_backends import _workspace
 
 
 def _ptr_array(tensors):
@@ -96,6 +96,21 @@ class CorrPool:
 
     def release(self, slots):
         self._free.extend(reversed(list(slots)))
+
+    def grow(self, capacity):
+        """enlarge the pool (graphs created with max_factors = -1 have no bound, e.g. PoseTrajectoryFiller's,
+        src/trajectory_filler.py:63): new buffers, one copy of the old slots, slot ids stay valid."""
+        capacity = int(capacity)
+        if capacity <= self.capacity:
+            return
+        dev = self.levels[0].device
+        for i, old in enumerate(self.levels):
+            new = torch.empty((capacity,) + tuple(old.shape[1:]), dtype=old.dtype, device=dev)
+            new[:self.capacity].copy_(old)
+            self.levels[i] = new
+        self._free = list(range(capacity - 1, self.capacity - 1, -1)) + self._free
+        self._iota = torch.arange(capacity, dtype=torch.int32, device=dev)
+        self.capacity = capacity
 
 
 class CorrBlock:
@@ -291,28 +306,14 @@ class AltCorrBlock:
             if lvl + 1 < num_levels:
                 level = F.avg_pool2d(level, kernel_size=2, stride=2)
 
-    def corr_fn(self, coords, ii, jj):
-        """reference-shaped path: one altcorr_forward per level on gathered fp32 maps
-        (coords [B, N, H, W, S, 2] -> [B, N, L*(2r+1)^2, H, W, S])."""
-        b, n, h, w, s, _ = coords.shape
-        pts = coords.permute(0, 1, 4, 2, 3, 5)
-        src = self.pyramid[0][:, ii]
-        src = src.reshape((b * n,) + tuple(src.shape[2:])).float().contiguous()
-        per_level = []
-        for lvl, maps in enumerate(self.pyramid):
-            tgt = maps[:, jj]
-            tgt = tgt.reshape((b * n,) + tuple(tgt.shape[2:])).float().contiguous()
-            pts_l = (pts / float(1 << lvl)).reshape(b * n, s, h, w, 2).contiguous()
-            corr, = altcorr_forward(src, tgt, pts_l, self.radius)
-            per_level.append(corr.view(b, n, s, -1, h, w).permute(0, 1, 3, 4, 5, 2))
-        return torch.cat(per_level, dim=2)
-
     def __call__(self, coords, ii, jj):
+        """coords [B, N, H, W, 2] (what FactorGraph.update_lowmem passes) or [B, N, H, W, S, 2] (S coordinate
+        sets per edge, the reference's general form): [B, N, L*(2r+1)^2, H, W(, S)] in float32."""
+        if not coords.is_cuda:
+            raise RuntimeError("AltCorrBlock: CUDA tensors required (no CPU fallback)")
         if coords.dim() == 5:
-            if coords.is_cuda and self.pyramid[0].dtype == torch.float16:
-                return self._fused(coords, ii, jj)            # one launch, all levels, tensor cores
-            return self.corr_fn(coords.unsqueeze(-2), ii, jj).squeeze(-1).contiguous()
-        return self.corr_fn(coords, ii, jj).contiguous()
+            return self._fused(coords, ii, jj)
+        return torch.stack([self._fused(coords[..., s, :], ii, jj) for s in range(coords.shape[-2])], dim=-1)
 
     def _fused(self, coords, ii, jj):
         """one launch for all levels, feature maps indexed per edge on the device."""
@@ -323,7 +324,7 @@ class AltCorrBlock:
         dev = coords.device
         rd = 2 * self.radius + 1
         out = torch.empty((1, N, self.num_levels * rd * rd, H, W), dtype=torch.float32, device=dev)
-        pyr = [p.contiguous() for p in self.pyramid]
+        pyr = [p.contiguous() if p.dtype == torch.float16 else p.half().contiguous() for p in self.pyramid]
         ii = torch.as_tensor(ii, device=dev).long().contiguous()
         jj = torch.as_tensor(jj, device=dev).long().contiguous()
         c = coords.reshape(N, H, W, 2).float().contiguous()

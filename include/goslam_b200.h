@@ -35,6 +35,8 @@ extern "C" {
 int goslam_version(void);
 int goslam_sm_arch(void);
 const char* goslam_strerror(int code);
+/* cudaGetErrorString of the CUDA error behind this thread's most recent GOSLAM_ELAUNCH ("" if none) */
+const char* goslam_last_cuda_error(void);
 
 /* ------------------------------------------------------------------------------------
  * Correlation volume — radius-r bilinear window lookup, one pyramid level.
@@ -163,6 +165,13 @@ int goslam_depth_filter(const float* poses, const float* disps, const float* int
 int goslam_reproject(const float* poses, const float* disps, const float* intrinsics_all,
                      const int64_t* ii, const int64_t* jj, float* coords, float* valid,
                      int K, int ht, int wd, void* stream);
+/* reproject + the motion features FactorGraph.update feeds the update operator
+ * (src/factor_graph.py:202-206): motion [K,4,ht,wd] = clamp(cat([coords1 - coords0, target - coords1]),
+ * -64, 64) with coords0 the pixel grid and target [K,ht,wd,2] the edge's current flow target; one
+ * launch instead of reproject + 5 elementwise kernels.  valid may be NULL. */
+int goslam_reproject_motion(const float* poses, const float* disps, const float* intrinsics_all,
+                            const int64_t* ii, const int64_t* jj, const float* target, float* coords,
+                            float* valid, float* motion, int K, int ht, int wd, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Dense bundle adjustment.  Replaces droid_backends.ba (src/lib/droid.cpp:88-117,

@@ -218,9 +218,24 @@ def test_altcorr_forward():
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=1e-4)
 
 
+def _altcorr_per_level_twin(blk, coords, ii, jj):
+    """test twin of AltCorrBlock: one drop-in `altcorr_forward` launch per level on gathered fp32 maps — the
+    shape of the reference's own path (src/modules/corr.py:113-131), kept HERE as a checker only."""
+    from goslam_b200 import droid_backends
+    b, n, h, w, s, _ = coords.shape
+    pts = coords.permute(0, 1, 4, 2, 3, 5)
+    src = blk.pyramid[0][0, ii].float().contiguous()
+    outs = []
+    for lvl, maps in enumerate(blk.pyramid):
+        tgt = maps[0, jj].float().contiguous()
+        c, = droid_backends.altcorr_forward(src, tgt, (pts / float(1 << lvl)).reshape(n, s, h, w, 2).contiguous(), blk.radius)
+        outs.append(c.view(b, n, s, -1, h, w).permute(0, 1, 3, 4, 5, 2))
+    return torch.cat(outs, dim=2)
+
+
 def test_altcorr_block_fused_matches_per_level_path():
-    """AltCorrBlock(fmaps)(coords, ii, jj): fused indexed half-precision launch == the reference-shaped
-    per-level path (gather + .float() + altcorr_forward) == the oracle."""
+    """AltCorrBlock(fmaps)(coords, ii, jj): fused indexed half-precision tensor-core launch == per-level
+    drop-in altcorr_forward launches on gathered fp32 maps == the oracle; 5-D and 6-D (S sets) coords."""
     from goslam_b200.modules import AltCorrBlock
     g = torch.Generator().manual_seed(8)
     F, H, W, N = 6, 30, 40, 9
@@ -231,13 +246,42 @@ def test_altcorr_block_fused_matches_per_level_path():
     base = torch.stack(torch.meshgrid(torch.arange(W).float(), torch.arange(H).float(), indexing="xy"), -1)
     coords = (base[None, None].repeat(1, N, 1, 1, 1) + 3 * torch.randn(1, N, H, W, 2, generator=g)).to(dev())
     fused = blk(coords, ii, jj)
-    slow = blk.corr_fn(coords.unsqueeze(-2), ii, jj).squeeze(-1).contiguous()
+    slow = _altcorr_per_level_twin(blk, coords.unsqueeze(-2), ii, jj).squeeze(-1).contiguous()
     assert fused.shape == slow.shape == (1, N, 196, H, W)
     assert (fused - slow).abs().max().item() < 1e-4 * max(1.0, slow.abs().max().item())
     lvl = 2
     ref = corr_oracle.altcorr_forward(blk.pyramid[0][0, ii].float().cpu().numpy(), blk.pyramid[lvl][0, jj].float().cpu().numpy(),
                                       (coords[0] / 2 ** lvl).unsqueeze(1).cpu().numpy(), 3)
     np.testing.assert_allclose(fused[0, :, 49 * lvl:49 * (lvl + 1)].cpu().numpy(), ref[:, 0], rtol=1e-4, atol=1e-4)
+    c6 = torch.stack([coords, coords + torch.tensor([0.25, -0.5], device=dev())], dim=-2)      # S = 2
+    out6 = blk(c6, ii, jj)
+    want6 = _altcorr_per_level_twin(blk, c6, ii, jj)
+    assert out6.shape == want6.shape == (1, N, 196, H, W, 2)
+    assert torch.equal(out6[..., 0], fused)
+    assert (out6 - want6).abs().max().item() < 1e-4 * max(1.0, want6.abs().max().item())
+
+
+def test_altcorr_block_vs_reference_class_golden():
+    """outputs of the REFERENCE AltCorrBlock class (src/modules/corr.py:113-145; golden made with the oracle
+    standing in for its CUDA op, fp32 maps): gather per edge, coords / 2^l, channel order, 5-D and 6-D coords.
+    The per-level twin on the drop-in fp32 kernel reproduces it to fp32 summation order; the fused
+    half-precision launch to the half rounding of the pooled maps."""
+    from goslam_b200.modules import AltCorrBlock
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "altcorr_block.npz"))
+    fm = torch.from_numpy(g["fmaps"]).to(dev())
+    ii, jj = torch.from_numpy(g["ii"]).to(dev()), torch.from_numpy(g["jj"]).to(dev())
+    c5, c6 = torch.from_numpy(g["coords"]).to(dev()), torch.from_numpy(g["coords6"]).to(dev())
+    blk32 = AltCorrBlock(fm)
+    out5 = _altcorr_per_level_twin(blk32, c5.unsqueeze(-2), ii, jj).squeeze(-1)
+    out6 = _altcorr_per_level_twin(blk32, c6, ii, jj)
+    np.testing.assert_allclose(out5[:, :, ::7].cpu().numpy(), g["out5"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(out6[:, :, ::7].cpu().numpy(), g["out6"], rtol=1e-4, atol=1e-4)
+    blk16 = AltCorrBlock(fm.half())
+    f5, f6 = blk16(c5, ii, jj), blk16(c6, ii, jj)
+    assert f5.shape == (1, 3, 196, 16, 24) and f6.shape == (1, 3, 196, 16, 24, 2)
+    scale = float(np.abs(g["out5"]).max())
+    assert np.abs(f5[:, :, ::7].cpu().numpy() - g["out5"]).max() < 4e-3 * scale      # fp16 inputs (2^-11 each)
+    assert np.abs(f6[:, :, ::7].cpu().numpy() - g["out6"]).max() < 4e-3 * scale
 
 
 # ------------------------------------------------------------------------------ geometry

@@ -115,6 +115,35 @@ def test_lietorch_shim_group_axioms_and_oracle_agreement():
     assert np.allclose(SE3.exp(torch.zeros(2, 6)).data.numpy(), [[0, 0, 0, 0, 0, 0, 1]] * 2)
 
 
+def test_lietorch_shim_log_is_the_inverse_of_exp():
+    """PoseTrajectoryFiller calls dP.log() (src/trajectory_filler.py:53); exp(log(T)) == T and
+    log(exp(xi)) == xi for rotations below pi, through the small-angle branches and for qw < 0."""
+    from goslam_b200.lietorch import SE3
+    g = torch.Generator().manual_seed(0)
+    xi = torch.randn(4000, 6, generator=g, dtype=torch.float64) * torch.tensor([1, 1, 1, .8, .8, .8], dtype=torch.float64)
+    xi[:10, 3:] *= 1e-6
+    xi[10:20, 3:] *= 1e-3
+    xi[20:25, 3:] *= 0.99e-4 / xi[20:25, 3:].norm(dim=-1, keepdim=True)     # either side of the switch-over (exp
+    xi[25:30, 3:] *= 1.01e-4 / xi[25:30, 3:].norm(dim=-1, keepdim=True)     # itself jumps by ~theta/2 * |tau| there)
+    xi[30, 3:] = 0.0
+    xi = xi[xi[:, 3:].norm(dim=-1) < 3.0]
+    T = SE3.exp(xi)
+    assert (T.log() - xi).abs().max() < 1e-9
+    assert (SE3.exp(T.log()).data - T.data).abs().max() < 1e-9
+    neg = SE3(torch.cat([T.data[:, :3], -T.data[:, 3:]], dim=-1))           # same rotation, qw < 0
+    assert (neg.log() - xi).abs().max() < 1e-9
+    # float32: (1 - cos t) / t^2 of the reference's expSE3 cancels completely for t ~ 1e-4 .. 3e-4 (cos t rounds
+    # to 1), so exp itself is off by ~t/2 * |tau| there; away from that band the round trip is float-accurate
+    xf = xi.float()
+    err = (SE3.exp(xf).log() - xf).abs().max(dim=-1)[0]
+    band = (xf[:, 3:].norm(dim=-1) > 0.9e-4) & (xf[:, 3:].norm(dim=-1) < 2e-2)
+    assert err[~band].max() < 2e-5 and err.max() < 5e-4
+    # the interpolation PoseTrajectoryFiller does with it
+    P0, P1 = SE3.exp(0.4 * xi[100:150]), SE3.exp(0.4 * xi[150:200])      # relative rotation stays below pi
+    v = (P1 * P0.inv()).log()
+    assert ((SE3.exp(v) * P0).data - P1.data).abs().max() < 1e-9
+
+
 def test_lietorch_shim_indexing_like_the_reference_call_sites():
     from goslam_b200.lietorch import SE3, cat
     G = SE3(_rand_se3(6, 2)[None])                 # [1, 6, 7] like DepthVideo.reproject

@@ -236,22 +236,3 @@ def test_altcorr_block_pyramid_matches_reference_constructor():
     assert len(blk.pyramid) == 4
     for i, lvl in enumerate(blk.pyramid):
         assert torch.equal(lvl, torch.from_numpy(g["level%d" % i]))
-
-
-def test_altcorr_block_host_plumbing_matches_reference_class(monkeypatch):
-    """AltCorrBlock's reference-shaped path (gather per edge, coords / 2^l, channel order) against outputs
-    of the reference class, with the oracle standing in for the CUDA op on both sides."""
-    import goslam_b200.modules.corr as ours
-    from oracle import corr_oracle
-    g = _load("altcorr_block.npz")
-
-    def alt_fwd(f1, f2, coords, r):
-        return [torch.from_numpy(corr_oracle.altcorr_forward(f1.numpy(), f2.numpy(), coords.numpy(), r))]
-    monkeypatch.setattr(ours, "altcorr_forward", alt_fwd)
-    blk = ours.AltCorrBlock(torch.from_numpy(g["fmaps"]))
-    ii, jj = torch.from_numpy(g["ii"]), torch.from_numpy(g["jj"])
-    out5 = blk(torch.from_numpy(g["coords"]), ii, jj)
-    out6 = blk(torch.from_numpy(g["coords6"]), ii, jj)
-    assert out5.shape == (1, 3, 196, 16, 24) and out6.shape == (1, 3, 196, 16, 24, 2)
-    np.testing.assert_array_equal(out5[:, :, ::7].numpy(), g["out5"])
-    np.testing.assert_array_equal(out6[:, :, ::7].numpy(), g["out6"])
