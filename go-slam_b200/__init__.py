@@ -28,6 +28,16 @@ def install(force=True):
     return _db, _lt
 
 
+def __getattr__(name):
+    """goslam_b200.FactorGraph / DepthVideo / CorrBlock / AltCorrBlock / InstantNeuS, imported on first use"""
+    import importlib
+    where = {"FactorGraph": ".factor_graph", "DepthVideo": ".depth_video", "CorrBlock": ".modules.corr",
+             "AltCorrBlock": ".modules.corr", "InstantNeuS": ".neus"}
+    if name in where:
+        return getattr(importlib.import_module(where[name], __name__), name)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))
+
+
 def build_library(verbose=False, force=False):
     """compile csrc/*.cu for sm_100a into go-slam_b200/libgoslam_b200.so"""
     import importlib

@@ -22,6 +22,8 @@ _IDENTITY = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0)
 
 
 class DepthVideo:
+    takes_frame_eta = True            # ba(..., eta_by_frame=True) is understood (FactorGraph checks this)
+
     # (attribute, trailing shape builder, dtype, initial value) — src/depth_video.py:39-72
     @staticmethod
     def _state_table(ht, wd, c):

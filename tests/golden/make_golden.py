@@ -17,6 +17,7 @@ What each fixture pins:
     proximity.npz     FactorGraph.add_proximity_factors edges     src/factor_graph.py:384-450
     altcorr_pyramid.npz AltCorrBlock.__init__ pyramid            src/modules/corr.py:97-111
     backend_edges.npz Backend.ba edge selection (loop=False)      src/backend.py:25-99
+    factor_graph.npz  FactorGraph + DepthVideo state machine      src/factor_graph.py:85-450, src/depth_video.py:194-269
 Run:  python tests/golden/make_golden.py      (writes next to this file)
 """
 import importlib
@@ -367,6 +368,67 @@ def gen_altcorr_pyramid():
     for i, lvl in enumerate(blk.pyramid):
         out["level%d" % i] = lvl.numpy()
     np.savez_compressed(os.path.join(HERE, "altcorr_pyramid.npz"), **out)
+
+
+def gen_factor_graph():
+    """The REFERENCE FactorGraph + DepthVideo (src/factor_graph.py, src/depth_video.py) driven through
+    tests/tools/fg_scenario.py on the CPU.  Natives are the oracle: droid_backends.{ba, frame_distance,
+    corr_index_forward, altcorr_forward}; lietorch = the host SE3 shim; update_op = tests/tools/stub_update_op."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
+    import fg_scenario
+    from oracle import ba_oracle, geom_oracle
+    db = sys.modules["droid_backends"]
+
+    def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iters, lm, ep, motion_only):
+        rp, rd, dx, dz, st = ba_oracle.ba(poses.numpy(), disps.numpy(), intrinsics.numpy(), disps_sens.numpy(),
+                                          targets.numpy(), weights.numpy(), eta.numpy(), ii.numpy(), jj.numpy(),
+                                          int(t0), int(t1), int(iters), lm, ep, bool(motion_only))
+        assert list(st) == [0] * int(iters)
+        poses.copy_(torch.from_numpy(rp))
+        disps.copy_(torch.from_numpy(rd))
+        return [torch.from_numpy(dx), torch.from_numpy(dz)]
+
+    def frame_distance(poses, disps, intrinsics, ii, jj, beta):
+        return torch.from_numpy(geom_oracle.frame_distance(poses.numpy(), disps.numpy(), intrinsics.numpy(),
+                                                           ii.numpy(), jj.numpy(), beta))
+
+    def altcorr_forward(f1, f2, coords, r):
+        return [torch.from_numpy(corr_oracle.altcorr_forward(f1.numpy(), f2.numpy(), coords.numpy(), r))]
+    db.ba, db.frame_distance, db.altcorr_forward = ba, frame_distance, altcorr_forward
+    dv_mod = ref_import("src.depth_video")
+    fg_mod = ref_import("src.factor_graph")
+
+    # DepthVideo.format_indices defaults to device='cuda' (src/depth_video.py:184) and distance() relies on it
+    orig_fmt = dv_mod.DepthVideo.format_indices
+    dv_mod.DepthVideo.format_indices = staticmethod(lambda ii, jj, device="cpu": orig_fmt(ii, jj, "cpu"))
+    CpuVideo = dv_mod.DepthVideo
+
+    # the reference's age eviction uses an UNSTABLE argsort (src/factor_graph.py:103); record whether it and the
+    # stable order we use ever disagree in this scenario
+    disagreements = []
+    orig_argsort = torch.argsort
+
+    def spy_argsort(x, *a, **k):
+        got = orig_argsort(x, *a, **k)
+        if x.dim() == 1 and not k.get("stable", False):
+            disagreements.append(not torch.equal(got, orig_argsort(x, *a, stable=True, **k)))
+        return got
+    torch.argsort = spy_argsort
+    try:
+        cfg, args = fg_scenario.cfg_and_args("cpu")
+        video = CpuVideo(cfg, args)
+        fg_scenario.fill_video(video, fg_scenario.make_inputs())
+        with torch.no_grad():
+            out = fg_scenario.run(fg_mod.FactorGraph, video, "cpu")
+    finally:
+        torch.argsort = orig_argsort
+    print("argsort calls (True = differs from the stable order):", disagreements,
+          [int(out["s%02d_ii" % k].size) for k in range(int(out["n_steps"]))])
+    assert disagreements and not any(disagreements), "age eviction hit an argsort tie that the stable order resolves differently"
+    out["evictions"] = np.int64(len(disagreements))
+    np.savez_compressed(os.path.join(HERE, "factor_graph.npz"), **out)
+    print("factor_graph: %d snapshots, %d age evictions, final edges %s" % (int(out["n_steps"]), len(disagreements),
+                                                                            [int(out["s%02d_ii" % k].size) for k in range(int(out["n_steps"]))]))
 
 
 if __name__ == "__main__":
