@@ -130,7 +130,7 @@ class Window:
         self.disps0 = self.d["disps"].clone()
         # the factor graph's correlation slot pool, allocated once (FactorGraph.max_factors slots)
         from goslam_b200.modules.corr import CorrPool
-        self.pool = CorrPool(int(sc["ii"].numel()), HT, WD, device=dev, layout=os.environ.get("GOSLAM_BENCH_LAYOUT", "tiled"))
+        self.pool = CorrPool(int(sc["ii"].numel()), HT, WD, device=dev, layout="tiled")
         self.corr = None
 
     def build(self, km):
@@ -323,7 +323,7 @@ def workload_config(world):
             "keyframes": NUM_KF, "grid": [HT, WD], "edges": 36, "ba_iters": BA_ITERS,
             "windows_per_gpu": 1, "parallelism": "window-per-gpu x%d (no collective)" % world,
             "l2": "each step writes a 0.98 GB correlation pyramid (> 126 MB L2) before it is read back, no explicit flush needed",
-            "corr_layout": os.environ.get("GOSLAM_BENCH_LAYOUT", "tiled") + " slot pool (CorrPool)",
+            "corr_layout": "tiled slot pool (CorrPool)",
             "render": {"rays": RAYS, "samples_per_ray": SAMPLES}}
 
 

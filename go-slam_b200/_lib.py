@@ -82,8 +82,7 @@ SIGNATURES = {
 
 
 def lib_path():
-    # GOSLAM_B200_LIB: load another build of the same library (kernel A/B experiments)
-    return os.environ.get("GOSLAM_B200_LIB") or _build.LIB
+    return _build.LIB
 
 
 def load(build_if_missing=True):

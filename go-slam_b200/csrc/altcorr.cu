@@ -377,7 +377,11 @@ int goslam_altcorr_pyramid(const void* const* pyramid, int num_levels, const flo
     cudaFuncSetAttribute(altcorr_pyramid_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  static const bool force_simt = [] { const char* e = getenv("GOSLAM_ALTCORR_SIMT"); return e && e[0] == '1'; }();
+#ifdef GOSLAM_ALTCORR_FORCE_SIMT     // build-time A/B switch (tools/time_altcorr.py), never in the shipped library
+  constexpr bool force_simt = true;
+#else
+  constexpr bool force_simt = false;
+#endif
   if (C == 128 && !force_simt) {                   // tensor-core path (the model's feature width)
     dim3 grid(gs_cdiv(H * W, kTcPix), N, num_levels);
     altcorr_tc_kernel<3><<<grid, kTcWarps * 32, 0, (cudaStream_t)stream>>>(a);

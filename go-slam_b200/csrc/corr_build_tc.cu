@@ -26,6 +26,7 @@
 // The 1/4 feature scaling of the reference (`fmap / 4.0` in half) is applied by the K-major
 // re-layout prepass, exactly as the reference does it, so the accumulator needs no scaling.
 #include "common.cuh"
+#include <mutex>
 #include <cstdio>
 #include <cuda.h>
 #include <cstdlib>
@@ -705,6 +706,68 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+#ifndef GOSLAM_TC_EXPERIMENT
+#define GOSLAM_TC_EXPERIMENT 0
+#endif
+#ifndef GOSLAM_TC_BULK
+#define GOSLAM_TC_BULK 0
+#endif
+#ifndef GOSLAM_TC_PINGPONG
+#define GOSLAM_TC_PINGPONG 0
+#endif
+
+// Tensor maps depend only on (base pointer, frame count, h, w): a factor graph builds from the same
+// video-level K-major buffer for its whole life, so the two cuTensorMapEncodeTiled driver calls per launch
+// (~2 us of host time each) are paid once.  Small most-recently-used table, shared by all threads.
+struct MapKey { const void* base; int F, h, w, kind; };
+struct MapSlot { MapKey key; CUtensorMap map; unsigned long long stamp; bool used; };
+constexpr int kMapSlots = 16;
+
+bool encode_map(EncodeTiledFn enc, const MapKey& k, CUtensorMap* out) {
+  const cuuint64_t hw = (cuuint64_t)k.h * k.w;
+  if (k.kind == 0) {           // A: [F, hw, 128] as (ch, pixel, frame), box 64 ch x 128 pixels
+    cuuint64_t dims[3] = {(cuuint64_t)kD, hw, (cuuint64_t)k.F};
+    cuuint64_t strides[2] = {(cuuint64_t)kD * 2, hw * kD * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kKBox, (cuuint32_t)kBM, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(k.base), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  // B: (ch, x, y, frame), box 64 ch x 16 x 8: an image patch; rows / columns outside the image read as zero
+  cuuint64_t dims[4] = {(cuuint64_t)kD, (cuuint64_t)k.w, (cuuint64_t)k.h, (cuuint64_t)k.F};
+  cuuint64_t strides[3] = {(cuuint64_t)kD * 2, (cuuint64_t)k.w * kD * 2, hw * kD * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kKBox, (cuuint32_t)kPX, (cuuint32_t)kPY, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(k.base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool cached_map(EncodeTiledFn enc, const MapKey& k, CUtensorMap* out) {
+  static MapSlot table[kMapSlots];
+  static unsigned long long clock = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int victim = -1;
+  for (int i = 0; i < kMapSlots; ++i) {
+    MapSlot& s = table[i];
+    if (s.used && s.key.base == k.base && s.key.F == k.F && s.key.h == k.h && s.key.w == k.w &&
+        s.key.kind == k.kind) {
+      s.stamp = ++clock;
+      *out = s.map;
+      return true;
+    }
+    // victim: a free slot if there is one, else the least recently used
+    if (victim < 0 || (table[victim].used && (!s.used || s.stamp < table[victim].stamp))) victim = i;
+  }
+  MapSlot& v = table[victim];
+  if (!encode_map(enc, k, &v.map)) { v.used = false; return false; }
+  v.key = k; v.used = true; v.stamp = ++clock;
+  *out = v.map;
+  return true;
+}
+
 // launch the tensor-core kernel on K-major (pre-scaled) operands: f1t/f2t = [F1|F2, hw, 128]
 int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_t* ii,
               const int64_t* jj, int rig, const int* out_slot, int tiled, __half* const* levels,
@@ -713,26 +776,8 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return GOSLAM_ELAUNCH;
   CUtensorMap mapA, mapB;
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)hw, (cuuint64_t)F1};
-    cuuint64_t strides[2] = {(cuuint64_t)kD * 2, (cuuint64_t)hw * kD * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kKBox, (cuuint32_t)kBM, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    if (enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(f1t), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return GOSLAM_ELAUNCH;
-  }
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)kD, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)F2};
-    cuuint64_t strides[3] = {(cuuint64_t)kD * 2, (cuuint64_t)w * kD * 2, (cuuint64_t)hw * kD * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kKBox, (cuuint32_t)kPX, (cuuint32_t)kPY, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    if (enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(f2t), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return GOSLAM_ELAUNCH;
-  }
+  if (!cached_map(enc, MapKey{f1t, F1, h, w, 0}, &mapA) || !cached_map(enc, MapKey{f2t, F2, h, w, 1}, &mapB))
+    return GOSLAM_ELAUNCH;
   TcParams p{};
   for (int i = 0; i < 4; ++i) p.lvl[i] = i < num_levels ? levels[i] : nullptr;
   p.num_levels = num_levels; p.N = N; p.h = h; p.w = w; p.hw = hw;
@@ -744,23 +789,30 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
   p.w4_1 = gs_cdiv(w >> 1, 4); p.h4_1 = gs_cdiv(h >> 1, 4);
   p.pitch2 = (p.n_xb * 16 + 31) / 32 * 32; p.pitch3 = 32;
   p.aligned = (w % 16 == 0 && h % 8 == 0) ? 1 : 0;
-  { const char* e = getenv("GOSLAM_TC_EXPERIMENT"); p.experiment = e ? atoi(e) : 0; }
-  // experiment switch: measured 278 us with bulk stores vs 273 us with plain stores on config 2 — the
+  // Build-time A/B switches (-DGOSLAM_TC_EXPERIMENT=1 ..., tools/ only): the shipped library has them all 0.
+  p.experiment = GOSLAM_TC_EXPERIMENT;
+  // measured 278 us with bulk stores vs 273 us with plain stores on config 2 — the
   // limit is past the SM (L2 / fabric), so the TMA path is off by default
-  { const char* e = getenv("GOSLAM_TC_BULK"); p.bulk = (p.tiled && e && atoi(e) == 1) ? 1 : 0; }
-  { const char* e = getenv("GOSLAM_TC_PINGPONG"); p.pingpong = (p.tiled && e && atoi(e) == 1) ? 1 : 0; }
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(corr_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kSmemTC) != cudaSuccess)
-      return GOSLAM_ELAUNCH;
-    attr = true;
-  }
-  int sms = 148;
+  p.bulk = (p.tiled && GOSLAM_TC_BULK) ? 1 : 0;
+  p.pingpong = (p.tiled && GOSLAM_TC_PINGPONG) ? 1 : 0;
+  // per-device: opt-in shared memory + SM count, looked up once per device
+  static int sm_count[64];
+  static std::mutex dev_mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int sms;
   {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    std::lock_guard<std::mutex> lock(dev_mu);
+    if (sm_count[dev] == 0) {
+      if (cudaFuncSetAttribute(corr_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kSmemTC) != cudaSuccess)
+        return GOSLAM_ELAUNCH;
+      int n = 148;
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      sm_count[dev] = n > 0 ? n : 148;
+    }
+    sms = sm_count[dev];
   }
   const int grid = p.n_items < sms ? p.n_items : sms;
   corr_build_tc_kernel<<<grid, kThreadsTC, kSmemTC, st>>>(mapA, mapB, p);
