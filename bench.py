@@ -110,9 +110,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ workload
-def make_window(seed):
+def make_window(seed, ht=None, wd=None, num_kf=None):
     from goslam_b200 import synthetic
-    sc, g = synthetic.make_scene(num_kf=NUM_KF, ht=HT, wd=WD, seed=seed, rgbd=True)
+    ht, wd, num_kf = ht or HT, wd or WD, num_kf or NUM_KF
+    sc, g = synthetic.make_scene(num_kf=num_kf, ht=ht, wd=wd, seed=seed, rgbd=True)
     coords = synthetic.true_reprojection(sc)          # plain-torch setup helper (targets = reprojection + noise)
     targets, weights, eta = synthetic.make_update(sc, coords[0], g, noise=0.5)
     sc.update(targets=targets, weights=weights, eta=eta)
@@ -124,20 +125,21 @@ class Window:
 
     def __init__(self, sc, dev):
         self.dev = dev
+        self.num_kf, self.ht, self.wd = int(sc["num_kf"]), int(sc["ht"]), int(sc["wd"])
         self.host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in sc.items()}
         self.d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc.items()}
         self.poses0 = self.d["poses"].clone()
         self.disps0 = self.d["disps"].clone()
         # the factor graph's correlation slot pool, allocated once (FactorGraph.max_factors slots)
         from goslam_b200.modules.corr import CorrPool
-        self.pool = CorrPool(int(sc["ii"].numel()), HT, WD, device=dev, layout="tiled")
+        self.pool = CorrPool(int(sc["ii"].numel()), self.ht, self.wd, device=dev, layout="tiled")
         self.corr = None
 
     def build(self, km):
         from goslam_b200.modules import CorrBlock
         if self.corr is not None:
             self.corr.free()                    # rm_factors: the slots go back to the pool
-        self.corr = CorrBlock.from_video(km, self.d["ii"], self.d["jj"], HT, WD, pool=self.pool)
+        self.corr = CorrBlock.from_video(km, self.d["ii"], self.d["jj"], self.ht, self.wd, pool=self.pool)
         return self.corr
 
     def step(self, reset=True):
@@ -151,12 +153,12 @@ class Window:
         ii, jj = d["ii"], d["jj"]
         # FactorGraph.add_factors' volume, video-level: K-major re-layout of the window's feature
         # maps (per keyframe, redone every step here) + on-device edge -> frame indexing
-        km = fmaps_to_kmajor(d["fmaps"][:NUM_KF])
+        km = fmaps_to_kmajor(d["fmaps"][:self.num_kf])
         corr = self.build(km)
         coords, _ = droid_backends.reproject(d["poses"], d["disps"], d["intrinsics"], ii, jj, want_valid=False)
         feat = corr(coords)
         droid_backends.ba(d["poses"], d["disps"], d["intrinsics"][0], d["disps_sens"], d["targets"],
-                          d["weights"], d["eta"], ii, jj, 1, NUM_KF, BA_ITERS, 1e-4, 0.1, False)
+                          d["weights"], d["eta"], ii, jj, 1, self.num_kf, BA_ITERS, 1e-4, 0.1, False)
         d["disps"].clamp_(min=0.001)            # src/depth_video.py:269
         return feat
 
@@ -183,7 +185,7 @@ class Window:
             for k in self.E2E_KEYS:
                 hv[k].copy_(self.host[k])
             self._e2e = dict(copy=torch.cuda.Stream(self.dev), bufs=[None, None], blocks=[None, None], packed=packed,
-                             ready=[None, None], done=[None, None], parity=0)
+                             ready=[None, None], done=[None, None], parity=0, graphs=[None, None], graph_failed=False)
             for b in range(2):
                 self._e2e["blocks"][b] = torch.empty(total, dtype=torch.uint8, device=self.dev)
                 self._e2e["bufs"][b] = views(self._e2e["blocks"][b])
@@ -196,12 +198,42 @@ class Window:
         for k in self.E2E_KEYS:
             self.d[k] = st["bufs"][cur][k]
         self._prefetch(cur ^ 1)                           # next update's inputs, overlapped
-        self.step(reset=False)
+        if st["graphs"][cur] is None and not st["graph_failed"]:
+            st["graphs"][cur] = self._capture()           # the six launches of the step become one graph launch
+            if st["graphs"][cur] is None:
+                st["graph_failed"] = True
+        if st["graphs"][cur] is not None:
+            st["graphs"][cur].replay()
+        else:
+            self.step(reset=False)
         out_pinned[0].copy_(self.d["poses"], non_blocking=True)
         out_pinned[1].copy_(self.d["disps"], non_blocking=True)
         st["done"][cur] = torch.cuda.Event()
         st["done"][cur].record(main)
         st["parity"] = cur ^ 1
+
+    @property
+    def graphed(self):
+        st = getattr(self, "_e2e", None)
+        return bool(st and st["graphs"][0] is not None and st["graphs"][1] is not None)
+
+    def _capture(self):
+        """CUDA graph of one step on the CURRENT input buffers (self.d): kmajor, correlation build, reproject,
+        lookup, BA table kernel, cooperative BA kernel — launched as one graph afterwards, which takes the host
+        (Python + ctypes + driver) out of the critical path of the end-to-end loop."""
+        try:
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                self.step(reset=False)                    # warm-up off the capture: module load, workspaces, attributes
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.step(reset=False)
+            return g
+        except Exception as e:   # noqa: BLE001 — e.g. a driver that cannot capture cooperative launches
+            self.graph_error = "%s: %s" % (type(e).__name__, e)
+            return None
 
     def _prefetch(self, b):
         st = self._e2e
@@ -321,10 +353,155 @@ def workload_config(world):
     return {"workload": "configs[1]: Replica room0 RGB-D shapes, 8-keyframe window, 40x80 @1/8, 36 edges, "
                         "corr build + 4-level r=3 lookup + 3 BA iters per update",
             "keyframes": NUM_KF, "grid": [HT, WD], "edges": 36, "ba_iters": BA_ITERS,
-            "windows_per_gpu": 1, "parallelism": "window-per-gpu x%d (no collective)" % world,
+            "windows_per_gpu": 1,
+            "parallelism": "value / e2e / headline_640x480 / render: one window + one ray batch per GPU x%d, no collective "
+                           "(weak scaling); sharded_graph: ONE graph over all ranks, NCCL all-reduce + all-gather per BA "
+                           "iteration (strong scaling)" % world,
             "l2": "each step writes a 0.98 GB correlation pyramid (> 126 MB L2) before it is read back, no explicit flush needed",
             "corr_layout": "tiled slot pool (CorrPool)",
             "render": {"rays": RAYS, "samples_per_ray": SAMPLES}}
+
+
+# ------------------------------------------------------------------------------------ legs
+def build_roofline(win, pk, steps, warm, ms_step):
+    """the dominant kernel (tcgen05 correlation build) timed alone on this stream, against the measured HBM peak"""
+    from goslam_b200.modules.corr import fmaps_to_kmajor
+    d = win.d
+    km = fmaps_to_kmajor(d["fmaps"][:win.num_kf])
+    ms_build = time_gpu(lambda: win.build(km), max(steps, 10), warm, lambda: None)
+    N, hw = int(d["ii"].numel()), win.ht * win.wd
+    lvl = sum((win.ht >> i) * (win.wd >> i) for i in range(4))
+    build_bytes = N * (2 * 128 * hw * 2 + hw * lvl * 2)
+    build_flops = N * 2.0 * 128 * hw * hw
+    ach = build_bytes / (ms_build * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tp):      # dram__bytes_read+write of the `ncu --set full` capture of this kernel on this workload
+        traffic = json.load(open(tp)).get("corr_build_tc_kernel@%dx%d" % (win.ht, win.wd), {}).get("dram_bytes_per_launch")
+    return {"kernel": "corr_build_tc_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": ach / pk["hbm"], "traffic": traffic, "algorithmic_bytes": build_bytes,
+            "peak_source": pk["src"] + " (burst copy bandwidth)", "ms_per_launch": ms_build,
+            "share_of_step": ms_build / ms_step, "tensor_tflops": build_flops / (ms_build * 1e-3) / 1e12,
+            "tensor_frac_of_measured_burst": build_flops / (ms_build * 1e-3) / 1e12 / pk["tf_burst"]}
+
+
+def window_leg(sc, dev, steps, warm, barrier, world, pk, clock_index=None):
+    """device-resident + end-to-end timing of the keyframe-BA-update on one window shape"""
+    win = Window(sc, dev)
+    if clock_index is not None:
+        with ClockSampler(clock_index) as clk:
+            ms_step = time_gpu(win.step, steps, warm, barrier)
+        clocks = clk.summary()
+    else:
+        ms_step, clocks = time_gpu(win.step, steps, warm, barrier), None
+    ms_step = max_over_ranks(ms_step, world)
+    outp = (torch.empty_like(sc["poses"]).pin_memory(), torch.empty_like(sc["disps"]).pin_memory())
+    ms_e2e = max_over_ranks(time_gpu(lambda: win.step_e2e(outp), steps, warm, barrier), world)
+    graphed = win.graphed
+    roof = build_roofline(win, pk, steps, warm, ms_step)
+    rec = {"value": world * 1e3 / ms_step, "unit": "updates/s", "ms_per_step": ms_step,
+           "e2e": {"value": world * 1e3 / ms_e2e, "unit": "updates/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": win.h2d_bytes(), "d2h_bytes_per_step": win.d2h_bytes(),
+                   "cuda_graph": graphed},
+           "roofline": roof}
+    return rec, clocks
+
+
+def sharded_graph_leg(dev, steps, warm, barrier, world, rank):
+    """configs[3]: ONE 64-keyframe global-BA graph (ScanNet shapes, 30x40) sharded over the ranks by source
+    frame — per update: reproject + motion features + 4-level windowed correlation of the local edges, then 2
+    BA iterations with one all-reduce of the reduced camera system and one all-gather of the owned inverse-
+    depth rows each.  Strong scaling: the graph is the same whatever N is."""
+    import torch.distributed as dist
+    from goslam_b200 import droid_backends, graph, parallel, synthetic
+    num_kf, ht, wd, iters = 64, 30, 40, 2
+    sc, g = synthetic.make_scene(num_kf=num_kf, ht=ht, wd=wd, seed=43, rgbd=True, buffer=num_kf + 2)
+    D = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc.items()}
+    # Backend.ba's edge rule (src/backend.py:25-99, radius 1, nms 5, thresh 25, max_factors 6*64), on the device
+    ix = torch.arange(0, num_kf)
+    gi, gj = torch.meshgrid(ix, ix, indexing="ij")
+    dmat = droid_backends.frame_distance_bidirectional(D["poses"], D["disps"], D["intrinsics"][0].contiguous(),
+                                                       gi.reshape(-1).to(dev), gj.reshape(-1).to(dev), 0.3)
+    ii, jj = graph.backend_edges(dmat, 0, num_kf, 1, 5, 25.0, 384, False)
+    sc["ii"], sc["jj"] = ii.cpu(), jj.cpu()
+    sc["t0"], sc["t1"] = 1, num_kf
+    coords = synthetic.true_reprojection(sc)
+    tg, wg, eta = synthetic.make_update(sc, coords[0], g, noise=0.5)
+    kx = torch.unique(torch.cat([torch.arange(1, num_kf), sc["ii"]]))
+    eta_f = torch.zeros(num_kf + 2, ht, wd)
+    eta_f[kx] = eta
+    eta_f = eta_f.to(dev)
+    group = None
+    if world == 1 and not dist.is_initialized():
+        # single process: a one-rank gloo group keeps the code path identical (no collective is issued)
+        dist.init_process_group("gloo", store=dist.HashStore(), rank=0, world_size=1)
+        own_group = True
+    else:
+        own_group = False
+    sg = parallel.ShardedGraph(D["poses"], D["disps"], D["intrinsics"], D["disps_sens"], D["fmaps"], ii, jj, 1, num_kf,
+                               group=group)
+    tg_l, wg_l = sg.local(tg.to(dev)), sg.local(wg.to(dev))                      # planar [n,2,h,w]
+    tgt_flow = sg.local(tg.permute(0, 2, 3, 1).contiguous().to(dev))            # [n,h,w,2] for the motion features
+    p0, d0 = D["poses"].clone(), D["disps"].clone()
+
+    def update():
+        D["poses"].copy_(p0)
+        D["disps"].copy_(d0)
+        sg.features(tgt_flow)
+        sg.bundle_adjust(tg_l, wg_l, eta_f, iters, 1e-5, 1e-2)
+
+    ms = max_over_ranks(time_gpu(update, steps, warm, barrier), world)
+    # replicas must agree bit for bit after the update (every rank solved the same all-reduced system)
+    agree = True
+    if world > 1:
+        ref = D["poses"].clone()
+        dist.broadcast(ref, src=0)
+        flag = torch.tensor([float(torch.equal(ref, D["poses"]))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        agree = bool(flag.item() == 1.0)
+    if own_group:
+        dist.destroy_process_group()
+    P = num_kf - 1
+    return {"metric": "keyframe-BA-updates/s (one sharded graph)", "value": 1e3 / ms, "unit": "updates/s",
+            "ms_per_update": ms, "scaling": "strong", "n_gpus": world,
+            "workload": "configs[3]: 64-keyframe global BA graph, ScanNet 30x40 @1/8, %d edges (Backend.ba rule), "
+                        "reproject + 4-level windowed correlation + 2 BA iters (lm 1e-5, ep 1e-2), P = %d poses" % (int(ii.numel()), P),
+            "parallelism": "edges sharded by source frame over %d rank(s); per BA iteration 1 all-reduce of %d B "
+                           "(reduced camera system, f64) + 1 all-gather of the owned inverse-depth rows" % (world, 8 * (36 * P * P + 6 * P)),
+            "local_edges_rank0": int(sg.ii.numel()), "replicas_bit_identical": agree}
+
+
+def render_leg(dev, rank, world, steps, barrier, pk, n_samples, n_surface, with_device_leg=True):
+    """2^18-ray batches through the fused marcher; e2e = Renderer.render_batch_ray from pinned host rays"""
+    import types
+    from goslam_b200 import render as render_mod
+    net, rays, _ = make_renderer(dev, 43 + rank)
+    out = {}
+    if with_device_leg:
+        rd = [r.to(dev) for r in rays]
+        ms_r = max_over_ranks(time_gpu(lambda: net(*rd), max(5, steps // 2), 3, barrier), world)
+        rbytes = RAYS * (512.0 * SAMPLES + 1216.0)
+        out.update({"metric": "rendered Mrays/s", "value": world * RAYS / ms_r / 1e3, "unit": "Mrays/s", "ms_per_batch": ms_r,
+                    "roofline": {"kernel": "neus_forward_kernel", "bound": "hbm", "achieved": rbytes / (ms_r * 1e-3) / 1e9,
+                                 "peak": pk["hbm"], "unit": "GB/s", "frac": rbytes / (ms_r * 1e-3) / 1e9 / pk["hbm"],
+                                 "traffic": None,
+                                 "note": "algorithmic bytes (38,080 B/ray); the 25 MB table is L2-resident"}})
+    rcfg = {"rendering": {"lindisp": False, "perturb": 1.0, "N_samples": n_samples, "N_surface": n_surface}}
+    renderer = render_mod.Renderer(rcfg, None, types.SimpleNamespace(H=512, W=512, fx=460.8, fy=460.8, cx=256.0, cy=256.0))
+    gt_depth = 0.5 + 2.5 * torch.rand(RAYS, generator=torch.Generator().manual_seed(43 + rank))
+    hp = [rays[0].pin_memory(), rays[1].pin_memory(), gt_depth.pin_memory()]
+    keep = {"color": torch.empty(RAYS, 3).pin_memory(), "depth": torch.empty(RAYS, 1).pin_memory()}
+
+    def render_e2e():
+        ro, rdir, gd = [x.to(dev, non_blocking=True) for x in hp]
+        o = renderer.render_batch_ray(ro, rdir, net, None, device=dev, gt_depth=gd)
+        for k in ("color", "depth"):
+            keep[k].copy_(o[k].reshape(keep[k].shape), non_blocking=True)
+    ms_re = max_over_ranks(time_gpu(render_e2e, max(5, steps // 2), 3, barrier), world)
+    out["e2e"] = {"value": world * RAYS / ms_re / 1e3, "unit": "Mrays/s", "ms_per_batch": ms_re,
+                  "call": "Renderer.render_batch_ray (z-sampling %d+%d + marcher), host rays in, colour+depth out" % (n_samples, n_surface),
+                  "h2d_bytes_per_batch": RAYS * 7 * 4, "d2h_bytes_per_batch": RAYS * 4 * 4}
+    return out
 
 
 # ------------------------------------------------------------------------------------ main
@@ -336,6 +513,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="", help="comma list of legs to run besides the main one: headline,sharded,render")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -354,94 +532,53 @@ def main():
         barrier = lambda: dist.barrier()   # noqa: E731
     else:
         barrier = lambda: None             # noqa: E731
+    legs = set(x for x in args.only.split(",") if x) or {"headline", "sharded", "render"}
+    if args.no_render:
+        legs.discard("render")
 
     from goslam_b200 import _lib
     _lib.load()
     pk = peaks()
-    sc = make_window(43 + rank)
-    win = Window(sc, dev)
     warm = max(args.warmup, 3)
 
-    with ClockSampler(local) as clk:
-        ms_step = time_gpu(win.step, args.steps, warm, barrier)
-    ms_step = max_over_ranks(ms_step, world)
-    clocks = clk.summary()
-
-    # ---- end to end through the public API from pinned host buffers
-    outp = (torch.empty_like(sc["poses"]).pin_memory(), torch.empty_like(sc["disps"]).pin_memory())
-    ms_e2e = max_over_ranks(time_gpu(lambda: win.step_e2e(outp), args.steps, warm, barrier), world)
-
-    # ---- dominant kernel: correlation build (tcgen05) timed alone on this stream
-    from goslam_b200.modules import CorrBlock
-    d = win.d
-    from goslam_b200.modules.corr import fmaps_to_kmajor
-    km = fmaps_to_kmajor(d["fmaps"][:NUM_KF])
-    ms_build = time_gpu(lambda: win.build(km), max(args.steps, 10), warm, lambda: None)
-    N, hw = 36, HT * WD
-    lvl = sum((HT >> i) * (WD >> i) for i in range(4))
-    build_bytes = N * (2 * 128 * hw * 2 + hw * lvl * 2)
-    build_flops = N * 2.0 * 128 * hw * hw
-    ach = build_bytes / (ms_build * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp):      # dram__bytes_read+write of one `ncu --set full` capture of this kernel/workload
-        traffic = json.load(open(tp)).get("corr_build_tc_kernel", {}).get("dram_bytes_per_launch")
-    roof = {"kernel": "corr_build_tc_kernel", "bound": "hbm", "achieved": ach,
-            "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic,
-            "algorithmic_bytes": build_bytes,
-            "peak_source": pk["src"] + " (burst copy bandwidth)", "ms_per_launch": ms_build,
-            "share_of_step": ms_build / ms_step,
-            "tensor_tflops": build_flops / (ms_build * 1e-3) / 1e12,
-            "tensor_frac_of_measured_burst": build_flops / (ms_build * 1e-3) / 1e12 / pk["tf_burst"]}
-
-    line = {"metric": METRIC, "value": world * 1e3 / ms_step, "unit": "updates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
+    # ---- configs[1]: the metric's own configuration (value / e2e / roofline of the line)
+    sc = make_window(43 + rank)
+    main_rec, clocks = window_leg(sc, dev, args.steps, warm, barrier, world, pk, clock_index=local)
+    line = {"metric": METRIC, "value": main_rec["value"], "unit": "updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": main_rec["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 corr (f32 accumulate) / f32 BA (f64 solve)",
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
-            "e2e": {"value": world * 1e3 / ms_e2e, "unit": "updates/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": win.h2d_bytes(), "d2h_bytes_per_step": win.d2h_bytes()},
+            "e2e": main_rec["e2e"],
             "gpu_launches": 6 * args.steps,   # kmajor, corr build, reproject, lookup, ba_prep, ba (all iterations in one cooperative kernel)
-            "roofline": roof}
+            "roofline": main_rec["roofline"]}
 
-    if not args.no_render:
-        net, rays, _ = make_renderer(dev, 43 + rank)
-        rd = [r.to(dev) for r in rays]
-        ms_r = max_over_ranks(time_gpu(lambda: net(*rd), max(5, args.steps // 2), 3, barrier), world)
-        # end to end = the reference's public call, Renderer.render_batch_ray(rays_o, rays_d, net,
-        # gt_depth): rays and sensor depth come from pinned host memory, z-sampling (one launch)
-        # and the marcher run on the device, colour + depth go back to the host.
-        from goslam_b200 import render as render_mod
-        import types
-        rcfg = {"rendering": {"lindisp": False, "perturb": 1.0, "N_samples": 24, "N_surface": SAMPLES - 24}}
-        renderer = render_mod.Renderer(rcfg, None, types.SimpleNamespace(H=512, W=512, fx=460.8, fy=460.8, cx=256.0, cy=256.0))
-        gt_depth = 0.5 + 2.5 * torch.rand(RAYS, generator=torch.Generator().manual_seed(43 + rank))
-        hp = [rays[0].pin_memory(), rays[1].pin_memory(), gt_depth.pin_memory()]
-        keep = {"color": torch.empty(RAYS, 3).pin_memory(), "depth": torch.empty(RAYS, 1).pin_memory()}
+    # ---- north_star headline shape: 640x480 input -> 60x80 @1/8, same 8-keyframe / 36-edge window
+    if "headline" in legs:
+        sc60 = make_window(143 + rank, ht=60, wd=80)
+        rec60, _ = window_leg(sc60, dev, max(10, args.steps // 2), warm, barrier, world, pk)
+        rec60["workload"] = ("synthetic 640x480 RGB-D -> 60x80 @1/8, 8-keyframe window, 36 edges, corr build + 4-level "
+                             "r=3 lookup + 3 BA iters per update; one window per GPU (weak scaling)")
+        line["headline_640x480"] = rec60
 
-        def render_e2e():
-            ro, rdir, gd = [x.to(dev, non_blocking=True) for x in hp]
-            out = renderer.render_batch_ray(ro, rdir, net, None, device=dev, gt_depth=gd)
-            for k in ("color", "depth"):
-                keep[k].copy_(out[k].reshape(keep[k].shape), non_blocking=True)
-        ms_re = max_over_ranks(time_gpu(render_e2e, max(5, args.steps // 2), 3, barrier), world)
-        rbytes = RAYS * (512.0 * SAMPLES + 1216.0)
-        line["render"] = {"metric": "rendered Mrays/s", "value": world * RAYS / ms_r / 1e3, "unit": "Mrays/s",
-                          "ms_per_batch": ms_r,
-                          "e2e": {"value": world * RAYS / ms_re / 1e3, "unit": "Mrays/s", "ms_per_batch": ms_re,
-                                  "call": "Renderer.render_batch_ray (z-sampling + marcher), host rays in, colour+depth out",
-                                  "h2d_bytes_per_batch": RAYS * 7 * 4, "d2h_bytes_per_batch": RAYS * 4 * 4},
-                          "roofline": {"kernel": "neus_forward_kernel", "bound": "hbm",
-                                       "achieved": rbytes / (ms_r * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                                       "frac": rbytes / (ms_r * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
-                                       "note": "algorithmic bytes (38,080 B/ray); the 25 MB table is L2-resident"}}
+    # ---- configs[3]: one global-BA graph sharded over the ranks (strong scaling, NCCL exchange per BA iteration)
+    if "sharded" in legs:
+        line["sharded_graph"] = sharded_graph_leg(dev, max(10, args.steps // 2), warm, barrier, world, rank)
+
+    if "render" in legs:
+        line["render"] = render_leg(dev, rank, world, args.steps, barrier, pk, 24, SAMPLES - 24)
+        # configs[2] (Replica mono): 48 stratified + 24 surface samples (configs/Replica/replica_mono.yaml:54-55);
+        # the marcher's work is the same 72 samples per ray, only the z-sampling split differs
+        line["render"]["mono_48_24"] = render_leg(dev, rank, world, args.steps, barrier, pk, 48, SAMPLES - 48,
+                                                  with_device_leg=False)["e2e"]
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        # the whole step (36 edges, 3 iterations, nothing extrapolated) when the host does it in <= 20 s,
+        # the whole step (36 edges, 3 iterations, nothing extrapolated) when the host does it in <= 40 s,
         # else a proportional sample
-        n_e, n_it = cpu_sample_plan(sc, 20.0)
+        n_e, n_it = cpu_sample_plan(sc, 40.0)
         full, spent = cpu_reference_step(sc, n_e, n_it)
         line["cpu_baseline"] = {"value": 1.0 / full, "unit": "updates/s", "cores": os.cpu_count(), "kind": "port",
+                                "extrapolated": n_e != 36,
                                 "sample": "corr build+pyramid+lookup on %d/36 edges + %d/3 BA iterations "
                                           "(%.1f s of CPU work)%s" % (n_e, n_it, spent, "" if n_e == 36 else
                                                                       ", extrapolated linearly to the full step")}

@@ -158,6 +158,60 @@ def sharded_ba(backend, disps, targets, weights, eta_by_frame, ii, jj, iteration
     return dx
 
 
+class ShardedGraph:
+    """ONE factor graph (global BA, config 4) sharded over the ranks of a process group — the multi-GPU form
+    of FactorGraph.update_lowmem's per-step work without the update operator:
+
+        reproject + motion features of the LOCAL edges        (no exchange)
+        windowed 4-level correlation of the LOCAL edges        (no exchange; feature pyramid replicated)
+        dense BA: local linearisation + local reduced system -> all-reduce [(6P)^2 + 6P] f64 -> redundant
+        solve + pose retraction -> depth back-substitution of the OWNED frames -> all-gather of those rows
+
+    Edges are assigned by source frame (`shard_frames_by_edges`), state (poses, disps, intrinsics, sensor
+    depth, feature maps) is replicated; every rank ends each update with identical poses and disps."""
+
+    def __init__(self, poses, disps, intrinsics_all, disps_sens, fmaps, ii, jj, t0, t1, group=None):
+        from .modules.corr import AltCorrBlock
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.poses, self.disps, self.intr_all = poses, disps, intrinsics_all
+        num = disps.shape[0]
+        self.bounds = shard_frames_by_edges(ii, num, self.world)
+        self.lo, self.hi = self.bounds[self.rank]
+        self.sel = local_edges(ii, self.lo, self.hi)
+        self.ii, self.jj = ii[self.sel].contiguous(), jj[self.sel].contiguous()
+        self.backend = CudaBackend(poses, disps, intrinsics_all[0].contiguous(), disps_sens, t0, t1)
+        f, rig, ch, ht, wd = fmaps.shape
+        self.rig = rig
+        self.corr_op = AltCorrBlock(fmaps.view(1, f * rig, ch, ht, wd))
+        self.f1 = (rig * self.ii).contiguous()
+        self.f2 = (rig * self.jj + (self.ii == self.jj).long()).contiguous()
+        self.exchange = RowExchange(disps, self.bounds, self.rank) if self.world > 1 else None
+
+    def local(self, per_edge):
+        """this rank's slice of a replicated per-edge tensor [N, ...]"""
+        return per_edge[self.sel].contiguous()
+
+    def features(self, target_local):
+        """coords1, motion features and correlation features of the local edges (what the update operator eats)"""
+        from . import droid_backends
+        coords, motion = droid_backends.reproject_motion(self.poses, self.disps, self.intr_all, self.ii, self.jj,
+                                                         target_local)
+        return coords, motion, self.corr_op(coords, self.f1, self.f2)
+
+    def bundle_adjust(self, target_planar_local, weight_planar_local, eta_by_frame, iters, lm, ep, motion_only=False):
+        dx = None
+        for _ in range(iters):
+            system = self.backend.phase1(target_planar_local, weight_planar_local, eta_by_frame, self.ii, self.jj,
+                                         motion_only)
+            if self.world > 1:
+                dist.all_reduce(system, op=dist.ReduceOp.SUM, group=self.group)
+            dx = self.backend.phase2(system, lm, ep, motion_only, self.lo, self.hi)
+            if self.exchange is not None and not motion_only:
+                self.exchange(self.disps, self.group)
+        return dx
+
+
 def sharded_pairs(fn, ii, jj, group=None):
     """Embarrassingly parallel per-pair work (DepthVideo.distance over K frame pairs):
     the pair list is split evenly and contiguously over the ranks, each rank evaluates `fn(ii_part,
