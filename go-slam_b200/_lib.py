@@ -29,7 +29,7 @@ class NeusOut(ctypes.Structure):
     _fields_ = [
         ("color", c_void_p), ("depth", c_void_p), ("depth_variance", c_void_p),
         ("normal", c_void_p), ("weight_sum", c_void_p), ("sdf", c_void_p), ("z_mid", c_void_p),
-        ("gradient_error", c_void_p),
+        ("gradient_error", c_void_p), ("alpha", c_void_p), ("grad", c_void_p), ("pos", c_void_p),
     ]
 
 

@@ -467,6 +467,15 @@ neus_forward_kernel(const NeusArgs a) {
         alpha = inb ? alpha : 0.f;
         a.o.sdf[gidx] = sdf;
         a.o.z_mid[gidx] = zm;
+        if (a.o.alpha) a.o.alpha[gidx] = alpha;
+        if (a.o.grad) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) a.o.grad[gidx * 3 + c] = g3[c];
+        }
+        if (a.o.pos) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) a.o.pos[gidx * 3 + c] = xn[c];
+        }
         if (inb) {
           const float gn = sqrtf(g3[0] * g3[0] + g3[1] * g3[1] + g3[2] * g3[2]) - 1.0f;
           gerr_local += gn * gn;

@@ -189,7 +189,9 @@ class InstantNeuS(nn.Module):
 
     # ---- forward ------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, rays_o, rays_d, z_vals, dists, render_params: dict = None):
+    def forward(self, rays_o, rays_d, z_vals, dists, render_params: dict = None, debug=False):
+        """debug=True (tests only): additionally keeps the per-sample NeuS alpha [R,S] and SDF normal [R,S,3]
+        in `self.last_debug`."""
         if not z_vals.is_cuda:
             raise RuntimeError("InstantNeuS.forward: CUDA tensors required (no CPU fallback)")
         dev = z_vals.device
@@ -211,6 +213,13 @@ class InstantNeuS(nn.Module):
         o.depth_variance = out['depth_variance'].data_ptr(); o.normal = out['normal'].data_ptr()
         o.weight_sum = out['weight_sum'].data_ptr(); o.sdf = out['sdf'].data_ptr()
         o.z_mid = out['z_vals'].data_ptr(); o.gradient_error = out['gradient_error'].data_ptr()
+        self.last_debug = None
+        if debug:
+            self.last_debug = {'alpha': torch.empty((R, S), **f32), 'grad': torch.empty((R, S, 3), **f32)}
+            o.alpha = self.last_debug['alpha'].data_ptr()
+            o.grad = self.last_debug['grad'].data_ptr()
+            self.last_debug['pos'] = torch.empty((R, S, 3), **f32)
+            o.pos = self.last_debug['pos'].data_ptr()
         lib = _lib.load()
         with torch.cuda.device(dev):
             ws = _workspace(lib.goslam_neus_workspace_bytes(R, S), dev)

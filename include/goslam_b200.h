@@ -242,6 +242,11 @@ typedef struct goslam_neus_out {
   float* sdf;            /* [R,S]  */
   float* z_mid;          /* [R,S]  (z_vals + dists/2)                    */
   float* gradient_error; /* [1]    */
+  /* optional per-sample intermediates (NULL in production; the parity tests read them to check the
+   * composited outputs sample by sample): */
+  float* alpha;          /* [R,S]   NeuS alpha of every sample (0 outside the bound)  */
+  float* grad;           /* [R,S,3] SDF normal of every sample (0 outside the bound)  */
+  float* pos;            /* [R,S,3] normalised sample position in [-1,1] (0 outside the bound) */
 } goslam_neus_out;
 
 size_t goslam_neus_workspace_bytes(int R, int S);

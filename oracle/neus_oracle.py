@@ -33,10 +33,14 @@ PER_LEVEL_SCALE = 1.447269237440378
 
 
 def hashgrid_meta():
-    log2b = np.log2(F32(PER_LEVEL_SCALE)).astype(F32)
+    # scale_l = exp2f(l * log2f(per_level_scale)) * base - 1 in float, with CORRECTLY ROUNDED log2f / exp2f
+    # (double evaluation, one rounding to float) — what glibc's exp2f / log2f give in the library's host code.
+    # numpy's float32 exp2 is 1 ulp off at levels 3, 6, 8 and 11, which moved samples that sit within an ulp
+    # of a cell face of those levels into the neighbouring cell (a different, piecewise-constant, normal).
+    log2b = F32(math.log2(float(F32(PER_LEVEL_SCALE))))
     metas, off = [], 0
     for l in range(N_LEVELS):
-        scale = F32(np.exp2(F32(l) * log2b).astype(F32) * F32(BASE_RES) - F32(1.0))
+        scale = F32(F32(2.0 ** float(F32(F32(l) * log2b))) * F32(BASE_RES) - F32(1.0))
         res = int(math.ceil(float(scale))) + 1
         p = min(res ** 3, 0xFFFFFFFF // 2)
         p = (p + 7) // 8 * 8
@@ -142,7 +146,7 @@ def _sigmoid(x):
 
 
 def forward(grid, sdf_w, sdf_b, color_B, mlp_w, bound, rt_bound, variance, scale_factor,
-            rays_o, rays_d, z_vals, dists, cos_anneal_ratio=1.0):
+            rays_o, rays_d, z_vals, dists, cos_anneal_ratio=1.0, debug=False):
     """Standalone restatement of InstantNeuS.forward.  grid: float16 [total_params];
     bound / rt_bound: [3,2].  Returns the reference's 9-key dict (numpy)."""
     table = np.asarray(grid, F16).reshape(-1, N_FEAT)
@@ -209,4 +213,5 @@ def forward(grid, sdf_w, sdf_b, color_B, mlp_w, bound, rt_bound, variance, scale
         "sdf": sdf.reshape(R, S),
         "z_vals": zm,
         "gradient_error": np.array([gerr], F32),
+        **({"_alpha": alpha, "_grad": grad, "_weights": w, "_xn": xn, "_mask": mask} if debug else {}),
     }

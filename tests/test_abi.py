@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -88,7 +90,9 @@ def test_hashgrid_layout_matches_oracle(lib):
     assert ress == [m["res"] for m in metas] == [16, 24, 34, 49, 71, 102, 148, 213, 308, 446, 646, 934, 1352, 1956, 2831, 4096]
     assert offs[:-1] == [2 * m["offset"] for m in metas]
     for s, m in zip(scales, metas):
-        assert abs(s - float(m["scale"])) <= 1e-6 * s
+        # BIT-exact: a 1-ulp difference in a level's scale moves samples on that level's cell faces into the
+        # neighbouring cell, i.e. changes their normal (found with tests/tools/diag_render_parity.py)
+        assert np.float32(s).tobytes() == np.float32(m["scale"]).tobytes(), (s, float(m["scale"]))
 
 
 def test_header_is_plain_c_and_library_links_without_torch(tmp_path):

@@ -421,7 +421,7 @@ def test_ba_failed_factorisation_gives_zero_step():
 
 
 # ------------------------------------------------------------------------------ renderer
-@pytest.mark.parametrize("R", [37, 256])
+@pytest.mark.parametrize("R", [37, 256, 1500])
 def test_neus_forward(R):
     from goslam_b200 import neus, synthetic
     offs, ress, _, total = neus.hashgrid_layout()
@@ -439,12 +439,12 @@ def test_neus_forward(R):
     net = net.to(dev())
     net.update_bound(torch.tensor([[-1.8, 1.9], [-2.0, 2.0], [-1.5, 2.0]]))
     ro, rd, zv, ds = synthetic.make_rays(R, S=72, seed=11)
-    out = net(ro.to(dev()), rd.to(dev()), zv.to(dev()), ds.to(dev()))
+    out = net(ro.to(dev()), rd.to(dev()), zv.to(dev()), ds.to(dev()), debug=True)
     ref = neus_oracle.forward(
         w["grid"].half().numpy(), w["sdf_w"].numpy(), w["sdf_b"].numpy(), w["color_B"].numpy(),
         w["mlp"].half().numpy(), np.array(bound, np.float32), net.realtime_bound.cpu().numpy(),
-        0.2, 10.0, ro.numpy(), rd.numpy(), zv.numpy(), ds.numpy())
-    assert set(out.keys()) == set(ref.keys())
+        0.2, 10.0, ro.numpy(), rd.numpy(), zv.numpy(), ds.numpy(), debug=True)
+    assert set(out.keys()) == set(k for k in ref.keys() if not k.startswith("_"))
     got = {k: v.cpu().numpy() for k, v in out.items()}
     assert (ref["weight_sum"] > 1e-3).mean() > 0.2, "degenerate test scene: nothing is rendered"
     # per-sample quantities before the NeuS alpha: 1e-4 relative (north_star)
@@ -454,26 +454,59 @@ def test_neus_forward(R):
     inb = ref["sdf"] != 100.0                 # the 100 sentinel would hide errors in a max-norm
     assert np.array_equal(inb, got["sdf"] != 100.0)
     assert np.abs(got["sdf"][inb] - ref["sdf"][inb]).max() < 1e-4 * np.abs(ref["sdf"][inb]).max()
-    # Composited outputs are NOT 1e-4-conditioned in fp32 for ANY implementation: the trilinear
-    # hash-grid gradient (the SDF normal that drives alpha) is piecewise constant, so a 1-ulp
-    # change of a sample position that sits on a fine-level cell face flips alpha for that
-    # sample.  We measure that conditioning on the oracle itself (ray origins moved by 1 ulp)
-    # and require (a) >= 95 % of rays (all but 3 for tiny batches) within 2e-4 of the scale and (b) the worst ray
-    # within max(8x the oracle's own 1-ulp sensitivity, one flipped sample = 2/S).
-    ref_ulp = neus_oracle.forward(
-        w["grid"].half().numpy(), w["sdf_w"].numpy(), w["sdf_b"].numpy(), w["color_B"].numpy(),
-        w["mlp"].half().numpy(), np.array(bound, np.float32), net.realtime_bound.cpu().numpy(),
-        0.2, 10.0, np.nextafter(ro.numpy(), np.float32(10)), rd.numpy(), zv.numpy(), ds.numpy())
-    for k in ("depth", "weight_sum", "normal", "depth_variance", "color"):
+    # per-sample intermediates that drive the compositing (test-only outputs of the kernel)
+    dbg = net.last_debug
+    assert np.abs(dbg["alpha"].cpu().numpy() - ref["_alpha"]).max() < 1e-5
+    assert np.abs(dbg["grad"].cpu().numpy().reshape(-1, 3) - ref["_grad"]).max() < 1e-5 * max(1.0, np.abs(ref["_grad"]).max())
+    assert np.array_equal(dbg["pos"].cpu().numpy().reshape(-1, 3)[ref["_mask"]], ref["_xn"])     # bit-identical positions
+    # Composited outputs, EVERY ray: 1e-4 relative (north_star).  (Round 1 needed a loose bound here: the
+    # oracle's level scales were 1 ulp off the library's at levels 3/6/8/11, which put samples on those levels'
+    # cell faces into the neighbouring cell — a different piecewise-constant normal.  Scales are now bit-exact,
+    # tests/test_abi.py, and the measured worst ray of 16k is 5e-6: profiles/r02_render_parity.txt.)
+    for k in ("depth", "weight_sum", "normal", "depth_variance"):
         assert got[k].shape == ref[k].shape, k
-        scale = max(np.abs(ref[k]).max(), 1e-12)
-        err = np.abs(got[k] - ref[k]).reshape(R, -1).max(1) / scale
-        sens = np.abs(ref_ulp[k] - ref[k]).max() / scale
-        tight = 2e-4 if k != "color" else 1.5e-3     # rgb passes through fp16 activations / fp16 sigmoid
-        assert (err >= tight).sum() <= max(3, 0.05 * R), (k, int((err >= tight).sum()), float(err.max()))
-        # a flipped fine-level cell changes ONE sample's alpha: at most ~2/S of the ray's scale
-        assert err.max() < max(8 * sens, 2.0 / 72), (k, float(err.max()), float(sens))
+        assert _rel(got[k], ref[k]) < 1e-4, (k, _rel(got[k], ref[k]))
+    # colour passes through fp16 activations and an fp16 sigmoid output per sample (tcnn's contract): one fp16
+    # rounding flip of one sample moves the composited colour by at most weight * 2^-11.  Bound: half an fp16 ulp
+    # of a value in [0.5, 1) in absolute terms for every ray, 1e-4 relative for 99 % of the rays.
+    assert got["color"].shape == ref["color"].shape
+    cerr = np.abs(got["color"] - ref["color"]).max(1)
+    assert cerr.max() < 2.5e-4, float(cerr.max())
+    assert (cerr / max(np.abs(ref["color"]).max(), 1e-12) < 1e-4).mean() >= 0.99
     assert abs(float(got["gradient_error"][0]) - float(ref["gradient_error"][0])) < 2e-3 * abs(float(ref["gradient_error"][0]))
+
+
+def test_neus_forward_vs_reference_golden():
+    """tests/golden/neus.npz = the REFERENCE's own InstantNeuS.forward (src/InstantNeuS.py:295-370, imported from
+    /root/reference by make_golden.py with only the tcnn modules restated): all 9 outputs, 1e-4 (colour: fp16 bound)."""
+    from goslam_b200 import neus, synthetic
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "neus.npz"))
+    offs, ress, _, total = neus.hashgrid_layout()
+    w = synthetic.make_neus_weights(seed=int(g["weights_seed"]), total_grid_params=total, layout=(offs, ress))
+    net = neus.InstantNeuS(synthetic.NEUS_CFG, g["bound"].tolist())
+    with torch.no_grad():
+        net.sdf_network.encoding.encoding.params.copy_(w["grid"])
+        net.sdf_network.sdf_layer.weight.copy_(w["sdf_w"])
+        net.sdf_network.sdf_layer.bias.copy_(w["sdf_b"])
+        net.color_network._B.copy_(w["color_B"])
+        net.color_network.network.params.copy_(w["mlp"])
+    net = net.to(dev())
+    net.update_bound(torch.from_numpy(g["rt_bound"]))
+    out = net(*[torch.from_numpy(g[k]).to(dev()) for k in ("rays_o", "rays_d", "z_vals_in", "dists")])
+    assert set(out.keys()) == set(k[4:] for k in g.files if k.startswith("out_"))
+    for k, v in out.items():
+        want = g["out_" + k]
+        got = v.cpu().numpy().reshape(want.shape)
+        if k == "color":
+            assert np.abs(got - want).max() < 2.5e-4
+        elif k == "sdf":
+            inb = want != 100.0
+            assert np.array_equal(inb, got != 100.0)
+            assert np.abs(got[inb] - want[inb]).max() < 1e-4 * np.abs(want[inb]).max()
+        elif k == "gradient_error":
+            assert abs(float(got.reshape(-1)[0]) - float(want.reshape(-1)[0])) < 1e-4 * abs(float(want.reshape(-1)[0]))
+        else:
+            assert _rel(got, want) < 1e-4, (k, _rel(got, want))
 
 
 # ------------------------------------------------------------------------------ z sampling
