@@ -901,7 +901,7 @@ ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __re
 // step on the host with Eigen SimplicialLLT (src/lib/droid_kernels.cu:1192-1213).
 // ------------------------------------------------------------------------------------
 constexpr int kCl = 8;        // portable cluster size
-constexpr int kClT = 256;     // threads per CTA
+constexpr int kClT = 512;     // threads per CTA
 
 __host__ __device__ inline int cl_row_off(int q, int l) {      // doubles before local block row l of CTA q
   return 36 * (l * (q + 1) + kCl * (l * (l - 1) / 2));
@@ -914,10 +914,16 @@ inline size_t cl_rows_doubles(int P) {                         // largest per-CT
   }
   return mx;
 }
+// rows | rhs[n] | ps[n] | panel[P][36] | dloc[36] | xs[16] | inbox[kCl][6]
 inline size_t cl_smem_bytes(int P) {
-  return (cl_rows_doubles(P) + 2 * (size_t)(6 * P) + (size_t)P * 36 + 36 + 16) * sizeof(double);
+  return (cl_rows_doubles(P) + 2 * (size_t)(6 * P) + (size_t)P * 36 + 36 + 16 + kCl * 6) * sizeof(double);
 }
 
+// Everything that crosses CTAs is PUSHED (remote stores, fire and forget) ahead of the cluster barrier that
+// publishes it, so no phase starts with a round trip through distributed shared memory:
+//   panel blocks  -> every CTA's `panel`   (by their owners, after the panel solve)
+//   next diagonal -> every CTA's `dloc`    (by its owner, as soon as its own row is updated)
+//   backward pass -> partial sums of the next 8 block rows go to their owners' `inbox`
 __global__ void __launch_bounds__(kClT)
 ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restrict__ sys_in, float lm,
                         float ep, int rows_doubles, float* dx_out, int* status_out) {
@@ -934,10 +940,18 @@ ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restric
   double* rows = smd;                                  // own block rows, row l = blocks 0..r (r = q + l*kCl)
   double* rhs = smd + rows_doubles;                    // [n]  replica of the right-hand side -> y = L^-1 b
   double* ps = rhs + n;                                // [n]  backward substitution: local partial sums
-  double* panel = ps + n;                              // [P][36] gathered block column
-  double* dloc = panel + (size_t)P * 36;               // [36] diagonal block of the current column
+  double* panel = ps + n;                              // [P][36] block column of the current step (pushed in)
+  double* dloc = panel + (size_t)P * 36;               // [36] diagonal block of the current step (pushed in)
   double* xs = dloc + 36;                              // [6] + [6]
+  double* inbox = xs + 16;                             // [kCl][6]: partial sums from CTA s for my NEXT own block row
   const int nl = (P - q + kCl - 1) / kCl;              // own block rows (may be <= 0 for tiny P)
+  double* peer_panel[kCl];
+  double* peer_dloc[kCl];
+#pragma unroll
+  for (int oq = 0; oq < kCl; ++oq) {
+    peer_panel[oq] = cluster.map_shared_rank(panel, oq);
+    peer_dloc[oq] = cluster.map_shared_rank(dloc, oq);
+  }
 
   // ---- load own rows (lower blocks incl. the diagonal one), damping on the diagonal
   for (int l = 0; l < nl; ++l) {
@@ -952,59 +966,100 @@ ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restric
     }
   }
   for (int i = tid; i < n; i += kClT) { rhs[i] = sys_in[(size_t)n * n + i]; ps[i] = 0.0; }
+  for (int i = tid; i < kCl * 6; i += kClT) inbox[i] = 0.0;
   if (tid == 0) failed = 0;
+  __syncthreads();
+  // 6x6 Cholesky of a diagonal block held in shared memory (lower triangle); leaves L^-1 (lower triangular) in
+  // its place.  With the explicit inverse, the panel solve X = A L^-T, the forward substitution of the right-hand
+  // side and the backward solve x = L^-T v are 6 INDEPENDENT dot products instead of a 21-deep chain of dependent
+  // fp64 operations (a dependent DFMA costs ~50 cycles here; probes: profiles/r02_cluster_solve.md).  The blocks
+  // are damped 6x6 pose blocks, far from singular; the factorisation itself stays a Cholesky.
+  // One thread; returns false when a pivot is not positive.
+  auto factor_block = [](double* blk) -> bool {
+    double l[6][6];
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) l[r][c] = blk[r * 6 + c];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double dkk = l[k][k];
+#pragma unroll
+      for (int m = 0; m < k; ++m) dkk -= l[k][m] * l[k][m];
+      ok = ok && (dkk > 0.0);
+      const double inv = rsqrt(dkk);
+      l[k][k] = inv;
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) {
+        double v = l[r][k];
+#pragma unroll
+        for (int m = 0; m < k; ++m) v -= l[r][m] * l[k][m];
+        l[r][k] = v * inv;
+      }
+    }
+    // in-place inverse of the lower-triangular factor (l[k][k] already holds 1/l_kk), column by column
+    double li[6][6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      li[k][k] = l[k][k];
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) {
+        double v = 0.0;
+#pragma unroll
+        for (int m = k; m < r; ++m) v -= l[r][m] * li[m][k];
+        li[r][k] = v * l[r][r];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) blk[r * 6 + c] = li[r][c];
+    return ok;
+  };
+  constexpr int kFG = 64;                              // "factor group": threads 0..63 of the next row's owner
+  if (q == 0) {                                        // first diagonal block: factor, then to everyone
+    if (tid == 0 && !factor_block(rows)) failed = 1;
+    __syncthreads();
+    if (tid < 36) {
+      const double v = rows[tid];
+#pragma unroll
+      for (int oq = 0; oq < kCl; ++oq) peer_dloc[oq][tid] = v;
+    }
+  }
   cluster.sync();
 
-  bool bad = false;
+#ifdef GOSLAM_BA_PROBE
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long pt0 = clock64();
+#define CL_PROBE(i) do { const long long t__ = clock64(); pc[i] += t__ - pt0; pt0 = t__; } while (0)
+#else
+#define CL_PROBE(i) do {} while (0)
+#endif
   for (int jb = 0; jb < P; ++jb) {
-    const int owner = jb % kCl, lo = jb / kCl;
-    // (A) diagonal block from its owner
-    if (tid < 36) {
-      const double* src = cluster.map_shared_rank(rows, owner) + cl_row_off(owner, lo) + jb * 36;
-      dloc[tid] = src[tid];
-    }
-    __syncthreads();
     // first own block row below jb
     const int l0 = jb < q ? 0 : (jb - q) / kCl + 1;
     const int npan = nl > l0 ? nl - l0 : 0;
-    double l[6][6];
+    // (A) panel solve of own rows with L_d^-1 of the diagonal block, which its owner pushed into dloc
     if (tid < 6 * npan || tid == 0) {
+      double l[6][6];
 #pragma unroll
       for (int r = 0; r < 6; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) l[r][c] = dloc[r * 6 + c];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        double dkk = l[k][k];
-#pragma unroll
-        for (int m = 0; m < k; ++m) dkk -= l[k][m] * l[k][m];
-        bad = bad || !(dkk > 0.0);
-        const double inv = rsqrt(dkk);
-        l[k][k] = inv;
-#pragma unroll
-        for (int r = k + 1; r < 6; ++r) {
-          double v = l[r][k];
-#pragma unroll
-          for (int m = 0; m < k; ++m) v -= l[r][m] * l[k][m];
-          l[r][k] = v * inv;
-        }
-      }
-      // (B) panel: one scalar row of one own block per thread
-      if (tid < 6 * npan) {
+      if (tid < 6 * npan) {                           // one scalar row of one own block per thread
         const int lr = l0 + tid / 6, a = tid % 6;
         double* blk = rows + cl_row_off(q, lr) + jb * 36 + a * 6;
         double x[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) x[k] = blk[k];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          double v = x[k];
+        for (int k = 0; k < 6; ++k) {                 // X = A L^-T: row a of the block times column k of L^-T
+          double v = x[0] * l[k][0];
 #pragma unroll
-          for (int m = 0; m < k; ++m) v -= x[m] * l[k][m];
-          x[k] = v * l[k][k];
+          for (int m = 1; m <= k; ++m) v += x[m] * l[k][m];
+          blk[k] = v;
         }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) blk[k] = x[k];
       }
       if (tid == 0) {                                 // right-hand-side row (replicated in every CTA)
         double x[6];
@@ -1012,98 +1067,117 @@ ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restric
         for (int k = 0; k < 6; ++k) x[k] = rhs[6 * jb + k];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-          double v = x[k];
+          double v = x[0] * l[k][0];
 #pragma unroll
-          for (int m = 0; m < k; ++m) v -= x[m] * l[k][m];
-          x[k] = v * l[k][k];
+          for (int m = 1; m <= k; ++m) v += x[m] * l[k][m];
+          rhs[6 * jb + k] = v; xs[k] = v;
         }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { rhs[6 * jb + k] = x[k]; xs[k] = x[k]; }
-      }
-    }
-    cluster.sync();                                   // panel blocks visible cluster-wide
-    if (q == owner && tid == 0) {                     // keep L_d (strictly lower + 1/l_kk) for the backward pass
-      double* blk = rows + cl_row_off(q, lo) + jb * 36;
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) blk[r * 6 + c] = l[r][c];
-    }
-    // (C) gather the block column below the diagonal
-    {
-      const int cnt = (P - 1 - jb) * 36;
-      for (int idx = tid; idx < cnt; idx += kClT) {
-        const int c = jb + 1 + idx / 36, e = idx % 36;
-        const int oq = c % kCl;
-        const double* src = cluster.map_shared_rank(rows, oq) + cl_row_off(oq, c / kCl) + jb * 36;
-        panel[(size_t)c * 36 + e] = src[e];
       }
     }
     __syncthreads();
-    // (D) trailing update of own rows: A[i,c] -= L[i,jb] L[c,jb]^T, jb < c <= i; one (c, row a) per item
-    for (int lr = l0; lr < nl; ++lr) {
-      const int r = q + lr * kCl;
-      double* rowp = rows + cl_row_off(q, lr);
-      const double* Li = rowp + jb * 36;
-      const int items = (r - jb) * 6;
-      for (int it = tid; it < items; it += kClT) {
-        const int c = jb + 1 + it / 6, a = it % 6;
-        double li[6], acc[6];
+    // push own panel blocks into every CTA's panel buffer
+    for (int idx = tid; idx < npan * 36 * kCl; idx += kClT) {
+      const int oq = idx % kCl, e = (idx / kCl) % 36, m = idx / (kCl * 36);
+      const int r = q + (l0 + m) * kCl;
+      peer_panel[oq][(size_t)r * 36 + e] = rows[cl_row_off(q, l0 + m) + jb * 36 + e];
+    }
+    CL_PROBE(0);
+    cluster.sync();                                   // the whole block column is in every CTA
+    CL_PROBE(1);
+    // (D0) In the CTA that owns block row jb+1, threads 0..63 update that row's diagonal block, factor it and
+    // push L_d to every CTA WHILE the other threads (and the other CTAs) do their trailing updates: the
+    // 6 sequential pivots (~1.5 k cycles of dependent fp64) are off the critical path.
+    const bool next_owner = (q == (jb + 1) % kCl) && (jb + 1 < P);
+    const bool in_fg = next_owner && tid < kFG;
+    if (in_fg) {
+      double* rowp = rows + cl_row_off(q, (jb + 1) / kCl);
+      double* dblk = rowp + (jb + 1) * 36;
+      if (tid < 36) {
+        const int a = tid / 6, b = tid % 6;
+        const double* Li = rowp + jb * 36;
+        double v = dblk[tid];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) li[k] = Li[a * 6 + k];
-        double* out = rowp + c * 36 + a * 6;
-        const double* Lc = panel + (size_t)c * 36;
+        for (int k = 0; k < 6; ++k) v -= Li[a * 6 + k] * Li[b * 6 + k];
+        dblk[tid] = v;
+      }
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+      if (tid == 0 && !factor_block(dblk)) failed = 1;
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+      if (tid < 36) {
+        const double v = dblk[tid];
 #pragma unroll
-        for (int b = 0; b < 6; ++b) {
-          double v = out[b];
+        for (int oq = 0; oq < kCl; ++oq) peer_dloc[oq][tid] = v;
+      }
+    } else {
+      // (D) trailing update of own rows: A[i,c] -= L[i,jb] L[c,jb]^T, jb < c <= i; items (row, c, scalar row a)
+      // flattened over the CTA's rows: row m (block row r = rb + kCl*m) has 6 * (base + kCl*m) items
+      const int ut = next_owner ? tid - kFG : tid, un = next_owner ? kClT - kFG : kClT;
+      if (npan > 0) {
+        const int base = q + l0 * kCl - jb;           // blocks of the first own row below jb (1..kCl)
+        const int total = 6 * (base * npan + (kCl / 2) * npan * (npan - 1));
+        // the next owner's first row is jb+1 itself (one block: the diagonal one, done by the factor group)
+        for (int it = ut + (next_owner ? 6 : 0); it < total; it += un) {
+          int m = 0, t = it, cnt = 6 * base;
+          while (t >= cnt) { t -= cnt; ++m; cnt += 6 * kCl; }
+          const int c = jb + 1 + t / 6, a = t % 6;
+          double* rowp = rows + cl_row_off(q, l0 + m);
+          const double* Li = rowp + jb * 36 + a * 6;
+          const double* Lc = panel + (size_t)c * 36;
+          double li[6], acc[6];
 #pragma unroll
-          for (int k = 0; k < 6; ++k) v -= li[k] * Lc[b * 6 + k];
-          acc[b] = v;
+          for (int k = 0; k < 6; ++k) li[k] = Li[k];
+          double* out = rowp + c * 36 + a * 6;
+#pragma unroll
+          for (int b = 0; b < 6; ++b) {
+            double v = out[b];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v -= li[k] * Lc[b * 6 + k];
+            acc[b] = v;
+          }
+#pragma unroll
+          for (int b = 0; b < 6; ++b) out[b] = acc[b];
         }
+      }
+      // right-hand-side row: b[c] -= y_jb L[c,jb]^T
+      for (int it = ut; it < (P - 1 - jb) * 6; it += un) {
+        const int c = jb + 1 + it / 6, b = it % 6;
+        const double* Lc = panel + (size_t)c * 36 + b * 6;
+        double v = rhs[6 * c + b];
 #pragma unroll
-        for (int b = 0; b < 6; ++b) out[b] = acc[b];
+        for (int k = 0; k < 6; ++k) v -= xs[k] * Lc[k];
+        rhs[6 * c + b] = v;
       }
     }
-    // right-hand-side row: b[c] -= y_jb L[c,jb]^T
-    for (int it = tid; it < (P - 1 - jb) * 6; it += kClT) {
-      const int c = jb + 1 + it / 6, b = it % 6;
-      const double* Lc = panel + (size_t)c * 36 + b * 6;
-      double v = rhs[6 * c + b];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) v -= xs[k] * Lc[k];
-      rhs[6 * c + b] = v;
-    }
-    cluster.sync();                                   // next diagonal block is final
+    CL_PROBE(2);
+    cluster.sync();                                   // next L_d is in every dloc; panel may be overwritten
+    CL_PROBE(3);
   }
-  if (bad && tid == 0) failed = 1;
-  __syncthreads();
 
-  // ---- backward substitution L^T x = y (only when the factorisation succeeded — uniform: every CTA
-  // factored the same diagonal blocks)
-  if (!failed) {
+  // ---- backward substitution L^T x = y.  Right-looking over block rows: the owner of row jb solves x_jb,
+  // folds it into its local partial sums ps[c] += L[jb,c]^T x_jb (c < jb) and pushes the entries of the next
+  // kCl block rows — final, because its next own row is jb - kCl — into their owners' inboxes.  Runs even
+  // after a failed pivot (NaNs are harmless here; the result is discarded): every CTA must take the same path.
+  {
     for (int jb = P - 1; jb >= 0; --jb) {
       const int owner = jb % kCl, lo = jb / kCl;
       if (q == owner) {
-        if (tid < 6) {
-          double sacc = 0.0;
-#pragma unroll
-          for (int oq = 0; oq < kCl; ++oq) sacc += cluster.map_shared_rank(ps, oq)[6 * jb + tid];
-          xs[6 + tid] = rhs[6 * jb + tid] - sacc;
-        }
-        __syncthreads();
         const double* Ld = rows + cl_row_off(q, lo) + jb * 36;
         if (tid == 0) {
-          double x[6];
+          double v6[6], x[6];
 #pragma unroll
-          for (int k = 0; k < 6; ++k) x[k] = xs[6 + k];
+          for (int k = 0; k < 6; ++k) {
+            const double s01 = inbox[0 * 6 + k] + inbox[1 * 6 + k], s23 = inbox[2 * 6 + k] + inbox[3 * 6 + k];
+            const double s45 = inbox[4 * 6 + k] + inbox[5 * 6 + k], s67 = inbox[6 * 6 + k] + inbox[7 * 6 + k];
+            v6[k] = rhs[6 * jb + k] - ((s01 + s23) + (s45 + s67));
+          }
           int nf = 0;
 #pragma unroll
-          for (int k = 5; k >= 0; --k) {
-            double v = x[k];
+          for (int k = 0; k < 6; ++k) {               // x = L_d^-T v (Ld holds L_d^-1)
+            double v = Ld[k * 6 + k] * v6[k];
 #pragma unroll
-            for (int m = k + 1; m < 6; ++m) v -= Ld[m * 6 + k] * x[m];
-            x[k] = v * Ld[k * 6 + k];
-            nf |= !isfinite(x[k]);
+            for (int m = k + 1; m < 6; ++m) v += Ld[m * 6 + k] * v6[m];
+            x[k] = v;
+            nf |= !isfinite(v);
           }
 #pragma unroll
           for (int k = 0; k < 6; ++k) { xs[k] = x[k]; ws.dx[6 * jb + k] = (float)x[k]; }
@@ -1111,7 +1185,18 @@ ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restric
         }
         __syncthreads();
         const double* rowp = rows + cl_row_off(q, lo);
-        for (int it = tid; it < jb * 6; it += kClT) {
+        // the next kCl block rows first (their sums are pushed), then the rest
+        const int cpush = jb < kCl ? jb : kCl;          // rows jb-1 .. jb-cpush
+        if (tid < cpush * 6) {
+          const int c = jb - 1 - tid / 6, k = tid % 6;
+          const double* blk = rowp + c * 36;
+          double v = ps[6 * c + k];
+#pragma unroll
+          for (int m = 0; m < 6; ++m) v += blk[m * 6 + k] * xs[m];
+          ps[6 * c + k] = v;
+          cluster.map_shared_rank(inbox, c % kCl)[q * 6 + k] = v;     // one slot per sender: a CTA has one own row per kCl rows
+        }
+        for (int it = tid; it < (jb - cpush) * 6; it += kClT) {
           const int c = it / 6, k = it % 6;
           const double* blk = rowp + c * 36;
           double v = ps[6 * c + k];
@@ -1120,9 +1205,16 @@ ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restric
           ps[6 * c + k] = v;
         }
       }
+      CL_PROBE(5);
       cluster.sync();
+      CL_PROBE(6);
     }
   }
+#ifdef GOSLAM_BA_PROBE
+  if (tid == 0 && (q == 0 || q == 5))
+    printf("[cluster solve probe cta %d, P=%d] panel+push %lld | barrier1 %lld | update (factor hidden) %lld | barrier2 %lld | "
+           "backward work %lld | backward barrier %lld (cycles)\n", q, P, pc[0], pc[1], pc[2], pc[3], pc[5], pc[6]);
+#endif
   // ---- status, dx, retraction (CTA 0); the others stay until their flags have been read
   if (q == 0) {
     __shared__ int any_fail;
