@@ -33,6 +33,10 @@ class NeusOut(ctypes.Structure):
     ]
 
 
+class GruWeights(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("w_zr", "w_q", "w_w", "b_zr", "b_q", "b_w", "w_glo", "b_glo")]
+
+
 # name -> (restype, argtypes); every symbol include/goslam_b200.h declares
 SIGNATURES = {
     "goslam_version": (c_int, []),
@@ -76,6 +80,10 @@ SIGNATURES = {
     "goslam_proximity_edges": (c_int, [c_void_p] + [c_int] * 5 + [c_float, c_float, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                                                c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                                                c_size_t, c_void_p]),
+    "goslam_conv_gru_workspace_bytes": (c_size_t, [c_int] * 3),
+    "goslam_conv_gru": (c_int, [ctypes.POINTER(GruWeights)] + [c_void_p] * 5 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "goslam_nchw_to_nhwc_f16": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
+    "goslam_nhwc_to_nchw_f16": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
     "goslam_corr_index_backward": (c_int, []),
     "goslam_altcorr_backward": (c_int, []),
 }

@@ -309,6 +309,32 @@ int goslam_proximity_edges(const float* dist, int t0, int t1, int t, int rad, in
                            int64_t* es_j, int cap, int* num_edges, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * ConvGRU of the update operator.  Replaces ConvGRU.forward (src/modules/gru.py:21-39) as
+ * UpdateModule calls it (src/droid_net.py:125): three tcgen05 implicit-GEMM convolution passes with the gate
+ * arithmetic fused into their epilogues (csrc/conv_tc.cu).
+ *   State and inputs are NHWC f16: net, inp, corr [B,h,w,128], flow [B,h,w,64]; net_out [B,h,w,128] (may alias
+ *   nothing else).  goslam_nchw_to_nhwc_f16 / goslam_nhwc_to_nchw_f16 convert from / to the reference's
+ *   [B,C,h,w] tensors ([B,C,hw] <-> [B,hw,C]).
+ *   Weights (device pointers), packed from the reference module's parameters:
+ *     w_zr  f16 [9][256][448]  convz.weight | convr.weight stacked along cout; tap = 3*ky + kx; cin order
+ *                              net(128) | inp(128) | corr(128) | flow(64) = torch.cat order of the reference
+ *     w_q   f16 [9][128][448]  convq.weight        w_w f16 [128][128]  w.weight (1x1)
+ *     b_zr  f32 [256], b_q f32 [128], b_w f32 [128]
+ *     w_glo f32 [384][128], b_glo f32 [384]   convz_glo | convr_glo | convq_glo (1x1 on the pooled vector)
+ * ---------------------------------------------------------------------------------- */
+typedef struct goslam_gru_weights {
+  const void* w_zr; const void* w_q; const void* w_w;
+  const float* b_zr; const float* b_q; const float* b_w;
+  const float* w_glo; const float* b_glo;
+} goslam_gru_weights;
+size_t goslam_conv_gru_workspace_bytes(int B, int h, int w);
+int goslam_conv_gru(const goslam_gru_weights* weights, const void* net, const void* inp, const void* corr,
+                    const void* flow, void* net_out, int B, int h, int w, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int goslam_nchw_to_nhwc_f16(const void* src, void* dst, int B, int C, int hw, void* stream);
+int goslam_nhwc_to_nchw_f16(const void* src, void* dst, int B, int C, int hw, void* stream);
+
 /* Training-only entry points of the reference module are exported for ABI completeness
  * and return GOSLAM_EUNSUPPORTED (inference path is torch.no_grad, src/slam.py:45). */
 int goslam_corr_index_backward(void);

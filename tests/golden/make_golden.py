@@ -18,6 +18,7 @@ What each fixture pins:
     altcorr_pyramid.npz AltCorrBlock.__init__ pyramid            src/modules/corr.py:97-111
     backend_edges.npz Backend.ba edge selection (loop=False)      src/backend.py:25-99
     factor_graph.npz  FactorGraph + DepthVideo state machine      src/factor_graph.py:85-450, src/depth_video.py:194-269
+    conv_gru.npz      ConvGRU.forward (fp32)                      src/modules/gru.py:21-39
 Run:  python tests/golden/make_golden.py      (writes next to this file)
 """
 import importlib
@@ -429,6 +430,27 @@ def gen_factor_graph():
     np.savez_compressed(os.path.join(HERE, "factor_graph.npz"), **out)
     print("factor_graph: %d snapshots, %d age evictions, final edges %s" % (int(out["n_steps"]), len(disagreements),
                                                                             [int(out["s%02d_ii" % k].size) for k in range(int(out["n_steps"]))]))
+
+
+def gen_conv_gru():
+    """ConvGRU.forward (src/modules/gru.py:21-39) itself, fp32 on the CPU, default-initialised weights under
+    torch.manual_seed(77) (the test rebuilds them the same way); ragged sizes (w % 16 != 0, h % 8 != 0)."""
+    gru_mod = ref_import("src.modules.gru")
+    out = {}
+    for tag, (B, h, w) in {"a": (3, 16, 24), "b": (2, 12, 20)}.items():
+        torch.manual_seed(77)
+        gru = gru_mod.ConvGRU(128, 128 + 128 + 64)
+        g = torch.Generator().manual_seed(5 + B)
+        # inputs are fp16-representable (stored as fp16): the graph keeps net / inp / corr / flow in half anyway
+        net = torch.tanh(torch.randn(B, 128, h, w, generator=g)).half()
+        inp = torch.relu(torch.randn(B, 128, h, w, generator=g)).half()
+        corr = torch.relu(torch.randn(B, 128, h, w, generator=g)).half()
+        flow = torch.relu(torch.randn(B, 64, h, w, generator=g)).half()
+        with torch.no_grad():
+            res = gru(net.float(), inp.float(), corr.float(), flow.float())
+        out.update({tag + "_net": net.numpy(), tag + "_inp": inp.numpy(), tag + "_corr": corr.numpy(), tag + "_flow": flow.numpy(),
+                    tag + "_out": res.numpy(), tag + "_wsum": np.float64(sum(float(p.double().sum()) for p in gru.parameters()))})
+    np.savez_compressed(os.path.join(HERE, "conv_gru.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -1,5 +1,5 @@
 """Tiny driver for ncu captures: runs each hot-path kernel a few times on config-2 shapes.
-usage: python tools/profile_driver.py [build|lookup|ba|neus|all] [reps]"""
+usage: python tools/profile_driver.py [build|build60|lookup|ba|balarge|neus|all] [reps]"""
 import os
 import sys
 
@@ -35,6 +35,24 @@ def main():
             d["disps"].copy_(win.disps0)
             droid_backends.ba(d["poses"], d["disps"], d["intrinsics"][0], d["disps_sens"], d["targets"], d["weights"],
                               d["eta"], ii, jj, 1, bench.NUM_KF, bench.BA_ITERS, 1e-4, 0.1, False)
+    if what == "build60":                          # north_star headline shape (640x480 -> 60x80)
+        sc60 = bench.make_window(143, ht=60, wd=80)
+        win60 = bench.Window(sc60, dev)
+        km60 = fmaps_to_kmajor(win60.d["fmaps"][:win60.num_kf])
+        for _ in range(reps):
+            win60.build(km60)
+    if what == "balarge":                          # config-4-sized global BA: prep, linearise, system, cluster solve, back-substitution
+        from goslam_b200 import synthetic
+        num_kf, ht, wd = 64, 30, 40
+        s4, g4 = synthetic.make_scene(num_kf=num_kf, ht=ht, wd=wd, rgbd=True, seed=43, with_fmaps=False, buffer=num_kf + 2)
+        s4["t0"], s4["t1"] = 1, num_kf
+        tg, wg, eta = synthetic.make_update(s4, synthetic.true_reprojection(s4)[0], g4, noise=0.7)
+        D4 = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in s4.items()}
+        tg, wg, eta = tg.to(dev), wg.to(dev), eta.to(dev)
+        for _ in range(reps):
+            p4, d4 = D4["poses"].clone(), D4["disps"].clone()
+            droid_backends.ba(p4, d4, D4["intrinsics"][0].contiguous(), D4["disps_sens"], tg, wg, eta, D4["ii"], D4["jj"], 1, num_kf,
+                              2, 1e-5, 1e-2, False)
     if what in ("neus", "all"):
         bench.RAYS = 1 << 16
         net, rays, _ = bench.make_renderer(dev, 43)
