@@ -968,7 +968,9 @@ ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restric
   for (int i = tid; i < n; i += kClT) { rhs[i] = sys_in[(size_t)n * n + i]; ps[i] = 0.0; }
   for (int i = tid; i < kCl * 6; i += kClT) inbox[i] = 0.0;
   if (tid == 0) failed = 0;
-  __syncthreads();
+  // every CTA of the cluster must be running before anybody stores into its shared memory (compute-sanitizer:
+  // "block that might not have entered yet"); also orders the loads above with the factor below
+  cluster.sync();
   // 6x6 Cholesky of a diagonal block held in shared memory (lower triangle); leaves L^-1 (lower triangular) in
   // its place.  With the explicit inverse, the panel solve X = A L^-T, the forward substitution of the right-hand
   // side and the backward solve x = L^-T v are 6 INDEPENDENT dot products instead of a 21-deep chain of dependent

@@ -47,6 +47,55 @@ __global__ void p5(uint4* out, int N) {   // warp = one src pixel, 8 full rows =
       }
   }
 }
+// ---- tiled slot-pool layout (levels 0: 4x4-element tiles, tile-row-major: a band of 8 rows = 1280 B contiguous per plane)
+// p6: the build kernel's epilogue pattern: thread = src pixel; per MMA tile (8x16 patch) two 128-byte runs (one per
+//     tile-row, 640 B apart) as 4 + 4 STG.256; 5 x-tiles per band, 5 bands
+__global__ void p6(uint4* out, int N) {
+  const int items = N * 25 * 5;
+  const int group = threadIdx.x >> 7, lane_src = threadIdx.x & 127;      // blockDim/128 groups alternate x-tiles
+  const int ngroups = blockDim.x >> 7;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int yb = item % 5, mt = (item / 5) % 25, n = item / 125;
+    const int src = mt * 128 + lane_src;
+    char* band = (char*)out + ((size_t)n * HW + src) * (H * W * 2) + yb * 1280;
+    for (int xb = group; xb < 5; xb += ngroups)
+      for (int tr = 0; tr < 2; ++tr)
+        for (int t = 0; t < 4; ++t) {
+          char* p = band + tr * 640 + (xb * 4 + t) * 32;
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%1,%2,%3,%4};" ::"l"(p), "r"(item), "r"(xb), "r"(tr), "r"(src) : "memory");
+        }
+  }
+}
+// p7: same bytes, but one store instruction = 8 planes x 128 contiguous bytes (lane -> plane lane/4, 32-byte piece lane%4)
+__global__ void p7(uint4* out, int N) {
+  const int items = N * 25 * 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int yb = item % 5, mt = (item / 5) % 25, n = item / 125;
+    // work units: (x-tile, tile-row, group of 8 planes): 5 * 2 * 16 = 160 per item
+    for (int u = warp; u < 160; u += nwarps) {
+      const int pg = u % 16, tr = (u / 16) % 2, xb = u / 32;
+      const int src = mt * 128 + pg * 8 + (lane >> 2);
+      char* p = (char*)out + ((size_t)n * HW + src) * (H * W * 2) + yb * 1280 + tr * 640 + (xb * 4 + (lane & 3)) * 32;
+      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%1,%2,%3,%4};" ::"l"(p), "r"(item), "r"(xb), "r"(tr), "r"(src) : "memory");
+    }
+  }
+}
+// p8: staged band: one warp writes one plane's whole 1280-byte band (40 x 32 B: 32 lanes + 8 lanes)
+__global__ void p8(uint4* out, int N) {
+  const int items = N * 25 * 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int yb = item % 5, mt = (item / 5) % 25, n = item / 125;
+    for (int s = warp; s < 128; s += nwarps) {
+      char* band = (char*)out + ((size_t)n * HW + mt * 128 + s) * (H * W * 2) + yb * 1280;
+      for (int k = lane; k < 40; k += 32) {
+        char* p = band + k * 32;
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%1,%2,%3,%4};" ::"l"(p), "r"(item), "r"(k), "r"(s), "r"(lane) : "memory");
+      }
+    }
+  }
+}
 __global__ void p4(uint4* out, size_t n16) {   // fully coalesced stream
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
     out[i] = make_uint4(i, 1, 2, 3);
@@ -72,5 +121,12 @@ int main() {
   run("p5 warp=src, 1280 B contiguous", [&] { p5<<<148, 128>>>(buf, N); });
   run("p5 same, 4 CTAs/SM", [&] { p5<<<592, 128>>>(buf, N); });
   run("p4 coalesced stream", [&] { p4<<<148 * 8, 256>>>(buf, bytes / 16); });
+  run("p6 tiled, thread=src, 2x128 B runs, 128 thr/SM", [&] { p6<<<148, 128>>>(buf, N); });
+  run("p6 same, 256 thr/SM", [&] { p6<<<148, 256>>>(buf, N); });
+  run("p6 same, 512 thr/SM (the kernel's 16 epilogue warps)", [&] { p6<<<148, 512>>>(buf, N); });
+  run("p7 tiled, 8 planes x 128 B per instruction, 128 thr/SM", [&] { p7<<<148, 128>>>(buf, N); });
+  run("p7 same, 512 thr/SM", [&] { p7<<<148, 512>>>(buf, N); });
+  run("p8 tiled, warp = plane, 1280 B band, 128 thr/SM", [&] { p8<<<148, 128>>>(buf, N); });
+  run("p8 same, 512 thr/SM", [&] { p8<<<148, 512>>>(buf, N); });
   return 0;
 }
