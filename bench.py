@@ -471,6 +471,73 @@ def sharded_graph_leg(dev, steps, warm, barrier, world, rank):
             "local_edges_rank0": int(sg.ii.numel()), "replicas_bit_identical": agree}
 
 
+def full_update_leg(dev, steps, warm, barrier, world, rank):
+    """configs[2]-style front-end update THROUGH THE REFERENCE-FACING API: goslam_b200.FactorGraph.update on a
+    goslam_b200.DepthVideo (Replica shapes: 8 keyframes, 40x80, 36 edges) with the update operator in the loop —
+    reproject + motion features, 4-level lookup, UpdateModule (tcgen05 ConvGRU, channels-last torch encoders / heads),
+    2 BA iterations, clamp.  Random-init weights of the reference architecture (no checkpoint travels to the box);
+    graph state is restored before every update so that all steps see the same inputs."""
+    import types
+    from goslam_b200 import synthetic
+    from goslam_b200.depth_video import DepthVideo
+    from goslam_b200.droid_net import UpdateModule
+    from goslam_b200.factor_graph import FactorGraph
+    sc, g = synthetic.make_scene(num_kf=NUM_KF, ht=HT, wd=WD, seed=243 + rank, rgbd=True, buffer=NUM_KF + 2)
+    cfg = {"cam": {"H_out": 8 * HT, "W_out": 8 * WD}, "mode": "rgbd", "tracking": {"buffer": NUM_KF + 2}}
+    video = DepthVideo(cfg, types.SimpleNamespace(device=str(dev)))
+    for k in ("poses", "disps", "disps_sens", "intrinsics", "fmaps"):
+        getattr(video, k)[:] = sc[k].to(dev)
+    video.nets[:] = (0.5 * torch.randn(NUM_KF + 2, 128, HT, WD, generator=g)).half().to(dev)
+    video.inps[:] = (0.5 * torch.randn(NUM_KF + 2, 128, HT, WD, generator=g)).abs().half().to(dev)
+    video.counter.value = NUM_KF
+    torch.manual_seed(11)
+    op = UpdateModule().to(dev).eval()
+    with torch.no_grad():                                    # keep the random operator's flow corrections small
+        for head in (op.delta[2], op.weight[2]):
+            head.weight.mul_(0.05)
+    graph = FactorGraph(video, op, device=str(dev), max_factors=48, upsample=False)
+    graph.add_neighborhood_factors(0, NUM_KF, r=3)
+    saved = dict(poses=video.poses.clone(), disps=video.disps.clone(), net=graph.net.clone(), target=graph.target.clone(),
+                 weight=graph.weight.clone(), damping=graph.damping.clone())
+
+    def update():
+        video.poses.copy_(saved["poses"]); video.disps.copy_(saved["disps"]); graph.damping.copy_(saved["damping"])
+        graph.net, graph.target, graph.weight = saved["net"].clone(), saved["target"].clone(), saved["weight"].clone()
+        graph.update(1, NUM_KF, iters=2, use_inactive=False)
+
+    ms = max_over_ranks(time_gpu(update, steps, warm, barrier), world)
+    # the operator alone, and its ConvGRU against the same module evaluated by torch / cuDNN under autocast
+    coords1, motion = graph._features(graph.ii, graph.jj, graph.target)
+    corr = graph.corr(coords1)
+    ms_op = time_gpu(lambda: op(graph.net, graph.inp, corr, motion, graph.ii, graph.jj), max(5, steps // 2), 3, lambda: None)
+    gru = op.gru
+    B = int(graph.ii.numel())
+    gi = [torch.randn(B, c, HT, WD, device=dev).half() for c in (128, 128, 128, 64)]
+
+    def cudnn_gru():
+        with torch.no_grad(), torch.autocast("cuda", enabled=True):
+            net, x = gi[0], torch.cat(gi[1:], dim=1)
+            net_inp = torch.cat([net, x], dim=1)
+            glo = (torch.sigmoid(gru.w(net)) * net).view(B, 128, HT * WD).mean(dim=-1, keepdim=True).view(B, 128, 1, 1)
+            z = torch.sigmoid(gru.convz(net_inp) + gru.convz_glo(glo))
+            r = torch.sigmoid(gru.convr(net_inp) + gru.convr_glo(glo))
+            q = torch.tanh(gru.convq(torch.cat([r * net, x], dim=1)) + gru.convq_glo(glo))
+            return (1 - z) * net + z * q
+    nh = [t.permute(0, 2, 3, 1).contiguous() for t in gi]
+    ms_gru = time_gpu(lambda: gru.forward_nhwc(*nh), max(5, steps // 2), 3, lambda: None)
+    ms_cudnn = time_gpu(cudnn_gru, max(5, steps // 2), 3, lambda: None)
+    flops = 2.0 * B * HT * WD * (3 * 9 * 448 * 128 + 128 * 128)
+    pk = peaks()
+    return {"metric": "keyframe-BA-updates/s incl. the update operator", "value": world * 1e3 / ms, "unit": "updates/s",
+            "ms_per_update": ms, "call": "goslam_b200.FactorGraph.update(t0=1, t1=8, iters=2) on goslam_b200.DepthVideo",
+            "workload": "configs[2]-style front-end update: 8 keyframes, 40x80 @1/8, 36 edges, update operator (random-init "
+                        "weights of the reference architecture) + lookup + 2 BA iterations",
+            "update_operator_ms": ms_op,
+            "conv_gru": {"kernel": "conv_tc_kernel x3 (tcgen05 implicit GEMM, fused gates)", "ms": ms_gru,
+                         "tflops": flops / (ms_gru * 1e-3) / 1e12, "frac_of_measured_bf16_burst": flops / (ms_gru * 1e-3) / 1e12 / pk["tf_burst"],
+                         "torch_cudnn_autocast_ms": ms_cudnn, "speedup_vs_cudnn": ms_cudnn / ms_gru, "bound": "tensor"}}
+
+
 def render_leg(dev, rank, world, steps, barrier, pk, n_samples, n_surface, with_device_leg=True):
     """2^18-ray batches through the fused marcher; e2e = Renderer.render_batch_ray from pinned host rays"""
     import types
@@ -513,7 +580,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--only", default="", help="comma list of legs to run besides the main one: headline,sharded,render")
+    ap.add_argument("--only", default="", help="comma list of legs to run besides the main one: headline,sharded,full,render")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -532,7 +599,7 @@ def main():
         barrier = lambda: dist.barrier()   # noqa: E731
     else:
         barrier = lambda: None             # noqa: E731
-    legs = set(x for x in args.only.split(",") if x) or {"headline", "sharded", "render"}
+    legs = set(x for x in args.only.split(",") if x) or {"headline", "sharded", "full", "render"}
     if args.no_render:
         legs.discard("render")
 
@@ -563,6 +630,10 @@ def main():
     # ---- configs[3]: one global-BA graph sharded over the ranks (strong scaling, NCCL exchange per BA iteration)
     if "sharded" in legs:
         line["sharded_graph"] = sharded_graph_leg(dev, max(10, args.steps // 2), warm, barrier, world, rank)
+
+    # ---- configs[2]-style update with the update operator in the loop, through FactorGraph.update
+    if "full" in legs:
+        line["full_update"] = full_update_leg(dev, max(10, args.steps // 2), warm, barrier, world, rank)
 
     if "render" in legs:
         line["render"] = render_leg(dev, rank, world, args.steps, barrier, pk, 24, SAMPLES - 24)

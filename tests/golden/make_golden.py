@@ -19,6 +19,7 @@ What each fixture pins:
     backend_edges.npz Backend.ba edge selection (loop=False)      src/backend.py:25-99
     factor_graph.npz  FactorGraph + DepthVideo state machine      src/factor_graph.py:85-450, src/depth_video.py:194-269
     conv_gru.npz      ConvGRU.forward (fp32)                      src/modules/gru.py:21-39
+    update_module.npz UpdateModule.forward incl. GraphAgg (fp32)  src/droid_net.py:33-140
 Run:  python tests/golden/make_golden.py      (writes next to this file)
 """
 import importlib
@@ -451,6 +452,28 @@ def gen_conv_gru():
         out.update({tag + "_net": net.numpy(), tag + "_inp": inp.numpy(), tag + "_corr": corr.numpy(), tag + "_flow": flow.numpy(),
                     tag + "_out": res.numpy(), tag + "_wsum": np.float64(sum(float(p.double().sum()) for p in gru.parameters()))})
     np.savez_compressed(os.path.join(HERE, "conv_gru.npz"), **out)
+
+
+def gen_update_module():
+    """UpdateModule.forward (src/droid_net.py:107-140) of the reference, fp32 on the CPU, default-initialised weights
+    under torch.manual_seed(78); inputs are fp16-representable (the graph holds them in half)."""
+    dn = ref_import("src.droid_net")
+    torch.manual_seed(78)
+    upd = dn.UpdateModule()
+    g = torch.Generator().manual_seed(9)
+    num, h, w = 6, 16, 24
+    net = torch.tanh(torch.randn(1, num, 128, h, w, generator=g)).half()
+    inp = torch.relu(torch.randn(1, num, 128, h, w, generator=g)).half()
+    corr = (0.7 * torch.randn(1, num, 196, h, w, generator=g)).half()
+    flow = (4.0 * torch.randn(1, num, 4, h, w, generator=g)).clamp(-64, 64).half()
+    ii = torch.tensor([0, 0, 1, 3, 3, 1])
+    jj = torch.tensor([1, 2, 0, 1, 2, 3])
+    with torch.no_grad():
+        n2, delta, weight, eta, upmask = upd(net.float(), inp.float(), corr.float(), flow.float(), ii, jj)
+    np.savez_compressed(os.path.join(HERE, "update_module.npz"), net=net.numpy(), inp=inp.numpy(), corr=corr.numpy(),
+                        flow=flow.numpy(), ii=ii.numpy(), jj=jj.numpy(), out_net=n2.half().numpy(), out_delta=delta.numpy(),
+                        out_weight=weight.numpy(), out_eta=eta.numpy(), out_upmask=upmask[:, :, ::9].numpy(),
+                        wsum=np.float64(sum(float(p.detach().double().sum()) for p in upd.parameters())))
 
 
 if __name__ == "__main__":

@@ -80,3 +80,42 @@ def test_layout_helpers_round_trip():
     y = to_nhwc(x)
     assert y.shape == (3, 11, 13, 70) and torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
     assert torch.equal(to_nchw(y), x)
+
+
+def test_update_module_vs_reference_golden():
+    """goslam_b200.droid_net.UpdateModule (tcgen05 ConvGRU + channels-last torch encoders / heads / GraphAgg, autocast)
+    against the reference UpdateModule's fp32 outputs (tests/golden/update_module.npz): same parameter names (the
+    `update.*` keys of pretrained/droid.pth load), same five outputs and shapes."""
+    from goslam_b200.droid_net import UpdateModule
+    g = np.load(os.path.join(HERE, "golden", "update_module.npz"))
+    torch.manual_seed(78)
+    m = UpdateModule()
+    assert abs(sum(float(p.detach().double().sum()) for p in m.parameters()) - float(g["wsum"])) < 1e-5
+    m = m.to(dev())
+    t = lambda k: torch.from_numpy(g[k]).to(dev())                              # noqa: E731
+    net, delta, weight, eta, upmask = m(t("net"), t("inp"), t("corr"), t("flow"), t("ii"), t("jj"))
+    assert net.shape == (1, 6, 128, 16, 24) and delta.shape == weight.shape == (1, 6, 16, 24, 2)
+    assert eta.shape == (1, 3, 16, 24) and upmask.shape == (1, 3, 576, 16, 24)
+    # fp16 autocast arithmetic (the reference's own precision on a GPU) against the fp32 CPU run
+    for name, got, want, tol in (("net", net, g["out_net"], 1.5e-2), ("delta", delta, g["out_delta"], 1.5e-2),
+                                 ("weight", weight, g["out_weight"], 1e-2), ("eta", eta, g["out_eta"], 1e-3),
+                                 ("upmask", upmask[:, :, ::9], g["out_upmask"], 2e-2)):
+        err = (got.float().cpu() - torch.from_numpy(want).float()).abs()
+        assert err.max().item() < tol, (name, err.max().item())
+        assert err.mean().item() < tol / 8, (name, err.mean().item())
+    # and as FactorGraph's update_op: one update of a small graph runs end to end
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "tools"))
+    import fg_scenario
+    from goslam_b200.depth_video import DepthVideo
+    from goslam_b200.factor_graph import FactorGraph
+    cfg, args = fg_scenario.cfg_and_args("cuda:0")
+    video = DepthVideo(cfg, args)
+    fg_scenario.fill_video(video, fg_scenario.make_inputs())
+    graph = FactorGraph(video, m, device="cuda:0", max_factors=40, upsample=True)
+    graph.add_neighborhood_factors(0, 6, r=2)
+    p0 = video.poses.clone()
+    graph.update(1, use_inactive=True)
+    graph.update(None, None, use_inactive=True)
+    assert torch.isfinite(video.poses).all() and torch.isfinite(video.disps).all() and not torch.equal(video.poses, p0)
+    assert graph.net.shape == (1, graph.ii.numel(), 128, 16, 24) and graph.weight.min().item() >= 0.0
