@@ -474,8 +474,8 @@ def sharded_graph_leg(dev, steps, warm, barrier, world, rank):
 def full_update_leg(dev, steps, warm, barrier, world, rank):
     """configs[2]-style front-end update THROUGH THE REFERENCE-FACING API: goslam_b200.FactorGraph.update on a
     goslam_b200.DepthVideo (Replica shapes: 8 keyframes, 40x80, 36 edges) with the update operator in the loop —
-    reproject + motion features, 4-level lookup, UpdateModule (tcgen05 ConvGRU, channels-last torch encoders / heads),
-    2 BA iterations, clamp.  Random-init weights of the reference architecture (no checkpoint travels to the box);
+    reproject + motion features, 4-level lookup, UpdateModule (one library call: tcgen05 implicit-GEMM encoders, ConvGRU,
+    heads, GraphAgg), 2 BA iterations, clamp.  Random-init weights of the reference architecture (no checkpoint travels to the box);
     graph state is restored before every update so that all steps see the same inputs."""
     import types
     from goslam_b200 import synthetic
@@ -512,6 +512,25 @@ def full_update_leg(dev, steps, warm, barrier, world, rank):
     ms_op = time_gpu(lambda: op(graph.net, graph.inp, corr, motion, graph.ii, graph.jj), max(5, steps // 2), 3, lambda: None)
     gru = op.gru
     B = int(graph.ii.numel())
+
+    def torch_update_op():
+        """the reference UpdateModule.forward op for op (src/droid_net.py:107-140) in torch / cuDNN under autocast, on the
+        same parameters: what `update_operator_ms` replaces"""
+        with torch.no_grad(), torch.autocast("cuda", enabled=True):
+            n_, i_, c_, f_ = [x.reshape(B, -1, HT, WD) for x in (graph.net, graph.inp, corr, motion)]
+            c_, f_ = op.corr_encoder(c_), op.flow_encoder(f_)
+            x = torch.cat([i_, c_, f_], dim=1)
+            net_inp = torch.cat([n_, x], dim=1)
+            glo = (torch.sigmoid(gru.w(n_)) * n_).view(B, 128, HT * WD).mean(dim=-1, keepdim=True).view(B, 128, 1, 1)
+            z = torch.sigmoid(gru.convz(net_inp) + gru.convz_glo(glo))
+            r = torch.sigmoid(gru.convr(net_inp) + gru.convr_glo(glo))
+            q = torch.tanh(gru.convq(torch.cat([r * n_, x], dim=1)) + gru.convq_glo(glo))
+            n2 = (1 - z) * n_ + z * q
+            delta = op.delta(n2).view(1, B, -1, HT, WD).permute(0, 1, 3, 4, 2)[..., :2].contiguous()
+            weight = op.weight(n2).view(1, B, -1, HT, WD).permute(0, 1, 3, 4, 2)[..., :2].contiguous()
+            eta, upmask = op.agg(n2.view(1, B, 128, HT, WD), graph.ii)
+            return n2, delta, weight, eta, upmask
+    ms_op_torch = time_gpu(torch_update_op, max(5, steps // 2), 3, lambda: None)
     gi = [torch.randn(B, c, HT, WD, device=dev).half() for c in (128, 128, 128, 64)]
 
     def cudnn_gru():
@@ -532,7 +551,8 @@ def full_update_leg(dev, steps, warm, barrier, world, rank):
             "ms_per_update": ms, "call": "goslam_b200.FactorGraph.update(t0=1, t1=8, iters=2) on goslam_b200.DepthVideo",
             "workload": "configs[2]-style front-end update: 8 keyframes, 40x80 @1/8, 36 edges, update operator (random-init "
                         "weights of the reference architecture) + lookup + 2 BA iterations",
-            "update_operator_ms": ms_op,
+            "update_operator_ms": ms_op, "update_operator_torch_cudnn_autocast_ms": ms_op_torch,
+            "update_operator_speedup_vs_cudnn": ms_op_torch / ms_op,
             "conv_gru": {"kernel": "conv_tc_kernel x3 (tcgen05 implicit GEMM, fused gates)", "ms": ms_gru,
                          "tflops": flops / (ms_gru * 1e-3) / 1e12, "frac_of_measured_bf16_burst": flops / (ms_gru * 1e-3) / 1e12 / pk["tf_burst"],
                          "torch_cudnn_autocast_ms": ms_cudnn, "speedup_vs_cudnn": ms_cudnn / ms_gru, "bound": "tensor"}}

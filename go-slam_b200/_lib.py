@@ -37,6 +37,20 @@ class GruWeights(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("w_zr", "w_q", "w_w", "b_zr", "b_q", "b_w", "w_glo", "b_glo")]
 
 
+class UpdateWeights(ctypes.Structure):
+    _fields_ = [("gru", GruWeights)] + [(n, c_void_p) for n in (
+        "corr0_w", "corr0_b", "corr2_w", "corr2_b", "flow0_w", "flow0_b", "flow2_w", "flow2_b", "hid_w", "hid_b",
+        "delta_w", "delta_b", "weight_w", "weight_b", "agg1_w", "agg1_b", "agg2_w", "agg2_b", "eta_w", "eta_b",
+        "upmask_w", "upmask_b")]
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [("inp", c_void_p * 4), ("cin", c_int * 4), ("cin_off", c_int * 4), ("cin_stride", c_int * 4), ("n_in", c_int),
+                ("weight", c_void_p), ("bias", c_void_p), ("taps", c_int), ("cout", c_int), ("cout_pad", c_int), ("act", c_int),
+                ("out_scale", c_float), ("out", c_void_p), ("out_f32", c_int), ("out_stride", c_int), ("out_offset", c_int),
+                ("split", c_int), ("act2", c_int), ("out2", c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/goslam_b200.h declares
 SIGNATURES = {
     "goslam_version": (c_int, []),
@@ -84,6 +98,11 @@ SIGNATURES = {
     "goslam_conv_gru": (c_int, [ctypes.POINTER(GruWeights)] + [c_void_p] * 5 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
     "goslam_nchw_to_nhwc_f16": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
     "goslam_nhwc_to_nchw_f16": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
+    "goslam_nchw_to_nhwc_f16_pad": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    "goslam_conv2d_nhwc": (c_int, [ctypes.POINTER(ConvDesc)] + [c_int] * 3 + [c_void_p]),
+    "goslam_update_op_workspace_bytes": (c_size_t, [c_int] * 4),
+    "goslam_update_op": (c_int, [ctypes.POINTER(UpdateWeights)] + [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 5 +
+                         [c_void_p, c_size_t, c_void_p]),
     "goslam_corr_index_backward": (c_int, []),
     "goslam_altcorr_backward": (c_int, []),
 }

@@ -237,6 +237,14 @@ class FactorGraph:
             eta = 0.2 * self.damping[torch.from_numpy(rows).to(self.device)].contiguous() + EPS
             self.video.ba(tgt, wgt, eta, ii, jj, **kw)
 
+    def _hint_sources(self, ii_host):
+        """tell an update operator that can use it (goslam_b200.UpdateModule) which source-frame slot each edge has —
+        GraphAgg's unique(ii, return_inverse) — from the host mirror instead of a device-side unique + sync"""
+        hint = getattr(self.update_op, "set_source_frames", None)
+        if hint is not None:
+            frames, slot = np.unique(ii_host, return_inverse=True)
+            hint(torch.from_numpy(frames), torch.from_numpy(slot.astype(np.int32)).to(self.device))
+
     def _features(self, ii, jj, target):
         """coords1 [1,N,h,w,2] and the clamped motion features [1,N,4,h,w] in one launch"""
         v = self.video
@@ -247,6 +255,7 @@ class FactorGraph:
         """one update-operator step + dense BA on the graph (src/factor_graph.py:198-252)"""
         coords1, motion = self._features(self.ii, self.jj, self.target)
         corr = self.corr(coords1)
+        self._hint_sources(self._h["ii"])
         with torch.autocast("cuda", enabled=True):
             self.net, delta, weight, damping, upmask = self.update_op(self.net, self.inp, corr, motion, self.ii, self.jj)
         t0, t1 = self._window(t0, t1)
@@ -277,6 +286,7 @@ class FactorGraph:
         for _ in range(steps):
             coords1, motion = self._features(self.ii, self.jj, self.target)
             corr = self.corr(coords1)
+            self._hint_sources(self._h["ii"])
             with torch.autocast("cuda", enabled=True):
                 self.net, delta, weight, damping, upmask = self.update_op(self.net, self.inp, corr, motion, self.ii, self.jj)
             self.target = coords1 + delta.float()
@@ -305,7 +315,7 @@ class FactorGraph:
             pos = np.nonzero((ii_h >= i) & (ii_h < i + 13))[0]
             if pos.size:
                 same = (ii_h[pos] == jj_h[pos]).astype(np.int64)        # stereo pair: the right image's map
-                chunks.append(dict(pos=torch.from_numpy(pos).to(self.device), contiguous=bool(pos[-1] - pos[0] + 1 == pos.size),
+                chunks.append(dict(pos=torch.from_numpy(pos).to(self.device), pos_h=pos, contiguous=bool(pos[-1] - pos[0] + 1 == pos.size),
                                    lo=int(pos[0]), hi=int(pos[-1]) + 1,
                                    f1=torch.from_numpy(rig * ii_h[pos]).to(self.device),
                                    f2=torch.from_numpy(rig * jj_h[pos] + same).to(self.device),
@@ -317,6 +327,7 @@ class FactorGraph:
                 sl = slice(c["lo"], c["hi"]) if c["contiguous"] else c["pos"]
                 iis, jjs = self.ii[sl], self.jj[sl]
                 corr1 = corr_op(coords1[:, sl], c["f1"], c["f2"])
+                self._hint_sources(ii_h[c["pos_h"]])
                 with torch.autocast("cuda", enabled=True):
                     net, delta, weight, damping, upmask = self.update_op(self.net[:, sl], v.inps[None, iis], corr1,
                                                                          motion[:, sl], iis, jjs)

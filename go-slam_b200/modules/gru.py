@@ -100,3 +100,61 @@ class ConvGRU(nn.Module):
             raise RuntimeError("ConvGRU: expected (net[128], inp[128], corr[128], flow[64]) channel layout")
         out = self.forward_nhwc(to_nhwc(net), *[to_nhwc(t) for t in inputs])
         return to_nchw(out).to(net.dtype)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Generic layer entry (goslam_conv2d_nhwc): the encoders, heads and GraphAgg of the update operator
+# ------------------------------------------------------------------------------------------------------
+ACT = {None: 0, "none": 0, "relu": 1, "sigmoid": 2, "softplus": 3}
+
+
+def pack_conv(weights, biases, cin_pad=None, cout_pad=None):
+    """torch conv parameters -> the kernel's layout.  `weights`: list of [co_i, ci, k, k] tensors stacked along cout
+    (k = 1 or 3); returns (w f16 [k*k, cout_pad, cin_pad], b f32 [cout_pad]); padding rows / columns are zero."""
+    w = torch.cat([x.detach() for x in weights], dim=0)
+    b = torch.cat([x.detach() for x in biases], dim=0).float()
+    co, ci, k, _ = w.shape
+    cin_pad = cin_pad or ci
+    cout_pad = cout_pad or ((co + 15) // 16 * 16)
+    out = torch.zeros((k * k, cout_pad, cin_pad), dtype=torch.float16, device=w.device)
+    out[:, :co, :ci] = w.permute(2, 3, 0, 1).reshape(k * k, co, ci).half()
+    bias = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
+    bias[:co] = b
+    return out.contiguous(), bias
+
+
+def conv2d_nhwc(inputs, weight, bias, cout, act=None, out=None, out_f32=False, out_offset=0, out_scale=1.0):
+    """One 1x1 / 3x3 layer on the tcgen05 kernel.  inputs: list of (NHWC f16 tensor, channels used, first channel);
+    weight / bias from `pack_conv`; out: optional NHWC destination (a wider tensor, written at channel out_offset)."""
+    x0 = inputs[0][0]
+    B, h, w, _ = x0.shape
+    taps, cout_pad, cin_total = weight.shape
+    if sum(c for _, c, _ in inputs) != cin_total:
+        raise RuntimeError("conv2d_nhwc: packed weight expects %d input channels" % cin_total)
+    if out is None:
+        out = torch.empty((B, h, w, cout), dtype=torch.float32 if out_f32 else torch.float16, device=x0.device)
+    d = _lib.ConvDesc()
+    for i, (t, c, off) in enumerate(inputs):
+        if t.dtype != torch.float16 or not t.is_contiguous():
+            raise RuntimeError("conv2d_nhwc: inputs must be contiguous NHWC float16")
+        d.inp[i], d.cin[i], d.cin_off[i], d.cin_stride[i] = t.data_ptr(), c, off, t.shape[-1]
+    d.n_in = len(inputs)
+    d.weight, d.bias = weight.data_ptr(), bias.data_ptr()
+    d.taps, d.cout, d.cout_pad, d.act = taps, cout, cout_pad, ACT[act]
+    d.out_scale = float(out_scale)
+    d.out, d.out_f32, d.out_stride, d.out_offset = out.data_ptr(), int(out.dtype == torch.float32), out.shape[-1], out_offset
+    with torch.cuda.device(x0.device):
+        rc = _lib.load().goslam_conv2d_nhwc(ctypes.byref(d), B, h, w, _lib.stream_ptr())
+    _lib.check(rc, "conv2d_nhwc")
+    return out
+
+
+def to_nhwc_padded(x, cpad):
+    """[B, C, h, w] -> [B, h, w, cpad] float16 with zero channels C..cpad-1 (one kernel)"""
+    b, c, h, w = x.shape
+    src = x.contiguous() if x.dtype == torch.float16 else x.half().contiguous()
+    dst = torch.empty((b, h, w, cpad), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().goslam_nchw_to_nhwc_f16_pad(_lib.ptr(src), _lib.ptr(dst), b, c, cpad, h * w, _lib.stream_ptr())
+    _lib.check(rc, "nchw_to_nhwc_pad")
+    return dst

@@ -333,7 +333,59 @@ int goslam_conv_gru(const goslam_gru_weights* weights, const void* net, const vo
                     const void* flow, void* net_out, int B, int h, int w, void* workspace,
                     size_t workspace_bytes, void* stream);
 int goslam_nchw_to_nhwc_f16(const void* src, void* dst, int B, int C, int hw, void* stream);
+/* same with the channel dimension zero-padded to Cpad (e.g. the 196 correlation channels -> 256) */
+int goslam_nchw_to_nhwc_f16_pad(const void* src, void* dst, int B, int C, int Cpad, int hw, void* stream);
+
+/* One convolution layer of the update operator (src/droid_net.py:70-105: the encoders, the delta / weight heads and
+ * GraphAgg) on the same tcgen05 implicit-GEMM kernel: 1x1 or 3x3 (padding 1), up to four NHWC f16 inputs read as if
+ * concatenated along channels (each may be a channel slice of a wider tensor), fused bias + activation.
+ *   in[i]: [B,h,w,cin_stride[i]] f16, channels cin_off[i] .. cin_off[i]+cin[i] used (all multiples of 64)
+ *   weight f16 [taps][cout_pad][sum cin] (tap = 3*ky + kx), bias f32 [cout_pad]; cout_pad multiple of 16 (rows
+ *   cout..cout_pad-1 zero) and <= 256 or a multiple of 128 / 192 / 256
+ *   act: 0 none, 1 ReLU, 2 sigmoid, 3 softplus; result * out_scale
+ *   out: NHWC [B,h,w,out_stride] f16 (out_f32 = 0; stride and offset multiples of 8) or f32, channels
+ *   out_offset .. out_offset + cout written. */
+typedef struct goslam_conv_desc {
+  const void* in[4]; int cin[4]; int cin_off[4]; int cin_stride[4]; int n_in;
+  const void* weight; const float* bias;
+  int taps, cout, cout_pad, act;
+  float out_scale;
+  void* out; int out_f32, out_stride, out_offset;
+  /* optional (f32 outputs, cout <= 8): channels >= split are written to out2 (same stride) as channel - split and
+   * get activation act2 instead of act — two small heads in one pass over block-diagonal weights */
+  int split, act2; void* out2;
+} goslam_conv_desc;
+int goslam_conv2d_nhwc(const goslam_conv_desc* d, int B, int h, int w, void* stream);
 int goslam_nhwc_to_nchw_f16(const void* src, void* dst, int B, int C, int hw, void* stream);
+
+/* The whole update operator in one call — UpdateModule.forward (src/droid_net.py:107-140): layout conversion of the
+ * reference-shaped inputs, corr / flow encoders, ConvGRU, delta / weight heads and GraphAgg; ~20 launches issued by
+ * the library on `stream`, no host synchronisation.
+ *   net, inp f16 [N,128,h,w]; corr f16 [N,196,h,w] (CorrBlock.__call__'s output); flow f32 [N,4,h,w] (the motion
+ *   features); frame_slot int32 [N]: index of each edge's source frame among the M distinct source frames in sorted
+ *   order (GraphAgg's unique(ii, return_inverse)), or NULL to skip GraphAgg (ii is None in the reference).
+ *   Outputs: net_out f16 [N,128,h,w]; delta, weight f32 [N,h,w,2]; eta f32 [M,h,w] (already times 0.01);
+ *   upmask f16 [M,576,h,w].
+ *   Weights (device pointers, packed like goslam_conv_desc.weight; "pad 16" = cout rows 2.. / 1.. are zero):
+ *     corr0 [1][128][256] (cin 196 zero-padded), corr2 [9][128][128], flow0 f16 [128][256] with k = (ky*7+kx)*4+ci
+ *     (zero beyond 196), flow2 [9][64][128], hid [9][256][128] = delta.0 | weight.0,
+ *     delta_w = both 2-channel heads block-diagonal [9][16][256]: rows 0-1 delta.2 on hidden channels 0..127, rows 2-3
+ *     weight.2 on 128..255, bias [16] likewise (weight_w / weight_b unused),
+ *     agg1, agg2 [9][128][128], eta [9][16][128] (pad 16), upmask [1][576][128]; biases f32 [cout_pad]. */
+typedef struct goslam_update_weights {
+  goslam_gru_weights gru;
+  const void* corr0_w; const float* corr0_b; const void* corr2_w; const float* corr2_b;
+  const void* flow0_w; const float* flow0_b; const void* flow2_w; const float* flow2_b;
+  const void* hid_w; const float* hid_b; const void* delta_w; const float* delta_b;
+  const void* weight_w; const float* weight_b;
+  const void* agg1_w; const float* agg1_b; const void* agg2_w; const float* agg2_b;
+  const void* eta_w; const float* eta_b; const void* upmask_w; const float* upmask_b;
+} goslam_update_weights;
+size_t goslam_update_op_workspace_bytes(int N, int M, int h, int w);
+int goslam_update_op(const goslam_update_weights* weights, const void* net, const void* inp, const void* corr,
+                     const float* flow, const int* frame_slot, int N, int M, int h, int w, void* net_out,
+                     float* delta, float* weight, float* eta, void* upmask, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* Training-only entry points of the reference module are exported for ABI completeness
  * and return GOSLAM_EUNSUPPORTED (inference path is torch.no_grad, src/slam.py:45). */

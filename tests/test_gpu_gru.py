@@ -75,11 +75,16 @@ def test_conv_gru_shapes_vs_torch(shape):
 
 
 def test_layout_helpers_round_trip():
-    from goslam_b200.modules.gru import to_nchw, to_nhwc
-    x = torch.randn(3, 70, 11, 13, device=dev()).half()
-    y = to_nhwc(x)
-    assert y.shape == (3, 11, 13, 70) and torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
-    assert torch.equal(to_nchw(y), x)
+    from goslam_b200.modules.gru import to_nchw, to_nhwc, to_nhwc_padded
+    for shape in [(3, 70, 11, 13), (5, 128, 40, 80), (2, 576, 30, 40), (2, 64, 12, 20), (3, 128, 9, 16)]:   # generic + 64x64-tile paths
+        x = torch.randn(*shape, device=dev()).half()
+        y = to_nhwc(x)
+        assert y.shape == (shape[0], shape[2], shape[3], shape[1]) and torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
+        assert torch.equal(to_nchw(y), x)
+    for shape, cpad in [((4, 196, 40, 80), 256), ((2, 196, 30, 40), 256), ((2, 5, 7, 9), 16)]:
+        x = torch.randn(*shape, device=dev()).half()
+        y = to_nhwc_padded(x, cpad)
+        assert torch.equal(y[..., :shape[1]], x.permute(0, 2, 3, 1)) and float(y[..., shape[1]:].abs().max()) == 0.0
 
 
 def test_update_module_vs_reference_golden():
