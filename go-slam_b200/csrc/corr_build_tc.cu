@@ -530,6 +530,302 @@ corr_build_tc_kernel(const __grid_constant__ CUtensorMap mapA,
   if (warp == 1) tmem_dealloc(tmem_base, kTStages * kBN);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Staged variant (tiled slot-pool layout, w <= 80): the write stream is DECOUPLED from the TMEM drain.
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2..9 drain warps (stage = (warp-2)/4, TMEM lane quadrant = warp%4):
+//   tcgen05.ld, fp16 conversion, pyramid pooling; they only write SHARED memory (a level-0 slot per TMEM stage, the band
+//   pool for levels 1-3) | warps 10..13 store warps: thread = source pixel, they move the staged level-0 tiles (two
+//   128-byte runs per tile) and, at the end of a band, the pooled pieces to global memory as whole 32-byte sectors.
+// Why: tools/wbench.cu (profiles/r02_wbench_v2.txt) — this very store pattern streams at 6.19 TB/s from 128 threads per
+// SM but at 4.92 TB/s from 512, and the direct-store kernel, whose 512 epilogue threads also sit in the store queue
+// instead of draining accumulators, ends at (no-write floor 116 µs) + (pure-store time 150 µs) = 283 µs.
+// 448 threads: no register cap below the direct-store kernel's 90.
+// ------------------------------------------------------------------------------------------------------
+#ifndef GOSLAM_ST_EXP
+#define GOSLAM_ST_EXP 0          // A/B builds only (tools/build_variant.py): 1 no global stores, 2 no pooling, 4 no level-0 staging
+#endif
+constexpr int kDrainWarps = 8, kStoreWarps = 4;
+constexpr int kThreadsST = 64 + (kDrainWarps + kStoreWarps) * 32;      // 448
+constexpr int kStageRow = 2 * 128 + 16;                                // staged level-0 bytes per source pixel and tile
+constexpr int kStageBytes = kBM * kStageRow;                           // 34,816 B per slot (one slot per TMEM stage)
+inline int pool_bytes_st(int n_xb) { return kBM * ((4 * n_xb * 16 + 16) + (((n_xb * 16 + 31) / 32 * 32) + 8)); }
+inline int smem_staged(int n_xb) { return 1024 + (1 + kBStages) * kTileBytes + pool_bytes_st(n_xb) + kTStages * kStageBytes + 256; }
+
+__global__ void __launch_bounds__(kThreadsST, 1)
+corr_build_tc_staged_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                            const TcParams p, const int pool_bytes) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base =
+      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smA = base;                                   // ONE A stage (reloaded once per 8-row band item)
+  unsigned char* smB = base + kTileBytes;
+  unsigned char* smPool = base + (1 + kBStages) * kTileBytes;
+  unsigned char* smStage = smPool + pool_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smStage + kTStages * kStageBytes);
+  uint64_t* full_a = bars;
+  uint64_t* empty_a = bars + 1;
+  uint64_t* full_b = bars + 2;          // [kBStages]
+  uint64_t* empty_b = full_b + kBStages;
+  uint64_t* tm_full = empty_b + kBStages;
+  uint64_t* tm_empty = tm_full + kTStages;
+  uint64_t* st_full = tm_empty + kTStages;      // slot written by its 4 drain warps
+  uint64_t* st_empty = st_full + kTStages;      // slot moved out by the 4 store warps
+  uint64_t* band_full = st_empty + kTStages;    // pooled pieces of a band complete (8 drain warps)
+  uint64_t* band_empty = band_full + 1;         // pool may be overwritten (4 store warps)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(band_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(full_a, 1); mbar_init(empty_a, 1);
+    for (int i = 0; i < kBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < kTStages; ++i) {
+      mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 4);
+      mbar_init(&st_full[i], 4); mbar_init(&st_empty[i], kStoreWarps);
+    }
+    mbar_init(band_full, kDrainWarps); mbar_init(band_empty, kStoreWarps);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTStages * kBN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int p1row = p.n_xb * 16, p1src = 4 * p1row + 16;
+  const int p2row = p.n_xb * 8, p2src = p.pitch2 + 8;
+  unsigned char* pool1 = smPool;
+  unsigned char* pool2 = smPool + kBM * p1src;
+  const int h2 = p.h >> 2, h3 = p.h >> 3;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int aph = 0, bs = 0, bph = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int yb = item % p.n_yb;
+        const int mt = (item / p.n_yb) % p.n_mt;
+        const int n = item / (p.n_yb * p.n_mt);
+        int n1 = n, n2 = n;
+        if (p.ii != nullptr) {
+          const int fi = (int)p.ii[n], fj = (int)p.jj[n];
+          n1 = p.rig * fi;
+          n2 = p.rig * fj + ((fi == fj && p.rig > 1) ? 1 : 0);
+        }
+        mbar_wait(empty_a, aph ^ 1);
+        mbar_expect_tx(full_a, kTileBytes);
+        tma_load_3d(&mapA, full_a, smA, 0, mt * kBM, n1);
+        tma_load_3d(&mapA, full_a, smA + kBoxBytes, kKBox, mt * kBM, n1);
+        aph ^= 1;
+        for (int xb = 0; xb < p.n_xb; ++xb) {
+          mbar_wait(&empty_b[bs], bph ^ 1);
+          mbar_expect_tx(&full_b[bs], kTileBytes);
+          tma_load_4d(&mapB, &full_b[bs], smB + bs * kTileBytes, 0, xb * kPX, yb * kPY, n2);
+          tma_load_4d(&mapB, &full_b[bs], smB + bs * kTileBytes + kBoxBytes, kKBox, xb * kPX, yb * kPY, n2);
+          if (++bs == kBStages) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int aph = 0, bs = 0, bph = 0, ts = 0, tph = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        mbar_wait(full_a, aph);
+        const uint32_t a_addr = smem_u32(smA);
+        for (int xb = 0; xb < p.n_xb; ++xb) {
+          mbar_wait(&tm_empty[ts], tph ^ 1);
+          mbar_wait(&full_b[bs], bph);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(smB + bs * kTileBytes);
+          const uint32_t d_tmem = tmem_base + ts * kBN;
+#pragma unroll
+          for (int kb = 0; kb < kD / kKBox; ++kb)
+#pragma unroll
+            for (int k = 0; k < kKBox / 16; ++k)
+              umma_f16(d_tmem, make_desc_sw128(a_addr + kb * kBoxBytes + k * 32), make_desc_sw128(b_addr + kb * kBoxBytes + k * 32),
+                       kIdesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_b[bs]);
+          umma_commit(&tm_full[ts]);
+          if (++bs == kBStages) { bs = 0; bph ^= 1; }
+          if (++ts == kTStages) { ts = 0; tph ^= 1; }
+        }
+        umma_commit(empty_a);
+        aph ^= 1;
+      }
+    }
+  } else if (warp < 2 + kDrainWarps) {
+    // ===================== drain warps =====================
+    const int ts = (warp - 2) >> 2;               // TMEM stage = staging slot of this warp
+    const int quad = warp & 3;                    // TMEM lane quadrant a warp may read = warp_id % 4
+    const int row = quad * 32 + lane;             // source pixel of the tile
+    unsigned char* slot = smStage + ts * kStageBytes + row * kStageRow;
+    int tph = 0, sph = 0, tile = 0, band = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++band) {
+      bool pool_ok = false;                       // the store warps have finished the previous band's write-out
+      for (int xb = 0; xb < p.n_xb; ++xb, ++tile) {
+        if ((tile & (kTStages - 1)) != ts) continue;
+        mbar_wait(&tm_full[ts], tph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ts * kBN + ((uint32_t)(quad * 32) << 16);
+        mbar_wait(&st_empty[ts], sph ^ 1);        // slot free (first use passes)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t hr[4][8];
+          {
+            uint32_t va[32], vb[32];
+            tmem_ld32_issue(taddr + (2 * half) * 32, va);
+            tmem_ld32_issue(taddr + (2 * half + 1) * 32, vb);
+            tmem_ld_wait();
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int x = 0; x < 8; ++x) {
+                hr[r][x] = pack2(__uint_as_float(va[r * 16 + 2 * x]), __uint_as_float(va[r * 16 + 2 * x + 1]));
+                hr[2 + r][x] = pack2(__uint_as_float(vb[r * 16 + 2 * x]), __uint_as_float(vb[r * 16 + 2 * x + 1]));
+              }
+          }
+          if (half == 1) {                         // both halves of the accumulator are in registers / staged
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tm_empty[ts]);
+          }
+          // level 0: the thread's 4 patch rows x 16 columns = four adjacent 4x4 tiles = one 128-byte run
+          unsigned char* sp = slot + half * 128;
+#pragma unroll
+          for (int t = 0; t < 4 && !(GOSLAM_ST_EXP & 4); ++t) {
+            *reinterpret_cast<uint4*>(sp + t * 32) = make_uint4(hr[0][2 * t], hr[0][2 * t + 1], hr[1][2 * t], hr[1][2 * t + 1]);
+            *reinterpret_cast<uint4*>(sp + t * 32 + 16) = make_uint4(hr[2][2 * t], hr[2][2 * t + 1], hr[3][2 * t], hr[3][2 * t + 1]);
+          }
+          // pooled levels go to the band pool: wait (once per band) until its previous content has left
+          if (!pool_ok) { mbar_wait(band_empty, (band & 1) ^ 1); pool_ok = true; }
+          if (GOSLAM_ST_EXP & 2) { if (hr[0][0] == 0x12345678u) *reinterpret_cast<uint32_t*>(pool2 + row * p2src) = hr[3][7] ^ hr[1][2]; continue; }
+          uint32_t l1[2][4];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              l1[cc][j] = pack2(pool_pair(hr[2 * cc][2 * j], hr[2 * cc + 1][2 * j]),
+                                pool_pair(hr[2 * cc][2 * j + 1], hr[2 * cc + 1][2 * j + 1]));
+            unsigned char* st = pool1 + row * p1src + (2 * half + cc) * 8;
+            *reinterpret_cast<uint2*>(st + (xb * 2) * 32) = make_uint2(l1[cc][0], l1[cc][1]);
+            *reinterpret_cast<uint2*>(st + (xb * 2 + 1) * 32) = make_uint2(l1[cc][2], l1[cc][3]);
+          }
+          const uint32_t a0 = pack2(pool_pair(l1[0][0], l1[1][0]), pool_pair(l1[0][1], l1[1][1]));
+          const uint32_t a1 = pack2(pool_pair(l1[0][2], l1[1][2]), pool_pair(l1[0][3], l1[1][3]));
+          *reinterpret_cast<uint2*>(pool2 + row * p2src + half * p2row + xb * 8) = make_uint2(a0, a1);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_full[ts]);
+        tph ^= 1; sph ^= 1;
+      }
+      if (!pool_ok) mbar_wait(band_empty, (band & 1) ^ 1);     // (a group without a tile in this band)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(band_full);       // this warp's part of the band pool is complete
+    }
+  } else {
+    // ===================== store warps =====================
+    // One STG.256 instruction = 8 source pixels x one whole 128-byte run (lane -> pixel lane/4, 32-byte piece lane%4):
+    // 8 LSU wavefronts of 128 B instead of the 32 wavefronts of 32 B a thread-per-pixel mapping costs.  (ncu, round 2:
+    // l1tex__data_pipe_lsu_wavefronts was the top unit at 77-80 %.)
+    const int row = threadIdx.x - (64 + kDrainWarps * 32);       // 0..127
+    const int swarp = row >> 5;
+    const int sub = lane >> 2, piece = lane & 3;
+    int tile = 0, band = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++band) {
+      const int yb = item % p.n_yb;
+      const int mt = (item / p.n_yb) % p.n_mt;
+      const int n = item / (p.n_yb * p.n_mt);
+      const int n_out = p.out_slot ? __ldg(p.out_slot + n) : n;
+      const long long pl0 = (long long)n_out * p.hw + mt * kBM;       // plane of the tile's first source pixel
+      const int n_src = min(kBM, p.hw - mt * kBM);                    // valid source pixels of this tile
+      for (int xb = 0; xb < p.n_xb; ++xb, ++tile) {
+        const int s_ = tile & (kTStages - 1);
+        mbar_wait(&st_full[s_], (tile / kTStages) & 1);
+        const bool col_ok = xb * 4 + piece < p.w4_0;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int ty = 2 * yb + hf;
+          uint4 va[4], vb[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const unsigned char* sp = smStage + s_ * kStageBytes + (swarp * 32 + g * 8 + sub) * kStageRow + hf * 128 + piece * 32;
+            va[g] = *reinterpret_cast<const uint4*>(sp);
+            vb[g] = *reinterpret_cast<const uint4*>(sp + 16);
+          }
+          if (ty < p.h4_0 && col_ok && !(GOSLAM_ST_EXP & 1)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int sr = swarp * 32 + g * 8 + sub;
+              if (sr < n_src) {
+                unsigned char* dst = reinterpret_cast<unsigned char*>(p.lvl[0]) +
+                                     (((pl0 + sr) * p.h4_0 + ty) * p.w4_0 + xb * 4 + piece) * 32LL;
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(va[g].x), "r"(va[g].y),
+                             "r"(va[g].z), "r"(va[g].w), "r"(vb[g].x), "r"(vb[g].y), "r"(vb[g].z), "r"(vb[g].w) : "memory");
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_empty[s_]);
+      }
+      // ---- band write-out: levels 1-3, staged byte-for-byte as they go to memory; consecutive lanes take consecutive
+      // 32-byte sectors of one source pixel's piece, so a wavefront carries up to 128 B here too
+      mbar_wait(band_full, band & 1);
+      if (p.num_levels > 1 && !(GOSLAM_ST_EXP & 1)) {
+        if (yb < p.h4_1) {
+          for (int idx = row; idx < n_src * p.w4_1; idx += kStoreWarps * 32) {
+            const int sr = idx / p.w4_1, sec = idx - sr * p.w4_1;
+            const unsigned char* sp1 = pool1 + sr * p1src + sec * 32;
+            const uint4 a = *reinterpret_cast<const uint4*>(sp1), b = *reinterpret_cast<const uint4*>(sp1 + 16);
+            unsigned char* g1 = reinterpret_cast<unsigned char*>(p.lvl[1]) + (((pl0 + sr) * p.h4_1 + yb) * p.w4_1 + sec) * 32LL;
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(g1), "r"(a.x), "r"(a.y), "r"(a.z),
+                         "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+          }
+        }
+        if (p.num_levels > 2 && 2 * yb < h2) {
+          const int spp = p.pitch2 >> 5;                       // sectors per (source pixel, band) piece
+          for (int idx = row; idx < n_src * spp; idx += kStoreWarps * 32) {
+            const int sr = idx / spp, sec = idx - sr * spp;
+            const unsigned char* sp2 = pool2 + sr * p2src + sec * 32;
+            uint32_t rr[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint2 t = *reinterpret_cast<const uint2*>(sp2 + 8 * k);
+              rr[2 * k] = t.x; rr[2 * k + 1] = t.y;
+            }
+            unsigned char* g2 = reinterpret_cast<unsigned char*>(p.lvl[2]) + ((pl0 + sr) * p.n_yb + yb) * (long long)p.pitch2 + sec * 32;
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(g2), "r"(rr[0]), "r"(rr[1]), "r"(rr[2]),
+                         "r"(rr[3]), "r"(rr[4]), "r"(rr[5]), "r"(rr[6]), "r"(rr[7]) : "memory");
+          }
+        }
+        if (p.num_levels > 3 && yb < h3 && row < n_src) {
+          const unsigned char* sp2 = pool2 + row * p2src;
+          uint32_t rr[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {                    // level-3 columns 2k, 2k+1 of this band's row
+            rr[k] = 0u;
+            if (k < p.n_xb) {
+              const uint32_t t = *reinterpret_cast<const uint32_t*>(sp2 + 8 * k);
+              const uint32_t t2 = *reinterpret_cast<const uint32_t*>(sp2 + 8 * k + 4);
+              const uint32_t b = *reinterpret_cast<const uint32_t*>(sp2 + p2row + 8 * k);
+              const uint32_t b2 = *reinterpret_cast<const uint32_t*>(sp2 + p2row + 8 * k + 4);
+              rr[k] = pack2(pool_pair(t, b), pool_pair(t2, b2));
+            }
+          }
+          unsigned char* g3 = reinterpret_cast<unsigned char*>(p.lvl[3]) + ((pl0 + row) * p.n_yb + yb) * 32LL;
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(g3), "r"(rr[0]), "r"(rr[1]), "r"(rr[2]),
+                       "r"(rr[3]), "r"(rr[4]), "r"(rr[5]), "r"(rr[6]), "r"(rr[7]) : "memory");
+        }
+      }
+      // the pool is read by all four store warps: hand it back only when every one of them is done with it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(band_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTStages * kBN);
+}
+
 // [F, D, hw] (channel-major) -> [F, hw, D] (K-major), D = 128, times 1/4 in half — the reference's
 // `fmap / 4.0` on the half tensor (src/modules/corr.py:71-72): exact for normal values.
 __global__ void __launch_bounds__(256)
@@ -596,6 +892,10 @@ EncodeTiledFn get_encode_fn() {
 #ifndef GOSLAM_TC_PINGPONG
 #define GOSLAM_TC_PINGPONG 0
 #endif
+#ifndef GOSLAM_TC_STAGED
+#define GOSLAM_TC_STAGED 1       // -DGOSLAM_TC_STAGED=0: always the direct-store kernel (A/B builds)
+#endif
+constexpr int kSmemStagedMax = 227 * 1024 - 1024;
 
 // Tensor maps depend only on (base pointer, frame count, h, w): a factor graph builds from the same
 // video-level K-major buffer for its whole life, so the two cuTensorMapEncodeTiled driver calls per launch
@@ -687,7 +987,9 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
     std::lock_guard<std::mutex> lock(dev_mu);
     if (sm_count[dev] == 0) {
       if (cudaFuncSetAttribute(corr_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               kSmemTC) != cudaSuccess)
+                               kSmemTC) != cudaSuccess ||
+          cudaFuncSetAttribute(corr_build_tc_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kSmemStagedMax) != cudaSuccess)
         return GOSLAM_ELAUNCH;
       int n = 148;
       cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -696,6 +998,12 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
     sms = sm_count[dev];
   }
   const int grid = p.n_items < sms ? p.n_items : sms;
+  if (p.tiled && !p.bulk && !p.pingpong && p.experiment != 1 && GOSLAM_TC_STAGED && p.num_levels == 4 &&
+      smem_staged(p.n_xb) <= kSmemStagedMax) {
+    corr_build_tc_staged_kernel<<<grid, kThreadsST, smem_staged(p.n_xb), st>>>(mapA, mapB, p, pool_bytes_st(p.n_xb));
+    GS_CHECK_LAUNCH();
+    return GOSLAM_OK;
+  }
   corr_build_tc_kernel<<<grid, kThreadsTC, kSmemTC, st>>>(mapA, mapB, p);
   GS_CHECK_LAUNCH();
   return GOSLAM_OK;

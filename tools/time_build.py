@@ -4,6 +4,9 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
+if os.environ.get("TOOL_VARIANT"):            # an A/B build made by tools/build_variant.py
+    from tools.build_variant import use_variant
+    use_variant(os.environ["TOOL_VARIANT"])
 from goslam_b200.modules import CorrBlock
 from goslam_b200.modules.corr import CorrPool, fmaps_to_kmajor
 dev = torch.device("cuda:0")
@@ -13,7 +16,7 @@ fm = torch.randn(16, 1, 128, h, w, generator=g).half().to(dev)
 km = fmaps_to_kmajor(fm)
 layouts = [sys.argv[3]] if len(sys.argv) > 3 else ["rowmajor", "tiled"]
 for layout in layouts:
-    for N in (2, 36, 72):
+    for N in ((36,) if os.environ.get("TOOL_VARIANT") else (2, 36, 72)):
         ii = torch.arange(N, device=dev) % 16
         jj = (torch.arange(N, device=dev) * 7 + 3) % 16
         pool = CorrPool(N, h, w, device=dev, layout=layout)
