@@ -551,9 +551,13 @@ constexpr int kStageBytes = kBM * kStageRow;                           // 34,816
 inline int pool_bytes_st(int n_xb) { return kBM * ((4 * n_xb * 16 + 16) + (((n_xb * 16 + 31) / 32 * 32) + 8)); }
 inline int smem_staged(int n_xb) { return 1024 + (1 + kBStages) * kTileBytes + pool_bytes_st(n_xb) + kTStages * kStageBytes + 256; }
 
+// TMA_ST: level 0 leaves the slot as two tensor-map stores per tile (box = 128 source pixels x one 128-byte run, 128-byte
+// swizzle in shared memory) issued by one drain thread; no thread touches the load/store unit for it and the slot is free
+// again as soon as the copy engine has READ it.  The store warps then only write the pooled levels at the end of a band.
+template <int MODE>          // 0: store warps, 1: tensor-map stores, 2: TMEM stage 0 by tensor-map stores, stage 1 by the store warps
 __global__ void __launch_bounds__(kThreadsST, 1)
 corr_build_tc_staged_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                            const TcParams p, const int pool_bytes) {
+                            const __grid_constant__ CUtensorMap mapO, const TcParams p, const int pool_bytes) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -657,6 +661,7 @@ corr_build_tc_staged_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
     const int ts = (warp - 2) >> 2;               // TMEM stage = staging slot of this warp
     const int quad = warp & 3;                    // TMEM lane quadrant a warp may read = warp_id % 4
     const int row = quad * 32 + lane;             // source pixel of the tile
+    const bool TMA_ST = MODE == 1 || (MODE == 2 && ts == 0);
     unsigned char* slot = smStage + ts * kStageBytes + row * kStageRow;
     int tph = 0, sph = 0, tile = 0, band = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++band) {
@@ -666,7 +671,12 @@ corr_build_tc_staged_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
         mbar_wait(&tm_full[ts], tph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ts * kBN + ((uint32_t)(quad * 32) << 16);
-        mbar_wait(&st_empty[ts], sph ^ 1);        // slot free (first use passes)
+        if (TMA_ST) {
+          if (quad == 0 && lane == 0) bulk_wait_read();         // the copy engine has read this slot's previous tile
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + ts) : "memory");
+        } else {
+          mbar_wait(&st_empty[ts], sph ^ 1);      // slot free (first use passes)
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t hr[4][8];
@@ -689,11 +699,23 @@ corr_build_tc_staged_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
             if (lane == 0) mbar_arrive(&tm_empty[ts]);
           }
           // level 0: the thread's 4 patch rows x 16 columns = four adjacent 4x4 tiles = one 128-byte run
+          if (TMA_ST) {
+            // dense [128 pixels][128 B] box per half, 16-byte chunk c of row r at chunk c ^ (r & 7) (SWIZZLE_128B)
+            unsigned char* sp = smStage + ts * kStageBytes + half * (kBM * 128) + row * 128;
+#pragma unroll
+            for (int t = 0; t < 4 && !(GOSLAM_ST_EXP & 4); ++t) {
+              *reinterpret_cast<uint4*>(sp + (((2 * t) ^ (row & 7)) << 4)) =
+                  make_uint4(hr[0][2 * t], hr[0][2 * t + 1], hr[1][2 * t], hr[1][2 * t + 1]);
+              *reinterpret_cast<uint4*>(sp + (((2 * t + 1) ^ (row & 7)) << 4)) =
+                  make_uint4(hr[2][2 * t], hr[2][2 * t + 1], hr[3][2 * t], hr[3][2 * t + 1]);
+            }
+          } else {
           unsigned char* sp = slot + half * 128;
 #pragma unroll
           for (int t = 0; t < 4 && !(GOSLAM_ST_EXP & 4); ++t) {
             *reinterpret_cast<uint4*>(sp + t * 32) = make_uint4(hr[0][2 * t], hr[0][2 * t + 1], hr[1][2 * t], hr[1][2 * t + 1]);
             *reinterpret_cast<uint4*>(sp + t * 32 + 16) = make_uint4(hr[2][2 * t], hr[2][2 * t + 1], hr[3][2 * t], hr[3][2 * t + 1]);
+          }
           }
           // pooled levels go to the band pool: wait (once per band) until its previous content has left
           if (!pool_ok) { mbar_wait(band_empty, (band & 1) ^ 1); pool_ok = true; }
@@ -713,14 +735,30 @@ corr_build_tc_staged_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
           const uint32_t a1 = pack2(pool_pair(l1[0][2], l1[1][2]), pool_pair(l1[0][3], l1[1][3]));
           *reinterpret_cast<uint2*>(pool2 + row * p2src + half * p2row + xb * 8) = make_uint2(a0, a1);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&st_full[ts]);
+        if (TMA_ST) {
+          fence_async_smem();                      // this thread's staged bytes become visible to the copy engine
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + ts) : "memory");
+          if (quad == 0 && lane == 0 && !(GOSLAM_ST_EXP & 1)) {
+            const int yb = item % p.n_yb;
+            const int mt = (item / p.n_yb) % p.n_mt;
+            const int n = item / (p.n_yb * p.n_mt);
+            const int n_out = p.out_slot ? __ldg(p.out_slot + n) : n;
+            const unsigned char* sl = smStage + ts * kStageBytes;
+            tma_store_4d(&mapO, sl, xb * 64, 2 * yb, mt * kBM, n_out);                 // rows past h4_0 / pixels past hw
+            tma_store_4d(&mapO, sl + kBM * 128, xb * 64, 2 * yb + 1, mt * kBM, n_out);   // are clipped by the map
+            bulk_commit();
+          }
+        } else {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st_full[ts]);
+        }
         tph ^= 1; sph ^= 1;
       }
       if (!pool_ok) mbar_wait(band_empty, (band & 1) ^ 1);     // (a group without a tile in this band)
       __syncwarp();
       if (lane == 0) mbar_arrive(band_full);       // this warp's part of the band pool is complete
     }
+    if (TMA_ST && quad == 0 && lane == 0) bulk_wait_read();     // shared memory must outlive the last copies
   } else {
     // ===================== store warps =====================
     // One STG.256 instruction = 8 source pixels x one whole 128-byte run (lane -> pixel lane/4, 32-byte piece lane%4):
@@ -737,8 +775,9 @@ corr_build_tc_staged_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
       const int n_out = p.out_slot ? __ldg(p.out_slot + n) : n;
       const long long pl0 = (long long)n_out * p.hw + mt * kBM;       // plane of the tile's first source pixel
       const int n_src = min(kBM, p.hw - mt * kBM);                    // valid source pixels of this tile
-      for (int xb = 0; xb < p.n_xb; ++xb, ++tile) {
+      for (int xb = 0; xb < (MODE == 1 ? 0 : p.n_xb); ++xb, ++tile) {
         const int s_ = tile & (kTStages - 1);
+        if (MODE == 2 && s_ == 0) continue;        // that tile leaves through the copy engine
         mbar_wait(&st_full[s_], (tile / kTStages) & 1);
         const bool col_ok = xb * 4 + piece < p.w4_0;
 #pragma unroll
@@ -895,7 +934,11 @@ EncodeTiledFn get_encode_fn() {
 #ifndef GOSLAM_TC_STAGED
 #define GOSLAM_TC_STAGED 1       // -DGOSLAM_TC_STAGED=0: always the direct-store kernel (A/B builds)
 #endif
+#ifndef GOSLAM_TC_TMASTORE
+#define GOSLAM_TC_TMASTORE 0     // A/B builds: 1 = level 0 by tensor-map stores, 2 = half of the tiles (see the kernel)
+#endif
 constexpr int kSmemStagedMax = 227 * 1024 - 1024;
+constexpr int kMaxSlots = 1 << 16;   // slot extent of the output tensor map (a bound for clipping only: slots come from out_slot)
 
 // Tensor maps depend only on (base pointer, frame count, h, w): a factor graph builds from the same
 // video-level K-major buffer for its whole life, so the two cuTensorMapEncodeTiled driver calls per launch
@@ -913,6 +956,18 @@ bool encode_map(EncodeTiledFn enc, const MapKey& k, CUtensorMap* out) {
     cuuint32_t es[3] = {1, 1, 1};
     return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(k.base), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  if (k.kind == 2) {
+    // level 0 of the tiled slot pool, [slot, pixel, h/4, w/4, 16] halves, as (64-half run, tile row, pixel, slot): a box
+    // is one MMA tile's 128-byte run for 128 source pixels.  k.F = number of slots addressable through the map.
+    const cuuint64_t w4 = (cuuint64_t)gs_cdiv(k.w, 4), h4 = (cuuint64_t)gs_cdiv(k.h, 4);
+    cuuint64_t dims[4] = {w4 * 16, h4, hw, (cuuint64_t)k.F};
+    cuuint64_t strides[3] = {w4 * 32, h4 * w4 * 32, hw * h4 * w4 * 32};
+    cuuint32_t box[4] = {64, 1, (cuuint32_t)kBM, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(k.base), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   }
   // B: (ch, x, y, frame), box 64 ch x 16 x 8: an image patch; rows / columns outside the image read as zero
@@ -988,7 +1043,9 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
     if (sm_count[dev] == 0) {
       if (cudaFuncSetAttribute(corr_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                kSmemTC) != cudaSuccess ||
-          cudaFuncSetAttribute(corr_build_tc_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          cudaFuncSetAttribute(corr_build_tc_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kSmemStagedMax) != cudaSuccess ||
+          cudaFuncSetAttribute(corr_build_tc_staged_kernel<GOSLAM_TC_TMASTORE ? GOSLAM_TC_TMASTORE : 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                kSmemStagedMax) != cudaSuccess)
         return GOSLAM_ELAUNCH;
       int n = 148;
@@ -1000,7 +1057,12 @@ int launch_tc(const __half* f1t, int F1, const __half* f2t, int F2, const int64_
   const int grid = p.n_items < sms ? p.n_items : sms;
   if (p.tiled && !p.bulk && !p.pingpong && p.experiment != 1 && GOSLAM_TC_STAGED && p.num_levels == 4 &&
       smem_staged(p.n_xb) <= kSmemStagedMax) {
-    corr_build_tc_staged_kernel<<<grid, kThreadsST, smem_staged(p.n_xb), st>>>(mapA, mapB, p, pool_bytes_st(p.n_xb));
+    CUtensorMap mapO;
+    if (GOSLAM_TC_TMASTORE && cached_map(enc, MapKey{levels[0], kMaxSlots, h, w, 2}, &mapO)) {
+      corr_build_tc_staged_kernel<GOSLAM_TC_TMASTORE><<<grid, kThreadsST, smem_staged(p.n_xb), st>>>(mapA, mapB, mapO, p, pool_bytes_st(p.n_xb));
+    } else {
+      corr_build_tc_staged_kernel<0><<<grid, kThreadsST, smem_staged(p.n_xb), st>>>(mapA, mapB, mapA, p, pool_bytes_st(p.n_xb));
+    }
     GS_CHECK_LAUNCH();
     return GOSLAM_OK;
   }
