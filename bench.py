@@ -377,8 +377,8 @@ def build_roofline(win, pk, steps, warm, ms_step):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tp):      # dram__bytes_read+write of the `ncu --set full` capture of this kernel on this workload
-        traffic = json.load(open(tp)).get("corr_build_tc_kernel@%dx%d" % (win.ht, win.wd), {}).get("dram_bytes_per_launch")
-    return {"kernel": "corr_build_tc_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+        traffic = json.load(open(tp)).get("corr_build_tc_staged_kernel@%dx%d" % (win.ht, win.wd), {}).get("dram_bytes_per_launch")
+    return {"kernel": "corr_build_tc_staged_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
             "frac": ach / pk["hbm"], "traffic": traffic, "algorithmic_bytes": build_bytes,
             "peak_source": pk["src"] + " (burst copy bandwidth)", "ms_per_launch": ms_build,
             "share_of_step": ms_build / ms_step, "tensor_tflops": build_flops / (ms_build * 1e-3) / 1e12,

@@ -2,7 +2,10 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import torch
+from build_variant import use_variant
+use_variant("probe")          # python tools/build_variant.py probe -DGOSLAM_BA_PROBE
 import bench
 from goslam_b200 import droid_backends
 
