@@ -566,7 +566,8 @@ def render_leg(dev, rank, world, steps, barrier, pk, n_samples, n_surface, with_
     out = {}
     if with_device_leg:
         rd = [r.to(dev) for r in rays]
-        ms_r = max_over_ranks(time_gpu(lambda: net(*rd), max(5, steps // 2), 3, barrier), world)
+        with torch.no_grad():
+            ms_r = max_over_ranks(time_gpu(lambda: net(*rd), max(5, steps // 2), 3, barrier), world)
         rbytes = RAYS * (512.0 * SAMPLES + 1216.0)
         out.update({"metric": "rendered Mrays/s", "value": world * RAYS / ms_r / 1e3, "unit": "Mrays/s", "ms_per_batch": ms_r,
                     "roofline": {"kernel": "neus_forward_kernel", "bound": "hbm", "achieved": rbytes / (ms_r * 1e-3) / 1e9,
@@ -584,10 +585,57 @@ def render_leg(dev, rank, world, steps, barrier, pk, n_samples, n_surface, with_
         o = renderer.render_batch_ray(ro, rdir, net, None, device=dev, gt_depth=gd)
         for k in ("color", "depth"):
             keep[k].copy_(o[k].reshape(keep[k].shape), non_blocking=True)
-    ms_re = max_over_ranks(time_gpu(render_e2e, max(5, steps // 2), 3, barrier), world)
+    with torch.no_grad():
+        ms_re = max_over_ranks(time_gpu(render_e2e, max(5, steps // 2), 3, barrier), world)
     out["e2e"] = {"value": world * RAYS / ms_re / 1e3, "unit": "Mrays/s", "ms_per_batch": ms_re,
                   "call": "Renderer.render_batch_ray (z-sampling %d+%d + marcher), host rays in, colour+depth out" % (n_samples, n_surface),
                   "h2d_bytes_per_batch": RAYS * 7 * 4, "d2h_bytes_per_batch": RAYS * 4 * 4}
+    return out
+
+
+def mapping_leg(dev, rank, world, steps, barrier):
+    """one iteration of Mapper.optimize_map's loop body (src/mapping.py:84-131) — differentiable forward
+    through the fused marcher, the mapping losses, loss.backward() through the renderer backward kernels, clip, AdamW —
+    on 2^16 rays x 72 samples (the reference samples ~4.4 k pixels per iteration; the batch here is sized to fill the
+    GPU).  Also the reference-sized batch."""
+    import types
+    from goslam_b200 import synthetic
+    net, _, _ = make_renderer(dev, 43 + rank)
+    out = {}
+    for tag, R in (("rays_65536", 1 << 16), ("rays_4096", 1 << 12)):
+        ro, rd, zv, ds = [t.to(dev) for t in synthetic.make_rays(R, S=SAMPLES, seed=47 + rank)]
+        g = torch.Generator().manual_seed(5 + rank)
+        rc = torch.rand(R, 3, generator=g).to(dev)
+        depth = (0.5 + 2.5 * torch.rand(R, 1, generator=g)).to(dev)
+        opt = torch.optim.AdamW([{"params": net.get_training_parameters(), "lr": 1e-4},
+                                 {"params": net.get_volume_parameters(), "lr": 1e-3}], betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+        params = net.get_training_parameters() + net.get_volume_parameters()
+        parts = {}
+
+        def fwd_bwd():
+            opt.zero_grad()
+            with torch.enable_grad():
+                o = net(ro, rd, zv, ds)
+                unc = 1.0 / torch.sqrt(o["depth_variance"].detach() + 1e-10)
+                sl, spl = net.compute_sdf_error(sdf=o["sdf"], z_vals=o["z_vals"], gt_depth=depth)
+                total = (2.0 * torch.abs(o["color"] - rc).mean() + (torch.abs(o["depth"] - depth) * unc).mean()
+                         + 2.0 * (sl + spl) + 0.1 * o["gradient_error"].mean())
+            total.backward()
+
+        def step():
+            fwd_bwd()
+            torch.nn.utils.clip_grad_norm_(params, max_norm=35.0)
+            opt.step()
+
+        n = max(5, steps // 2)
+        ms = max_over_ranks(time_gpu(step, n, 3, barrier), world)
+        ms_fb = time_gpu(fwd_bwd, n, 3, lambda: None)
+        with torch.no_grad():
+            ms_f = time_gpu(lambda: net(ro, rd, zv, ds), n, 3, lambda: None)
+        out[tag] = {"value": world * R / ms / 1e3, "unit": "Mrays/s (forward + backward + AdamW)", "ms_per_iteration": ms,
+                    "ms_forward_backward": ms_fb, "ms_inference_forward": ms_f, "rays": R, "samples_per_ray": SAMPLES}
+    out["call"] = ("goslam_b200.InstantNeuS.forward under grad -> mapping losses -> loss.backward() (goslam_neus_composite_backward, "
+                   "cuBLAS fp32 GEMMs of the colour network, goslam_neus_grid_backward) -> clip_grad_norm_ -> torch.optim.AdamW.step")
     return out
 
 
@@ -600,7 +648,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--only", default="", help="comma list of legs to run besides the main one: headline,sharded,full,render")
+    ap.add_argument("--only", default="", help="comma list of legs to run besides the main one: headline,sharded,full,render,mapping")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -619,7 +667,7 @@ def main():
         barrier = lambda: dist.barrier()   # noqa: E731
     else:
         barrier = lambda: None             # noqa: E731
-    legs = set(x for x in args.only.split(",") if x) or {"headline", "sharded", "full", "render"}
+    legs = set(x for x in args.only.split(",") if x) or {"headline", "sharded", "full", "render", "mapping"}
     if args.no_render:
         legs.discard("render")
 
@@ -661,6 +709,9 @@ def main():
         # the marcher's work is the same 72 samples per ray, only the z-sampling split differs
         line["render"]["mono_48_24"] = render_leg(dev, rank, world, args.steps, barrier, pk, 48, SAMPLES - 48,
                                                   with_device_leg=False)["e2e"]
+
+    if "mapping" in legs:
+        line["mapping_step"] = mapping_leg(dev, rank, world, args.steps, barrier)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)

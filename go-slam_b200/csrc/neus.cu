@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <algorithm>
+#include <mutex>
 
 namespace {
 
@@ -388,6 +389,12 @@ neus_forward_kernel(const NeusArgs a) {
 #pragma unroll
         for (int l = 0; l < kLevels; ++l) encrow[l] = __float2half2_rn(0.f);
       }
+      if (a.o.enc && valid) {                        // training pass: keep the encoding row (64 B)
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.o.enc) + gidx * 32);
+        const uint4* src = reinterpret_cast<const uint4*>(encrow);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dst[v] = src[v];
+      }
       __syncwarp();
 
       // ---- phase 1b: SDF head  out[32 x 32] = enc (W_hi + W_lo)^T  on tensor cores ----
@@ -517,6 +524,12 @@ neus_forward_kernel(const NeusArgs a) {
           u.w = h2_as_u32(__floats2half2_rn(row[8 * v8 + 6], row[8 * v8 + 7]));
           rowA[v8] = u;
         }
+        if (a.o.mlp_in && valid) {                   // training pass: keep the MLP input row (160 B)
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.o.mlp_in) + gidx * kIn);
+          const uint4* src = reinterpret_cast<const uint4*>(rowh);
+#pragma unroll
+          for (int v = 0; v < kIn / 8; ++v) dst[v] = src[v];
+        }
       }
       __syncwarp();
 
@@ -551,6 +564,7 @@ neus_forward_kernel(const NeusArgs a) {
           const float x = __half2float(__float2half_rn(scratch[lane * 4 + c]));   // tcnn output is half
           const float sg = 1.0f / (1.0f + expf(-x));
           rgbv[c] = inb ? __half2float(__float2half_rn(sg)) : 0.f;                // torch.sigmoid(half)
+          if (a.o.rgb && valid) a.o.rgb[gidx * 3 + c] = rgbv[c];
         }
         __syncwarp();
       }
@@ -648,6 +662,263 @@ __global__ void neus_finalize_kernel(const float* blk_gerr, const unsigned* blk_
   if (mode == 0) *flag = (c == 0) ? 1 : 0;
 }
 
+// ======================================================================================================
+// Renderer backward (Mapper.optimize_map, src/mapping.py:60-148, differentiates
+// InstantNeuS.forward, src/InstantNeuS.py:295-370, through autograd + tiny-cuda-nn).  The training pass is the SAME
+// fused forward kernel with its per-sample intermediates kept (alpha, normal, sdf, rgb, MLP input row, encoding);
+// the backward is two kernels around the colour network's plain GEMMs (cuBLAS through the host mirror):
+//   neus_composite_bwd_kernel  dL/d{color, depth, sdf, gradient_error} -> per sample dL/d{MLP output, sdf, normal}
+//                              (compositing, NeuS alpha, sigmoid, eikonal term) and dL/d(inv_s)
+//   neus_grid_bwd_kernel       dL/d{encoding, normal} -> hash-grid gradient (scatter) and the part of dL/dW_sdf[0,:]
+//                              that flows through the ANALYTIC normal (second order: the normal is d sdf / d x)
+// ======================================================================================================
+struct CompBwdArgs {
+  goslam_neus_params p;
+  const float* rays_o; const float* rays_d; const float* dists;
+  const float* alpha; const float* rgb; const float* sdf; const float* grad; const float* z_mid;   // saved by the forward
+  const float* d_color; const float* d_depth; const float* d_sdf;                                  // upstream (may be null)
+  const float* d_gerr;               // dL/d gradient_error[0] (device scalar, may be null)
+  float gerr_norm;                   // 1 / (number of samples gradient_error averages over)
+  float* d_mlp_out;                  // [R,S,3]
+  float* d_sdf_out;                  // [R,S]
+  float* d_grad;                     // [R,S,3]
+  float* d_inv_s;                    // [1], accumulated
+  int R, S;
+};
+
+constexpr int kCompChunks = 4;       // S <= 128
+
+// one warp per ray
+__global__ void __launch_bounds__(256) neus_composite_bwd_kernel(const CompBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= a.R) return;
+  const int S = a.S, nch = (S + 31) >> 5;
+  float dc[3] = {0.f, 0.f, 0.f}, dd = 0.f, o[3], dir[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (a.d_color) dc[c] = a.d_color[(size_t)r * 3 + c];
+    o[c] = a.rays_o[(size_t)r * 3 + c];
+    dir[c] = a.rays_d[(size_t)r * 3 + c];
+  }
+  if (a.d_depth) dd = a.d_depth[r];
+  float al[kCompChunks], T[kCompChunks], G[kCompChunks], rg[kCompChunks][3];
+  float carry = 1.f, total = 0.f;
+#pragma unroll
+  for (int c = 0; c < kCompChunks; ++c) {
+    al[c] = 0.f; T[c] = 1.f; G[c] = 0.f; rg[c][0] = rg[c][1] = rg[c][2] = 0.f;
+    if (c < nch) {
+      const int sidx = c * 32 + lane;
+      const bool valid = sidx < S;
+      const size_t gi = (size_t)r * S + sidx;
+      float zm = 0.f;
+      if (valid) {
+        al[c] = a.alpha[gi]; zm = a.z_mid[gi];
+        rg[c][0] = a.rgb[gi * 3]; rg[c][1] = a.rgb[gi * 3 + 1]; rg[c][2] = a.rgb[gi * 3 + 2];
+      }
+      float inc = valid ? (1.0f - al[c] + 1e-7f) : 1.0f;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const float nb = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc *= nb;
+      }
+      float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+      if (lane == 0) exc = 1.0f;
+      T[c] = carry * exc;
+      carry *= __shfl_sync(0xffffffffu, inc, 31);
+      G[c] = dc[0] * rg[c][0] + dc[1] * rg[c][1] + dc[2] * rg[c][2] + dd * zm;     // dL/d weight
+      total += gs_warp_sum(valid ? G[c] * al[c] * T[c] : 0.f);
+    }
+  }
+  const float inv_s = a.p.inv_s, car = a.p.cos_anneal_ratio;
+  const float eik = a.d_gerr ? __ldg(a.d_gerr) * a.gerr_norm : 0.f;
+  float run = 0.f, dinv = 0.f;
+#pragma unroll
+  for (int c = 0; c < kCompChunks; ++c) {
+    if (c < nch) {
+      const int sidx = c * 32 + lane;
+      const bool valid = sidx < S;
+      const size_t gi = (size_t)r * S + sidx;
+      const float w = al[c] * T[c];
+      float incl = valid ? G[c] * w : 0.f;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const float nb = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += nb;
+      }
+      const float chunk = __shfl_sync(0xffffffffu, incl, 31);
+      const float suffix = total - (run + incl);          // sum_{k > s} G_k w_k
+      run += chunk;
+      if (valid) {
+        const float zm = a.z_mid[gi], dist = a.dists[gi];
+        float pt[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pt[k] = __fadd_rn(o[k], __fmul_rn(dir[k], zm));
+        const bool inb = pt[0] < a.p.rt_bound[1] && pt[0] > a.p.rt_bound[0] && pt[1] < a.p.rt_bound[3] &&
+                         pt[1] > a.p.rt_bound[2] && pt[2] < a.p.rt_bound[5] && pt[2] > a.p.rt_bound[4];
+        float dx[3] = {0.f, 0.f, 0.f}, dsdf = 0.f, dg[3] = {0.f, 0.f, 0.f};
+        if (inb) {
+          const float d_alpha = G[c] * T[c] - suffix / (1.0f - al[c] + 1e-7f);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) dx[k] = dc[k] * w * rg[c][k] * (1.0f - rg[c][k]);      // through the sigmoid
+          // ---- NeuS alpha (get_alpha, src/InstantNeuS.py:276-293), recomputed from the saved sdf / normal ----
+          const float sdf = a.sdf[gi];
+          const float g3[3] = {a.grad[gi * 3], a.grad[gi * 3 + 1], a.grad[gi * 3 + 2]};
+          const float tc = dir[0] * g3[0] + dir[1] * g3[1] + dir[2] * g3[2];
+          const float r0 = -tc * 0.5f + 0.5f, r1 = -tc;
+          const float iter_cos = -(fmaxf(r0, 0.f) * (1.0f - car) + fmaxf(r1, 0.f) * car);
+          const float hs = iter_cos * dist / 2.0f;
+          const float pc = 1.0f / (1.0f + expf(-(sdf - hs) * inv_s));
+          const float nc = 1.0f / (1.0f + expf(-(sdf + hs) * inv_s));
+          const float araw = (pc - nc + 1e-5f) / (pc + 1e-5f);
+          if (araw >= 0.f && araw <= 1.f) {                    // clip(0,1) passes the gradient inside the interval
+            const float den = pc + 1e-5f;
+            const float d_pc = d_alpha * (nc / (den * den));     // d/dp [(p - n + e)/(p + e)] = (n) / (p + e)^2
+            const float d_nc = -d_alpha / den;
+            const float d_ap = d_pc * pc * (1.0f - pc), d_an = d_nc * nc * (1.0f - nc);
+            dsdf = (d_ap + d_an) * inv_s;
+            const float d_hs = (d_an - d_ap) * inv_s;
+            dinv += d_ap * (sdf - hs) + d_an * (sdf + hs);
+            const float d_ic = d_hs * dist / 2.0f;
+            const float d_tc = d_ic * ((r0 > 0.f ? 0.5f * (1.0f - car) : 0.f) + (r1 > 0.f ? car : 0.f));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dg[k] = d_tc * dir[k];
+          }
+          if (a.d_sdf) dsdf += a.d_sdf[gi];
+          // ---- eikonal term: gradient_error = mean_n((|g| - 1)^2 * mask) ----
+          const float gn = sqrtf(g3[0] * g3[0] + g3[1] * g3[1] + g3[2] * g3[2]);
+          if (gn > 0.f) {
+            const float f = eik * 2.0f * (gn - 1.0f) / gn;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dg[k] += f * g3[k];
+          }
+        }
+        a.d_sdf_out[gi] = dsdf;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { a.d_mlp_out[gi * 3 + k] = dx[k]; a.d_grad[gi * 3 + k] = dg[k]; }
+      }
+    }
+  }
+  dinv = gs_warp_sum(dinv);
+  if (lane == 0 && dinv != 0.f) atomicAdd(a.d_inv_s, dinv);
+}
+
+struct GridBwdArgs {
+  goslam_neus_params p;
+  const float* rays_o; const float* rays_d; const float* z_vals; const float* dists;
+  const float* d_enc;                // [n,32]
+  const float* d_grad;               // [n,3]   dL/d normal (all paths)
+  float* grid_grad;                  // [entries*2], accumulated
+  float* d_w0;                       // [35] dL/dW_sdf[0,:] through the normal, accumulated
+  long long n; int S;
+};
+
+// thread per sample; recomputes the sample position exactly as the forward does
+__global__ void __launch_bounds__(256) neus_grid_bwd_kernel(const GridBwdArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool act = i < a.n;
+  float x01[3] = {0.f, 0.f, 0.f}, q[3] = {0.f, 0.f, 0.f}, dw_xyz[3] = {0.f, 0.f, 0.f};
+  if (act) {
+    const long long ray = i / a.S;
+    const float dist = a.dists[i];
+    const float zm = __fadd_rn(a.z_vals[i], dist / 2.0f);
+    float pt[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(a.rays_o[ray * 3 + c], __fmul_rn(a.rays_d[ray * 3 + c], zm));
+    act = pt[0] < a.p.rt_bound[1] && pt[0] > a.p.rt_bound[0] && pt[1] < a.p.rt_bound[3] && pt[1] > a.p.rt_bound[2] &&
+          pt[2] < a.p.rt_bound[5] && pt[2] > a.p.rt_bound[4];
+    if (act) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float b0 = a.p.bound[2 * c], b1 = a.p.bound[2 * c + 1];
+        const float raw = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(pt[c], b0), __fsub_rn(b1, b0)), 2.0f), 1.0f);
+        const float xn = fminf(fmaxf(raw, -1.0f), 1.0f);
+        const float dscale = (raw >= -1.0f && raw <= 1.0f) ? 2.0f / (b1 - b0) : 0.0f;
+        x01[c] = __fdiv_rn(__fadd_rn(xn, 1.0f), 2.0f);
+        const float dg = a.d_grad[i * 3 + c];
+        dw_xyz[c] = dscale * dg;            // normal_c = (W0[c] + 0.5 genc_c) * dscale_c
+        q[c] = 0.5f * dscale * dg;          // dL/d genc_c
+      }
+    }
+  }
+  const __half2* table = reinterpret_cast<const __half2*>(a.p.grid);
+  float2* gg = reinterpret_cast<float2*>(a.grid_grad);
+#pragma unroll 1
+  for (int l = 0; l < kLevels; ++l) {
+    float t0 = 0.f, t1 = 0.f;
+    if (act) {
+      const LevelConst L = c_lvl[l];
+      float fr[3]; unsigned pg[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float pos = fmaf(L.scale, x01[c], 0.5f);
+        const float fl = floorf(pos);
+        pg[c] = (unsigned)fl; fr[c] = pos - fl;
+      }
+      // what the forward multiplies this level's input gradient with: dL/dy of the sdf output, rounded to half (tcnn)
+      const float gy0 = __half2float(__float2half_rn(a.p.sdf_w[3 + 2 * l]));
+      const float gy1 = __half2float(__float2half_rn(a.p.sdf_w[3 + 2 * l + 1]));
+      const float de0 = a.d_enc[i * 32 + 2 * l], de1 = a.d_enc[i * 32 + 2 * l + 1];
+      const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        const int bx = c8 & 1, by = (c8 >> 1) & 1, bz = (c8 >> 2) & 1;
+        unsigned idx;
+        if (l >= kDenseLevels) {
+          idx = ((pg[0] + bx) ^ ((pg[1] + by) * 2654435761u) ^ ((pg[2] + bz) * 805459861u)) & 0x7FFFFu;
+        } else {
+          idx = (pg[0] + bx) + (pg[1] + by) * L.res + (pg[2] + bz) * L.res2;
+          idx = idx >= L.size ? idx - L.size : idx;
+        }
+        const float w = (wx[bx] * wy[by]) * wz[bz];
+        // q . grad_u(w_c): +/- the product of the other two axes' weights
+        const float sdot = L.scale * ((bx ? q[0] : -q[0]) * (wy[by] * wz[bz]) + (by ? q[1] : -q[1]) * (wx[bx] * wz[bz]) +
+                                      (bz ? q[2] : -q[2]) * (wx[bx] * wy[by]));
+        const float2 v = __half22float2(__ldg(table + L.offset + idx));
+        t0 = fmaf(v.x, sdot, t0); t1 = fmaf(v.y, sdot, t1);
+        const float c0 = fmaf(de0, w, gy0 * sdot), c1 = fmaf(de1, w, gy1 * sdot);
+        if (c0 != 0.f || c1 != 0.f) atomicAdd(gg + L.offset + idx, make_float2(c0, c1));
+      }
+    }
+    t0 = gs_warp_sum(t0); t1 = gs_warp_sum(t1);
+    if (lane == 0 && (t0 != 0.f || t1 != 0.f)) { atomicAdd(a.d_w0 + 3 + 2 * l, t0); atomicAdd(a.d_w0 + 3 + 2 * l + 1, t1); }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = gs_warp_sum(dw_xyz[c]);
+    if (lane == 0 && v != 0.f) atomicAdd(a.d_w0 + c, v);
+  }
+}
+
+// hash-grid constants are per DEVICE (constant memory) and the opt-in shared memory is per device too
+int neus_device_init() {
+  static bool ready[64];
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return GOSLAM_EINVAL;
+  std::lock_guard<std::mutex> lock(mu);
+  if (ready[dev]) return GOSLAM_OK;
+  GridMeta g = make_grid_meta(nullptr);
+  LevelConst lc[kLevels];
+  for (int l = 0; l < kLevels; ++l) {
+    lc[l].scale = g.scale[l];
+    lc[l].res = (unsigned)g.res[l];
+    lc[l].res2 = (unsigned)g.res[l] * (unsigned)g.res[l];
+    lc[l].offset = g.offset[l];
+    lc[l].size = g.size[l];
+    const unsigned long long dense = (unsigned long long)g.res[l] * g.res[l] * g.res[l];
+    const bool hashed = dense > g.size[l];
+    if (hashed != (l >= kDenseLevels) || (hashed && g.size[l] != (1u << 19))) return GOSLAM_EINVAL;
+  }
+  if (cudaMemcpyToSymbol(c_lvl, lc, sizeof(lc)) != cudaSuccess) return GOSLAM_ELAUNCH;
+  if (cudaFuncSetAttribute(neus_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(Smem)) != cudaSuccess) return GOSLAM_ELAUNCH;
+  ready[dev] = true;
+  return GOSLAM_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -678,25 +949,7 @@ int goslam_neus_forward(const goslam_neus_params* params, const float* rays_o, c
   if (workspace == nullptr || workspace_bytes < goslam_neus_workspace_bytes(R, S))
     return GOSLAM_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool init = false;
-  if (!init) {
-    GridMeta g = make_grid_meta(nullptr);
-    LevelConst lc[kLevels];
-    for (int l = 0; l < kLevels; ++l) {
-      lc[l].scale = g.scale[l];
-      lc[l].res = (unsigned)g.res[l];
-      lc[l].res2 = (unsigned)g.res[l] * (unsigned)g.res[l];
-      lc[l].offset = g.offset[l];
-      lc[l].size = g.size[l];
-      const unsigned long long dense = (unsigned long long)g.res[l] * g.res[l] * g.res[l];
-      const bool hashed = dense > g.size[l];
-      if (hashed != (l >= kDenseLevels) || (hashed && g.size[l] != (1u << 19))) return GOSLAM_EINVAL;
-    }
-    if (cudaMemcpyToSymbol(c_lvl, lc, sizeof(lc)) != cudaSuccess) return GOSLAM_ELAUNCH;
-    if (cudaFuncSetAttribute(neus_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(Smem)) != cudaSuccess) return GOSLAM_ELAUNCH;
-    init = true;
-  }
+  { const int rc = neus_device_init(); if (rc != GOSLAM_OK) return rc; }
   GsArena ar(workspace, workspace_bytes);
   NeusArgs a{};
   a.p = *params; a.o = *out;
@@ -721,6 +974,45 @@ int goslam_neus_forward(const goslam_neus_params* params, const float* rays_o, c
                                            out->gradient_error, a.flag, mode);
     GS_CHECK_LAUNCH();
   }
+  return GOSLAM_OK;
+}
+
+int goslam_neus_composite_backward(const goslam_neus_params* params, const float* rays_o, const float* rays_d,
+                                   const float* dists, const float* alpha, const float* rgb, const float* sdf,
+                                   const float* grad, const float* z_mid, const float* d_color, const float* d_depth,
+                                   const float* d_sdf, const float* d_gradient_error, long long total_samples, int R, int S,
+                                   float* d_mlp_out, float* d_sdf_out, float* d_grad, float* d_inv_s, void* stream) {
+  if (!params || !rays_o || !rays_d || !dists || !alpha || !rgb || !sdf || !grad || !z_mid || !d_mlp_out || !d_sdf_out ||
+      !d_grad || !d_inv_s || R < 0 || S <= 0 || S > 32 * kCompChunks || total_samples < (long long)R * S)
+    return GOSLAM_EINVAL;
+  if (R == 0) return GOSLAM_OK;
+  CompBwdArgs a{};
+  a.p = *params; a.rays_o = rays_o; a.rays_d = rays_d; a.dists = dists;
+  a.alpha = alpha; a.rgb = rgb; a.sdf = sdf; a.grad = grad; a.z_mid = z_mid;
+  a.d_color = d_color; a.d_depth = d_depth; a.d_sdf = d_sdf; a.d_gerr = d_gradient_error;
+  a.gerr_norm = total_samples > 0 ? (float)(1.0 / (double)total_samples) : 0.f;
+  a.d_mlp_out = d_mlp_out; a.d_sdf_out = d_sdf_out; a.d_grad = d_grad; a.d_inv_s = d_inv_s;
+  a.R = R; a.S = S;
+  neus_composite_bwd_kernel<<<gs_cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(a);
+  GS_CHECK_LAUNCH();
+  return GOSLAM_OK;
+}
+
+int goslam_neus_grid_backward(const goslam_neus_params* params, const float* rays_o, const float* rays_d,
+                              const float* z_vals, const float* dists, int R, int S, const float* d_enc,
+                              const float* d_grad, float* grid_grad, float* d_w0, void* stream) {
+  if (!params || !rays_o || !rays_d || !z_vals || !dists || !d_enc || !d_grad || !grid_grad || !d_w0 || R < 0 || S <= 0)
+    return GOSLAM_EINVAL;
+  if (R == 0) return GOSLAM_OK;
+  { const int rc = neus_device_init(); if (rc != GOSLAM_OK) return rc; }
+  GridBwdArgs a{};
+  a.p = *params; a.rays_o = rays_o; a.rays_d = rays_d; a.z_vals = z_vals; a.dists = dists;
+  a.d_enc = d_enc; a.d_grad = d_grad; a.grid_grad = grid_grad; a.d_w0 = d_w0;
+  a.n = (long long)R * S; a.S = S;
+  const long long blocks = (a.n + 255) / 256;
+  if (blocks > 0x7fffffffLL) return GOSLAM_EINVAL;
+  neus_grid_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  GS_CHECK_LAUNCH();
   return GOSLAM_OK;
 }
 

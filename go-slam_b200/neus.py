@@ -13,8 +13,12 @@ reference checkpoint (go.ckpt 'mapping_net') holds:
     color_network._B                       [3, 33]
     color_network.network.params           tcnn FullyFusedMLP params (fp32 master) 64x80|64x64|16x64
     variance_network.variance
-The forward pass is inference-only (the renderer backward / mapping optimiser step is a
-"next" row of the scope table); calling it with grad-requiring inputs raises.
+Under `torch.no_grad()` the forward pass is the inference path.  With grad enabled (what
+Mapper.optimize_map does, src/mapping.py:89-91) the same fused kernel keeps its per-sample intermediates and the
+returned tensors carry a grad_fn: `loss.backward()` runs goslam_neus_composite_backward, the colour network's GEMMs
+(cuBLAS, fp32) and goslam_neus_grid_backward, and fills `.grad` of the hash grid, sdf_layer, colour `_B`, colour
+network and variance parameters.  Differentiable outputs: color, depth, sdf, gradient_error; the other
+keys are returned detached (the reference's losses use depth_variance detached and never read normal / weight_sum).
 """
 import ctypes
 import math
@@ -145,6 +149,28 @@ class InstantNeuS(nn.Module):
     def update_bound(self, bound):
         self.realtime_bound[:] = bound.float().to(self.realtime_bound.device)
 
+    def compute_sdf_error(self, sdf, z_vals, gt_depth):
+        """the SDF supervision of the mapping step (src/InstantNeuS.py:372-400): returns (sdf_error, front_error).
+        Samples within +-truncation of the sensor depth are pulled to `depth - z`; samples in front of that band pay
+        max(exp(-sparse_factor * sdf) - 1, sdf - (depth - z)) clamped at 0; both averaged per ray over the ray's
+        supervised samples, then over the valid rays.  Plain elementwise torch on [n_rays, n_samples] (autograd
+        hands d_sdf to the renderer backward)."""
+        n_rays = z_vals.shape[0]
+        pred = sdf.reshape(n_rays, -1)
+        depth = gt_depth.reshape(n_rays, 1)
+        ok = (depth > 0).reshape(-1)
+        depth, z, pred = depth[ok], z_vals[ok], pred[ok]
+        to_surface = depth - z
+        in_front = z < (depth - self.sdf_truncation)
+        in_band = to_surface.abs() <= self.sdf_truncation
+        per_ray = in_front.sum(dim=1) + in_band.sum(dim=1) + 1e-8
+        n_ok = ok.sum()
+        sparse = torch.exp((-self.sdf_sparse_factor * pred).clamp(max=10.0)) - 1.0
+        front = torch.maximum(sparse, pred - to_surface).clamp(min=0.0) * in_front
+        front_error = (front.sum(dim=1) / per_ray).sum() / n_ok
+        band_error = (((pred - to_surface).abs() * in_band).sum(dim=1) / per_ray).sum() / n_ok
+        return band_error, front_error
+
     # ---- kernel-side parameter staging ------------------------------------------------------
     def refresh_device_params(self):
         """fp16 copies of the tcnn-style params (call after loading / changing weights)."""
@@ -188,10 +214,27 @@ class InstantNeuS(nn.Module):
         return p, keep, inv_s
 
     # ---- forward ------------------------------------------------------------------------------
-    @torch.no_grad()
+    def trainable_tensors(self):
+        """the parameters the renderer backward produces gradients for, in the order _NeusFunction takes them"""
+        return (self.sdf_network.encoding.encoding.params, self.color_network.network.params,
+                self.sdf_network.sdf_layer.weight, self.sdf_network.sdf_layer.bias, self.color_network._B,
+                self.variance_network.variance)
+
     def forward(self, rays_o, rays_d, z_vals, dists, render_params: dict = None, debug=False):
         """debug=True (tests only): additionally keeps the per-sample NeuS alpha [R,S] and SDF normal [R,S,3]
-        in `self.last_debug`."""
+        in `self.last_debug`.  With grad enabled and any trainable parameter requiring grad: differentiable."""
+        params = self.trainable_tensors()
+        if torch.is_grad_enabled() and not debug and any(p.requires_grad for p in params):
+            if any(t.requires_grad for t in (rays_o, rays_d, z_vals, dists)):
+                raise RuntimeError("InstantNeuS.forward: gradients w.r.t. rays / depths are not implemented "
+                                   "(the mapping step optimises the scene representation only)")
+            vals = _NeusFunction.apply(self, rays_o, rays_d, z_vals, dists, *params)
+            return dict(zip(_NeusFunction.KEYS, vals))
+        return self._forward_impl(rays_o, rays_d, z_vals, dists, debug=debug)
+
+    @torch.no_grad()
+    def _forward_impl(self, rays_o, rays_d, z_vals, dists, debug=False, train=False):
+        """the fused marcher; train=True keeps what the backward needs in `self.last_debug`"""
         if not z_vals.is_cuda:
             raise RuntimeError("InstantNeuS.forward: CUDA tensors required (no CPU fallback)")
         dev = z_vals.device
@@ -214,12 +257,19 @@ class InstantNeuS(nn.Module):
         o.weight_sum = out['weight_sum'].data_ptr(); o.sdf = out['sdf'].data_ptr()
         o.z_mid = out['z_vals'].data_ptr(); o.gradient_error = out['gradient_error'].data_ptr()
         self.last_debug = None
-        if debug:
+        if debug or train:
             self.last_debug = {'alpha': torch.empty((R, S), **f32), 'grad': torch.empty((R, S, 3), **f32)}
             o.alpha = self.last_debug['alpha'].data_ptr()
             o.grad = self.last_debug['grad'].data_ptr()
             self.last_debug['pos'] = torch.empty((R, S, 3), **f32)
             o.pos = self.last_debug['pos'].data_ptr()
+        if train:
+            f16 = dict(dtype=torch.float16, device=dev)
+            self.last_debug.update(rgb=torch.empty((R, S, 3), **f32), mlp_in=torch.empty((R, S, MLP_IN_PAD), **f16),
+                                   enc=torch.empty((R, S, N_LEVELS * N_FEAT), **f16))
+            o.rgb = self.last_debug['rgb'].data_ptr()
+            o.mlp_in = self.last_debug['mlp_in'].data_ptr()
+            o.enc = self.last_debug['enc'].data_ptr()
         lib = _lib.load()
         with torch.cuda.device(dev):
             ws = _workspace(lib.goslam_neus_workspace_bytes(R, S), dev)
@@ -229,3 +279,124 @@ class InstantNeuS(nn.Module):
         _lib.check(rc, "neus_forward")
         out['sdf_variance'] = torch.full((R, 1), 1.0 / inv_s, **f32)
         return out
+
+
+class _NeusFunction(torch.autograd.Function):
+    """InstantNeuS.forward as one autograd node (what autograd + tiny-cuda-nn do for the reference,
+    src/InstantNeuS.py:295-370 under torch.enable_grad() in src/mapping.py:89-91).
+    forward : the fused marcher with its per-sample intermediates kept.
+    backward: goslam_neus_composite_backward -> colour-network GEMMs (cuBLAS, fp32 on the fp16 activations the
+              forward used) -> sdf_layer / colour-embedding GEMMs -> goslam_neus_grid_backward (hash-grid scatter +
+              the second-order path through the analytic normal).  Chunked over rays to bound the activations."""
+    CHUNK_RAYS = 1 << 16
+    KEYS = ('color', 'depth', 'sdf', 'gradient_error', 'depth_variance', 'normal', 'weight_sum', 'z_vals', 'sdf_variance')
+
+    @staticmethod
+    def forward(ctx, net, rays_o, rays_d, z_vals, dists, grid, mlp, sdf_w, sdf_b, color_B, variance):
+        ctx.set_materialize_grads(False)
+        rays_o, rays_d = rays_o.detach().float().contiguous(), rays_d.detach().float().contiguous()
+        z_vals, dists = z_vals.detach().float().contiguous(), dists.detach().float().contiguous()
+        out = net._forward_impl(rays_o, rays_d, z_vals, dists, train=True)
+        saved = net.last_debug
+        net.last_debug = None
+        ctx.net = net
+        ctx.pstruct = net._params_struct()          # (struct, tensors it points to, inv_s) at forward time
+        ctx.save_for_backward(rays_o, rays_d, z_vals, dists, saved['alpha'], saved['grad'], saved['rgb'], saved['mlp_in'],
+                              saved['enc'], saved['pos'], out['sdf'], out['z_vals'], sdf_w.detach(), color_B.detach(),
+                              mlp.detach())
+        vals = tuple(out[k] for k in _NeusFunction.KEYS)
+        ctx.mark_non_differentiable(*vals[4:])
+        return vals
+
+    @staticmethod
+    def backward(ctx, d_color, d_depth, d_sdf, d_gerr, *_non_differentiable):
+        (rays_o, rays_d, z_vals, dists, alpha, grad, rgb, mlp_in, enc, pos, sdf, z_mid, sdf_w, color_B, mlp) = ctx.saved_tensors
+        net = ctx.net
+        p, keep, inv_s = ctx.pstruct
+        dev = z_vals.device
+        R, S = z_vals.shape
+        lib = _lib.load()
+        f32 = dict(dtype=torch.float32, device=dev)
+        c = lambda t: None if t is None else t.detach().float().contiguous()
+        d_color, d_depth, d_sdf = c(d_color), c(d_depth), c(d_sdf)
+        d_gerr = c(d_gerr)
+        # The colour network backward is plain GEMMs (cuBLAS).  Like tcnn it runs in fp16 on the tensor cores with a loss
+        # scale: the upstream gradients are multiplied by a power of two that brings their largest entry to ~1024 before
+        # the cast to half (mean-reduced losses give ~1e-6 entries, fp16's smallest normal is 6e-5), weight gradients
+        # accumulate in fp32 (mm out_dtype) and are divided by the scale at the end.  No host synchronisation.
+        f16 = dict(dtype=torch.float16, device=dev)
+        Wh = mlp.half()
+        W1 = Wh[:MLP_HID * MLP_IN_PAD].view(MLP_HID, MLP_IN_PAD)
+        W2 = Wh[MLP_HID * MLP_IN_PAD:MLP_HID * MLP_IN_PAD + MLP_HID * MLP_HID].view(MLP_HID, MLP_HID)
+        W3 = Wh[MLP_HID * MLP_IN_PAD + MLP_HID * MLP_HID:].view(MLP_OUT_PAD, MLP_HID)
+        Wsdf_enc = sdf_w.float()[:, 3:].half().contiguous()                      # [32, 32]
+        colB = color_B.float()
+        g_grid = torch.zeros(net.sdf_network.encoding.encoding.params.numel(), **f32)
+        g_W1 = torch.zeros(MLP_HID, MLP_IN_PAD, **f32)
+        g_W2 = torch.zeros(MLP_HID, MLP_HID, **f32)
+        g_W3 = torch.zeros(MLP_OUT_PAD, MLP_HID, **f32)
+        g_sdf_w, g_sdf_b = torch.zeros(32, 35, **f32), torch.zeros(32, **f32)
+        g_B = torch.zeros(3, 33, **f32)
+        g_w0 = torch.zeros(35, **f32)
+        g_inv_s = torch.zeros(1, **f32)
+        with torch.cuda.device(dev):
+            for r0 in range(0, R, _NeusFunction.CHUNK_RAYS):
+                r1 = min(R, r0 + _NeusFunction.CHUNK_RAYS)
+                n = (r1 - r0) * S
+                sl = slice(r0, r1)
+                ro, rd, zv, ds = rays_o[sl], rays_d[sl], z_vals[sl], dists[sl]
+                d_y = torch.empty(n, 3, **f32); d_s = torch.empty(n, **f32); d_g = torch.empty(n, 3, **f32)
+                dc = None if d_color is None else d_color[sl].contiguous()
+                dd = None if d_depth is None else d_depth[sl].contiguous()
+                dsu = None if d_sdf is None else d_sdf[sl].contiguous()
+                rc = lib.goslam_neus_composite_backward(
+                    ctypes.byref(p), _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(ds), _lib.ptr(alpha[sl]), _lib.ptr(rgb[sl]),
+                    _lib.ptr(sdf[sl]), _lib.ptr(grad[sl]), _lib.ptr(z_mid[sl]),
+                    None if dc is None else _lib.ptr(dc), None if dd is None else _lib.ptr(dd),
+                    None if dsu is None else _lib.ptr(dsu), None if d_gerr is None else _lib.ptr(d_gerr),
+                    ctypes.c_int64(R * S), r1 - r0, S,
+                    _lib.ptr(d_y), _lib.ptr(d_s), _lib.ptr(d_g), _lib.ptr(g_inv_s), _lib.stream_ptr())
+                _lib.check(rc, "neus_composite_backward")
+                amax = torch.maximum(d_y.abs().max(), d_s.abs().max()).clamp_min(1e-30)
+                sc = torch.exp2(torch.floor(torch.log2(1024.0 / amax))).clamp(max=2.0 ** 40)     # device scalar
+                # ---- colour network (tcnn FullyFusedMLP: no biases, ReLU, half activations) ----
+                X = mlp_in[sl].reshape(n, MLP_IN_PAD)                                 # half, as the forward built it
+                H1 = torch.relu(X @ W1.t())
+                H2 = torch.relu(H1 @ W2.t())
+                dY = torch.zeros(n, 8, **f16)
+                dY[:, :3] = d_y * sc
+                g_W3[:8] += torch.mm(dY.t(), H2, out_dtype=torch.float32) / sc
+                dH2 = (dY @ W3[:8]) * (H2 > 0)
+                g_W2 += torch.mm(dH2.t(), H1, out_dtype=torch.float32) / sc
+                dH1 = (dH2 @ W2) * (H1 > 0)
+                del dH2, H2
+                g_W1 += torch.mm(dH1.t(), X, out_dtype=torch.float32) / sc
+                dX = dH1 @ W1                                                          # [n, 80] half, scaled
+                del dH1, H1
+                # ---- colour embedding sin(pts @ B) ----
+                pts = (ro[:, None, :] + rd[:, None, :] * z_mid[sl][:, :, None]).reshape(n, 3)
+                g_B += (pts.t() @ (dX[:, :33].float() * torch.cos(pts @ colB))) / sc
+                # ---- sdf_layer: out = W h + b, h = [xn | enc]; sdf = out[0], feat = out[1:] ----
+                d_out = torch.empty(n, 32, **f16)
+                d_out[:, 0] = d_s * sc
+                d_out[:, 1:] = dX[:, 36:67]
+                h = torch.zeros(n, 40, **f16)                                          # K padded to a multiple of 8
+                h[:, :3] = pos[sl].reshape(n, 3)
+                h[:, 3:35] = enc[sl].reshape(n, 32)
+                g_sdf_w += torch.mm(d_out.t(), h, out_dtype=torch.float32)[:, :35] / sc
+                g_sdf_b += d_out.float().sum(0) / sc
+                d_enc = torch.mm(d_out, Wsdf_enc, out_dtype=torch.float32) / sc       # [n, 32] f32
+                d_gt = d_g + dX[:, 33:36].float() / sc                                # normal: alpha + eikonal + colour input
+                del dX, d_out, h
+                rc = lib.goslam_neus_grid_backward(ctypes.byref(p), _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(zv), _lib.ptr(ds),
+                                                   r1 - r0, S, _lib.ptr(d_enc), _lib.ptr(d_gt), _lib.ptr(g_grid),
+                                                   _lib.ptr(g_w0), _lib.stream_ptr())
+                _lib.check(rc, "neus_grid_backward")
+        g_sdf_w[0] += g_w0
+        # samples outside the real-time bound: the forward zeroed their rows' effect (rgb = 0, alpha = 0), the kernels
+        # return zeros for them, so the GEMMs above see zero rows.
+        sf = net.variance_network.scale_factor
+        raw = float(torch.exp(net.variance_network.variance.detach().float() * sf))
+        g_var = (g_inv_s[0] * inv_s * sf) if 1e-6 <= raw <= 1e6 else torch.zeros((), **f32)
+        g_mlp = torch.cat([g_W1.reshape(-1), g_W2.reshape(-1), g_W3.reshape(-1)])
+        return (None, None, None, None, None, g_grid, g_mlp, g_sdf_w, g_sdf_b, g_B, g_var.reshape(()))

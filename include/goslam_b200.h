@@ -247,6 +247,10 @@ typedef struct goslam_neus_out {
   float* alpha;          /* [R,S]   NeuS alpha of every sample (0 outside the bound)  */
   float* grad;           /* [R,S,3] SDF normal of every sample (0 outside the bound)  */
   float* pos;            /* [R,S,3] normalised sample position in [-1,1] (0 outside the bound) */
+  /* optional, kept by the training pass for goslam_neus_*_backward: */
+  float* rgb;            /* [R,S,3]  colour of every sample after the sigmoid (0 outside the bound) */
+  void* mlp_in;          /* [R,S,80] f16: the colour network's input row [sin(pB) 33 | normal 3 | feat 31 | 1.0 x 13] */
+  void* enc;             /* [R,S,32] f16: hash-grid encoding (0 outside the bound) */
 } goslam_neus_out;
 
 size_t goslam_neus_workspace_bytes(int R, int S);
@@ -254,6 +258,35 @@ int goslam_neus_forward(const goslam_neus_params* params, const float* rays_o,
                         const float* rays_d, const float* z_vals, const float* dists,
                         int R, int S, const goslam_neus_out* out,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* ------------------------------------------------------------------------------------
+ * Renderer backward.  The reference differentiates InstantNeuS.forward with autograd + tiny-cuda-nn
+ * inside Mapper.optimize_map (src/mapping.py:60-148: total_loss.backward()).  Here the training pass is
+ * goslam_neus_forward with the optional per-sample outputs kept (alpha, grad, rgb, mlp_in, enc), and the backward is
+ * these two kernels around the colour network's plain GEMMs (which the host mirror runs on cuBLAS):
+ *
+ * goslam_neus_composite_backward — per ray: compositing (weights = alpha * cumprod(1 - alpha + 1e-7)), NeuS alpha
+ *   (get_alpha, src/InstantNeuS.py:276-293, incl. the clip), the colour sigmoid and the eikonal term.
+ *   in : saved alpha, sdf, z_mid [R,S], rgb, grad [R,S,3]; upstream d_color [R,3], d_depth [R], d_sdf [R,S] (each may
+ *        be NULL = zero) and d_gradient_error (device scalar dL/d gradient_error[0], or NULL); total_samples = the number
+ *        of samples gradient_error was averaged over (R*S of the WHOLE forward call when this call covers a slice of it).
+ *   out: d_mlp_out [R,S,3] (w.r.t. the colour network's first three outputs, before the sigmoid), d_sdf_out [R,S],
+ *        d_grad [R,S,3] (w.r.t. the SDF normal: alpha path + eikonal), d_inv_s [1] (ACCUMULATED: zero it first).
+ *   Samples outside the real-time bound get zeros (the forward gives them constants).  S <= 128.
+ *
+ * goslam_neus_grid_backward — per sample: scatters dL/d(encoding) [R*S,32] and the part of dL/d(normal) [R*S,3] that
+ *   flows through the hash grid into grid_grad [n_params] f32 (ACCUMULATED), and accumulates into d_w0 [35] the gradient
+ *   of row 0 of sdf_layer.weight THROUGH THE NORMAL (normal = (W0[:3] + 0.5 * d enc/d u . W0[3:]) * 2/(b1-b0)), i.e. the
+ *   second-order path autograd takes with create_graph=True (src/InstantNeuS.py:139-146).  The direct path
+ *   (d_out^T h) is a plain GEMM left to the caller.  Positions are recomputed from the rays exactly as the forward does. */
+int goslam_neus_composite_backward(const goslam_neus_params* params, const float* rays_o, const float* rays_d,
+                                   const float* dists, const float* alpha, const float* rgb, const float* sdf,
+                                   const float* grad, const float* z_mid, const float* d_color,
+                                   const float* d_depth, const float* d_sdf, const float* d_gradient_error,
+                                   long long total_samples, int R, int S, float* d_mlp_out, float* d_sdf_out, float* d_grad,
+                                   float* d_inv_s, void* stream);
+int goslam_neus_grid_backward(const goslam_neus_params* params, const float* rays_o, const float* rays_d,
+                              const float* z_vals, const float* dists, int R, int S, const float* d_enc,
+                              const float* d_grad, float* grid_grad, float* d_w0, void* stream);
 /* hash-grid geometry helper (host side, no GPU): fills offsets[17] (in PARAMS, i.e.
  * entries*2), resolutions[16], scales[16]; returns total number of f16 params. */
 int64_t goslam_hashgrid_layout(int64_t* offsets, int* resolutions, float* scales);

@@ -235,6 +235,122 @@ def gen_neus():
                         **{"out_" + k: v.detach().float().numpy() for k, v in out.items()})
 
 
+def gen_neus_grad():
+    """Renderer backward golden: the REFERENCE's InstantNeuS.forward (its own autograd.grad normal included) under
+    enable_grad with the tcnn modules replaced by the differentiable restatements of oracle/neus_grad_oracle.py, the
+    loss of Mapper.optimize_map (src/mapping.py:97-128, weights of configs/go_slam.yaml, uncertainty weighting on) and
+    .backward().  Stored: inputs, the loss, the forward outputs and every parameter gradient (the 12.6 M-entry hash-grid
+    gradient as its non-zero entries)."""
+    neus_mod = ref_import("src.InstantNeuS")
+    import tinycudann
+    from oracle import neus_grad_oracle as ngo
+    from goslam_b200 import synthetic
+    old = tinycudann.Encoding, tinycudann.Network
+    tinycudann.Encoding, tinycudann.Network = ngo.TorchHashGrid, ngo.TorchMLP
+    try:
+        metas, total_entries = neus_oracle.hashgrid_meta()
+        offs = [m["offset"] * 2 for m in metas] + [total_entries * 2]
+        ress = [m["res"] for m in metas]
+        w = synthetic.make_neus_weights(seed=9, total_grid_params=total_entries * 2, layout=(offs, ress))
+        bound = [[-2.0, 2.0], [-2.0, 2.0], [-2.0, 2.0]]
+        net = neus_mod.InstantNeuS(synthetic.NEUS_CFG, bound, device="cpu")
+        with torch.no_grad():
+            net.sdf_network.encoding.encoding.params.copy_(w["grid"])
+            net.sdf_network.sdf_layer.weight.copy_(w["sdf_w"])
+            net.sdf_network.sdf_layer.bias.copy_(w["sdf_b"])
+            net.color_network._B.copy_(w["color_B"])
+            net.color_network.network.params.copy_(w["mlp"])
+        rt = torch.tensor([[-1.8, 1.9], [-2.0, 2.0], [-1.5, 2.0]])
+        net.update_bound(rt)
+        R, S = 40, 32
+        ro, rd, zv, ds = synthetic.make_rays(R, S=S, seed=13, n_uniform=12)
+        g = torch.Generator().manual_seed(17)
+        rays_color = torch.rand(R, 3, generator=g)
+        rays_depth = 0.5 + 2.5 * torch.rand(R, generator=g)
+        rays_depth[::9] = 0.0                                     # invalid sensor depth: ray excluded from the losses
+        with torch.enable_grad():
+            out = net(ro, rd, zv, ds)
+            # src/mapping.py:97-128
+            depth = rays_depth.reshape(-1, 1)
+            valid = (depth > 0).reshape(-1)
+            unc = 1.0 / torch.sqrt(out["depth_variance"][valid].detach() + 1e-10)
+            color_loss = torch.abs(out["color"][valid] - rays_color[valid]).mean()
+            depth_loss = (torch.abs(out["depth"][valid] - depth[valid]) * unc).mean()
+            sdf_loss, sparse_loss = net.compute_sdf_error(sdf=out["sdf"][valid], z_vals=out["z_vals"][valid], gt_depth=depth[valid])
+            total = color_loss * 2.0 + depth_loss * 1.0 + (sdf_loss + sparse_loss) * 2.0 + 0.1 * out["gradient_error"].mean()
+            total.backward()
+        gg = net.sdf_network.encoding.encoding.params.grad.numpy()
+        nz = np.nonzero(gg)[0]
+        np.savez_compressed(
+            os.path.join(HERE, "neus_grad.npz"), rays_o=ro.numpy(), rays_d=rd.numpy(), z_vals_in=zv.numpy(), dists=ds.numpy(),
+            rt_bound=rt.numpy(), bound=np.array(bound, np.float32), weights_seed=9, rays_color=rays_color.numpy(),
+            rays_depth=rays_depth.numpy(), loss=np.float32(total.item()),
+            parts=np.array([color_loss.item(), depth_loss.item(), sdf_loss.item(), sparse_loss.item(), out["gradient_error"].item()], np.float32),
+            grid_grad_idx=nz.astype(np.int64), grid_grad_val=gg[nz].astype(np.float32),
+            g_sdf_w=net.sdf_network.sdf_layer.weight.grad.numpy(), g_sdf_b=net.sdf_network.sdf_layer.bias.grad.numpy(),
+            g_color_B=net.color_network._B.grad.numpy(), g_mlp=net.color_network.network.params.grad.numpy(),
+            g_variance=net.variance_network.variance.grad.numpy(),
+            **{"out_" + k: v.detach().float().numpy() for k, v in out.items()})
+        print("neus_grad: loss %.6f, %d non-zero grid gradients, |g_sdf_w| %.4e |g_mlp| %.4e |g_B| %.4e g_var %.4e" % (
+            total.item(), nz.size, np.linalg.norm(net.sdf_network.sdf_layer.weight.grad.numpy()),
+            np.linalg.norm(net.color_network.network.params.grad.numpy()), np.linalg.norm(net.color_network._B.grad.numpy()),
+            float(net.variance_network.variance.grad)))
+    finally:
+        tinycudann.Encoding, tinycudann.Network = old
+
+
+def gen_neus_adamw():
+    """Mapping-step trajectory golden: 8 iterations of Mapper.optimize_map's loop body (src/mapping.py:84-131: forward
+    under enable_grad, loss, backward, clip_grad_norm_(35), AdamW step with the two parameter groups of :55-58) run by the
+    REFERENCE's InstantNeuS on the inputs of neus_grad.npz, with uncertainty weighting off and both learning rates x0.1
+    (with the config's rates this synthetic scene's uncertainty-weighted depth loss grows 20x in one step — in the
+    reference as well).  Stored: the 8 losses and their parts."""
+    neus_mod = ref_import("src.InstantNeuS")
+    import tinycudann
+    from oracle import neus_grad_oracle as ngo
+    from goslam_b200 import synthetic
+    old = tinycudann.Encoding, tinycudann.Network
+    tinycudann.Encoding, tinycudann.Network = ngo.TorchHashGrid, ngo.TorchMLP
+    try:
+        g = np.load(os.path.join(HERE, "neus_grad.npz"))
+        metas, total_entries = neus_oracle.hashgrid_meta()
+        offs = [m["offset"] * 2 for m in metas] + [total_entries * 2]
+        ress = [m["res"] for m in metas]
+        w = synthetic.make_neus_weights(seed=int(g["weights_seed"]), total_grid_params=total_entries * 2, layout=(offs, ress))
+        net = neus_mod.InstantNeuS(synthetic.NEUS_CFG, g["bound"].tolist(), device="cpu")
+        with torch.no_grad():
+            net.sdf_network.encoding.encoding.params.copy_(w["grid"])
+            net.sdf_network.sdf_layer.weight.copy_(w["sdf_w"])
+            net.sdf_network.sdf_layer.bias.copy_(w["sdf_b"])
+            net.color_network._B.copy_(w["color_B"])
+            net.color_network.network.params.copy_(w["mlp"])
+        net.update_bound(torch.from_numpy(g["rt_bound"]))
+        net_lr, grid_lr = 1e-4, 1e-3
+        opt = torch.optim.AdamW([{"params": net.get_training_parameters(), "lr": net_lr},
+                                 {"params": net.get_volume_parameters(), "lr": grid_lr}], betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+        args = [torch.from_numpy(g[k]) for k in ("rays_o", "rays_d", "z_vals_in", "dists")]
+        rc, rdp = torch.from_numpy(g["rays_color"]), torch.from_numpy(g["rays_depth"])
+        rows = []
+        for it in range(8):
+            opt.zero_grad()
+            with torch.enable_grad():
+                out = net(*args)
+                depth = rdp.reshape(-1, 1)
+                valid = (depth > 0).reshape(-1)
+                cl = torch.abs(out["color"][valid] - rc[valid]).mean()
+                dl = torch.abs(out["depth"][valid] - depth[valid]).mean()
+                sl, spl = net.compute_sdf_error(sdf=out["sdf"][valid], z_vals=out["z_vals"][valid], gt_depth=depth[valid])
+                total = cl * 2.0 + dl * 1.0 + (sl + spl) * 2.0 + 0.1 * out["gradient_error"].mean()
+                total.backward()
+            torch.nn.utils.clip_grad_norm_(net.get_training_parameters() + net.get_volume_parameters(), max_norm=35.0)
+            opt.step()
+            rows.append([total.item(), cl.item(), dl.item(), sl.item(), spl.item(), out["gradient_error"].item()])
+            print("neus_adamw step %d: %s" % (it, " ".join("%.5f" % v for v in rows[-1])))
+        np.savez_compressed(os.path.join(HERE, "neus_adamw.npz"), rows=np.array(rows, np.float32), net_lr=net_lr, grid_lr=grid_lr)
+    finally:
+        tinycudann.Encoding, tinycudann.Network = old
+
+
 def gen_render_z():
     render_mod = ref_import("src.render")
     cfg = {"rendering": {"lindisp": False, "perturb": 1.0, "N_samples": 24, "N_surface": 48}}

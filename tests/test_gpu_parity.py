@@ -492,7 +492,8 @@ def test_neus_forward_vs_reference_golden():
         net.color_network.network.params.copy_(w["mlp"])
     net = net.to(dev())
     net.update_bound(torch.from_numpy(g["rt_bound"]))
-    out = net(*[torch.from_numpy(g[k]).to(dev()) for k in ("rays_o", "rays_d", "z_vals_in", "dists")])
+    with torch.no_grad():        # rendering runs under no_grad in the reference too; with grad enabled see test_gpu_neus_train.py
+        out = net(*[torch.from_numpy(g[k]).to(dev()) for k in ("rays_o", "rays_d", "z_vals_in", "dists")])
     assert set(out.keys()) == set(k[4:] for k in g.files if k.startswith("out_"))
     for k, v in out.items():
         want = g["out_" + k]

@@ -3,6 +3,7 @@ import os, sys, types
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
+torch.set_grad_enabled(False)      # inference tools
 import bench
 from goslam_b200 import render as render_mod
 
