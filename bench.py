@@ -438,27 +438,46 @@ def sharded_graph_leg(dev, steps, warm, barrier, world, rank):
         own_group = True
     else:
         own_group = False
-    sg = parallel.ShardedGraph(D["poses"], D["disps"], D["intrinsics"], D["disps_sens"], D["fmaps"], ii, jj, 1, num_kf,
-                               group=group)
-    tg_l, wg_l = sg.local(tg.to(dev)), sg.local(wg.to(dev))                      # planar [n,2,h,w]
-    tgt_flow = sg.local(tg.permute(0, 2, 3, 1).contiguous().to(dev))            # [n,h,w,2] for the motion features
     p0, d0 = D["poses"].clone(), D["disps"].clone()
-
-    def update():
+    res = {}
+    for exchange in (("nccl", "peer") if world > 1 else ("nccl",)):
         D["poses"].copy_(p0)
-        D["disps"].copy_(d0)
-        sg.features(tgt_flow)
-        sg.bundle_adjust(tg_l, wg_l, eta_f, iters, 1e-5, 1e-2)
+        sg = parallel.ShardedGraph(D["poses"], d0.clone(), D["intrinsics"], D["disps_sens"], D["fmaps"], ii, jj, 1, num_kf,
+                                   group=group, exchange=exchange)
+        tg_l, wg_l = sg.local(tg.to(dev)), sg.local(wg.to(dev))                      # planar [n,2,h,w]
+        tgt_flow = sg.local(tg.permute(0, 2, 3, 1).contiguous().to(dev))            # [n,h,w,2] for the motion features
 
-    ms = max_over_ranks(time_gpu(update, steps, warm, barrier), world)
-    # replicas must agree bit for bit after the update (every rank solved the same all-reduced system)
-    agree = True
-    if world > 1:
-        ref = D["poses"].clone()
-        dist.broadcast(ref, src=0)
-        flag = torch.tensor([float(torch.equal(ref, D["poses"]))], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        agree = bool(flag.item() == 1.0)
+        def update():
+            if sg.link is not None:
+                sg.link.wait_idle()              # the peers' last rows have landed before the replica is reset
+            sg.poses.copy_(p0)
+            sg.disps.copy_(d0)
+            sg.features(tgt_flow)
+            sg.bundle_adjust(tg_l, wg_l, eta_f, iters, 1e-5, 1e-2)
+
+        ms_x = max_over_ranks(time_gpu(update, steps, warm, barrier), world)
+        if sg.link is not None:
+            sg.link.wait_idle()
+        torch.cuda.synchronize()
+        # replicas must agree bit for bit after the update (every rank solved the same summed system)
+        agree_x = True
+        if world > 1:
+            for t in (sg.poses, sg.disps):
+                ref = t.clone()
+                dist.broadcast(ref, src=0)
+                flag = torch.tensor([float(torch.equal(ref, t))], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                agree_x = agree_x and bool(flag.item() == 1.0)
+        res[exchange] = {"ms_per_update": ms_x, "replicas_bit_identical": agree_x, "poses": sg.poses.clone(),
+                         "timeout": bool(sg.link.timeout.item()) if sg.link is not None else False}
+        if sg.link is not None:
+            sg.link.close()
+    best = min(res, key=lambda k: res[k]["ms_per_update"])
+    ms, agree = res[best]["ms_per_update"], all(r["replicas_bit_identical"] for r in res.values())
+    exchanges = {k: {"ms_per_update": r["ms_per_update"], "replicas_bit_identical": r["replicas_bit_identical"]} for k, r in res.items()}
+    if "peer" in res:
+        exchanges["peer"]["max_abs_pose_diff_vs_nccl"] = float((res["peer"]["poses"] - res["nccl"]["poses"]).abs().max())
+        exchanges["peer"]["wait_timed_out"] = res["peer"]["timeout"]
     if own_group:
         dist.destroy_process_group()
     P = num_kf - 1
@@ -468,7 +487,11 @@ def sharded_graph_leg(dev, steps, warm, barrier, world, rank):
                         "reproject + 4-level windowed correlation + 2 BA iters (lm 1e-5, ep 1e-2), P = %d poses" % (int(ii.numel()), P),
             "parallelism": "edges sharded by source frame over %d rank(s); per BA iteration 1 all-reduce of %d B "
                            "(reduced camera system, f64) + 1 all-gather of the owned inverse-depth rows" % (world, 8 * (36 * P * P + 6 * P)),
-            "local_edges_rank0": int(sg.ii.numel()), "replicas_bit_identical": agree}
+            "local_edges_rank0": int(sg.ii.numel()), "replicas_bit_identical": agree, "exchange": best,
+            "exchanges": exchanges,
+            "exchange_note": "nccl: all-reduce + all-gather per iteration; peer: the solve kernel sums the ranks' partial systems "
+                             "out of peer memory while it loads the matrix, the back-substitution writes the owned rows into every "
+                             "replica (goslam_ba_phase1_peers / goslam_ba_phase2_peers, CUDA IPC over NVLink, no collective)"}
 
 
 def full_update_leg(dev, steps, warm, barrier, world, rank):

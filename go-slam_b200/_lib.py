@@ -34,6 +34,11 @@ class NeusOut(ctypes.Structure):
     ]
 
 
+class BaPeers(ctypes.Structure):
+    _fields_ = [("world", c_int), ("rank", c_int), ("system", c_void_p * 8), ("disps", c_void_p * 8), ("flags", c_void_p * 8),
+                ("epoch", ctypes.c_uint), ("timeout", c_void_p)]
+
+
 class GruWeights(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("w_zr", "w_q", "w_w", "b_zr", "b_q", "b_w", "w_glo", "b_glo")]
 
@@ -85,6 +90,15 @@ SIGNATURES = {
                          [c_void_p, c_void_p, c_size_t, c_void_p]),
     "goslam_ba_phase2": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_float, c_float] + [c_int] * 3 +
                          [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "goslam_ba_phase1_peers": (c_int, [c_void_p] * 6 + [c_int] + [c_void_p] * 2 + [c_int] * 7 +
+                               [ctypes.POINTER(BaPeers), c_void_p, c_size_t, c_void_p]),
+    "goslam_ba_phase2_peers": (c_int, [c_void_p] + [c_int] * 6 + [c_float, c_float] + [c_int] * 3 +
+                               [ctypes.POINTER(BaPeers)] + [c_void_p] * 4 + [c_size_t, c_void_p]),
+    "goslam_ba_peers_wait": (c_int, [ctypes.POINTER(BaPeers), c_void_p]),
+    "goslam_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
+    "goslam_peer_free": (c_int, [c_void_p]),
+    "goslam_ipc_open": (c_int, [c_void_p, c_void_p]),
+    "goslam_ipc_close": (c_int, [c_void_p]),
     "goslam_neus_workspace_bytes": (c_size_t, [c_int, c_int]),
     "goslam_neus_forward": (c_int, [ctypes.POINTER(NeusParams)] + [c_void_p] * 4 + [c_int, c_int] +
                             [ctypes.POINTER(NeusOut), c_void_p, c_size_t, c_void_p]),

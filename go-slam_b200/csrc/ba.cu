@@ -31,6 +31,7 @@
 // zeroed (:320-323); stereo baseline (-0.1,0,0) (:219-229); MIN_DEPTH 0.25 (:26);
 // damping diag += ep + lm*diag (:1197); failed factorisation => dx = 0 (:1207-1210).
 #include "common.cuh"
+#include <cstring>
 #include "se3.cuh"
 #include <algorithm>
 #include <cstdio>
@@ -575,6 +576,65 @@ ba_system_kernel(const float* poses, const int64_t* __restrict__ ii,
 }
 
 // ------------------------------------------------------------------------------------
+// Multi-GPU split form over PEER MEMORY (goslam_ba_phase1_peers / goslam_ba_phase2_peers): every rank leaves its partial
+// reduced camera system in a buffer its peers have mapped (CUDA IPC over NVLink / NVSwitch); the solve kernels sum
+// the partial systems WHILE THEY LOAD the matrix into shared memory — in rank order, so every rank factors bit-identical
+// numbers — instead of waiting for an NCCL all-reduce, and the back-substitution writes the inverse-depth rows a rank
+// owns straight into every replica instead of an all-gather.  Ordering is by epoch flags in peer memory
+// (st.release.sys by a one-warp signal kernel after the producing kernels, ld.acquire.sys spin in the consumer).
+// ------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+struct SysSrc {
+  const double* p[kMaxPeers];        // partial systems in rank order (n == 1: the local, complete system)
+  int n;
+  const unsigned* flags;             // [n] local flag words, flags[r] >= epoch <=> rank r's partial system is complete
+  unsigned epoch;
+  int* timeout;
+};
+struct PeerRows {
+  float* p[kMaxPeers];               // every replica of disps (n == 0: local only)
+  int n;
+};
+
+__device__ __forceinline__ double sys_at(const SysSrc& s, size_t i) {
+  if (s.n <= 1) return s.p[0][i];
+  double v = 0.0;
+  for (int r = 0; r < s.n; ++r) {
+    double x;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(s.p[r] + i) : "memory");
+    v += x;
+  }
+  return v;
+}
+
+// threads 0..n-1 of the block wait for the n flag words; gives up after ~2 s (a dead peer must not hang the GPU)
+__device__ __forceinline__ void peer_wait(const unsigned* flags, int n, unsigned epoch, int* timeout) {
+  if (n > 1 && (int)threadIdx.x < n) {
+    const long long t0 = clock64();
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      if (clock64() - t0 > (1ll << 32)) { if (timeout) *timeout = 1; break; }
+    } while (true);
+  }
+  __syncthreads();
+}
+
+__global__ void ba_peer_wait_kernel(const unsigned* flags, int n, unsigned epoch, int* timeout) {
+  peer_wait(flags, n, epoch, timeout);
+}
+
+// after the kernels that produced the data (same stream): publish `epoch` in word `slot` of every rank's flag row
+__global__ void ba_peer_signal_kernel(PeerRows flag_rows, int slot, unsigned epoch) {
+  __threadfence_system();
+  if ((int)threadIdx.x < flag_rows.n) {
+    unsigned* dst = reinterpret_cast<unsigned*>(flag_rows.p[threadIdx.x]) + slot;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Damp + Cholesky (float64) + solve + pose retraction.  One block.
 // A lives in shared memory when it fits, else in the global scratch.
 // ------------------------------------------------------------------------------------
@@ -637,7 +697,7 @@ __device__ int g_phase_cycles[2][1024];
 //    and the panel solve.  2 barriers per block column.
 //  * Backward substitution is right-looking: solve a block, push it into the rows above.
 __device__ __forceinline__ void solve_small(float* poses, const BaDims& d, const BaWs& ws,
-                                            const double* sys_in, float lm, float ep, float* dx_out,
+                                            const SysSrc& sys_in, float lm, float ep, float* dx_out,
                                             int* status_out, double* smd, SolveSmem& ss) {
   double* xs = ss.xs;
   int& failed = ss.failed;
@@ -661,7 +721,7 @@ __device__ __forceinline__ void solve_small(float* poses, const BaDims& d, const
       for (int u = 0; u < 16; ++u) {
         const int idx = base + tid + 128 * u;
         const int r = idx / n, c = idx - r * n;
-        v[u] = (idx < tot && (c <= r || r == n)) ? sys_in[idx] : 0.0;
+        v[u] = (idx < tot && (c <= r || r == n)) ? sys_at(sys_in, idx) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
@@ -809,33 +869,35 @@ __device__ __forceinline__ void solve_small(float* poses, const BaDims& d, const
 }
 
 __global__ void __launch_bounds__(128)
-ba_solve_warp_kernel(float* poses, BaDims d, BaWs ws, const double* sys_in, float lm, float ep,
+ba_solve_warp_kernel(float* poses, BaDims d, BaWs ws, const SysSrc sys_in, float lm, float ep,
                      float* dx_out, int* status_out) {
   extern __shared__ double smd[];
   __shared__ SolveSmem ss;
   if (ws.counts[4]) { bad_argument_step(d, ws, dx_out, status_out, threadIdx.x, blockDim.x); return; }
+  peer_wait(sys_in.flags, sys_in.n, sys_in.epoch, sys_in.timeout);
   solve_small(poses, d, ws, sys_in, lm, ep, dx_out, status_out, smd, ss);
 }
 
 // General case: one block; A in shared memory when it fits, else in the global scratch.
 __global__ void __launch_bounds__(1024)
-ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const double* __restrict__ sys_in,
+ba_solve_kernel(float* __restrict__ poses, BaDims d, BaWs ws, const SysSrc sys_in,
                 float lm, float ep, int use_smem, float* __restrict__ dx_out,
                 int* __restrict__ status_out) {
   extern __shared__ double smd[];
   __shared__ int fail;
   const int n = d.n, tid = threadIdx.x, nt = blockDim.x;
   if (ws.counts[4]) { bad_argument_step(d, ws, dx_out, status_out, tid, nt); return; }
+  peer_wait(sys_in.flags, sys_in.n, sys_in.epoch, sys_in.timeout);
   double* A = use_smem ? smd : ws.chol;
   double* b = use_smem ? smd + (size_t)n * n : ws.rhs;
   if (tid == 0) fail = 0;
   for (size_t idx = tid; idx < (size_t)n * n; idx += nt) {
     const int r = (int)(idx / n), c = (int)(idx % n);
-    double val = sys_in[idx];
+    double val = sys_at(sys_in, idx);
     if (r == c) val += (double)ep + (double)lm * val;
     A[idx] = val;
   }
-  for (int i = tid; i < n; i += nt) b[i] = sys_in[(size_t)n * n + i];
+  for (int i = tid; i < n; i += nt) b[i] = sys_at(sys_in, (size_t)n * n + i);
   __syncthreads();
 
   // right-looking Cholesky on the lower triangle; the diagonal keeps 1/l_jj
@@ -925,7 +987,7 @@ inline size_t cl_smem_bytes(int P) {
 //   next diagonal -> every CTA's `dloc`    (by its owner, as soon as its own row is updated)
 //   backward pass -> partial sums of the next 8 block rows go to their owners' `inbox`
 __global__ void __launch_bounds__(kClT)
-ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restrict__ sys_in, float lm,
+ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const SysSrc sys_in, float lm,
                         float ep, int rows_doubles, float* dx_out, int* status_out) {
   namespace cg = cooperative_groups;
   extern __shared__ double smd[];
@@ -953,6 +1015,8 @@ ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restric
     peer_dloc[oq] = cluster.map_shared_rank(dloc, oq);
   }
 
+  // every CTA reads partial systems itself: each waits for the ranks' flags (no-op for a local system)
+  peer_wait(sys_in.flags, sys_in.n, sys_in.epoch, sys_in.timeout);
   // ---- load own rows (lower blocks incl. the diagonal one), damping on the diagonal
   for (int l = 0; l < nl; ++l) {
     const int r = q + l * kCl;
@@ -960,12 +1024,12 @@ ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restric
     const int width = 6 * (r + 1);
     for (int idx = tid; idx < 6 * width; idx += kClT) {
       const int a = idx / width, col = idx - a * width;
-      double val = sys_in[(size_t)(6 * r + a) * n + col];
+      double val = sys_at(sys_in, (size_t)(6 * r + a) * n + col);
       if (col == 6 * r + a) val += (double)ep + (double)lm * val;
       dst[(col / 6) * 36 + a * 6 + (col % 6)] = val;
     }
   }
-  for (int i = tid; i < n; i += kClT) { rhs[i] = sys_in[(size_t)n * n + i]; ps[i] = 0.0; }
+  for (int i = tid; i < n; i += kClT) { rhs[i] = sys_at(sys_in, (size_t)n * n + i); ps[i] = 0.0; }
   for (int i = tid; i < kCl * 6; i += kClT) inbox[i] = 0.0;
   if (tid == 0) failed = 0;
   // every CTA of the cluster must be running before anybody stores into its shared memory (compute-sanitizer:
@@ -1245,7 +1309,7 @@ ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const double* __restric
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ void backsub_tile(float* disps, const BaDims& d, const BaWs& ws,
                                              int owner_lo, int owner_hi, float* dz_out, int k,
-                                             int wt) {
+                                             int wt, const PeerRows* peers = nullptr) {
   const int f = ws.kx[k];
   if (f < owner_lo || f >= owner_hi) return;
   const int px = wt * 32 + (threadIdx.x & 31);
@@ -1272,14 +1336,19 @@ __device__ __forceinline__ void backsub_tile(float* disps, const BaDims& d, cons
   }
   const size_t o = (size_t)k * d.hw + px;
   const float dz = ws.Q[o] * (ws.w[o] - acc);
-  disps[(size_t)f * d.hw + px] += dz;
+  const float nv = disps[(size_t)f * d.hw + px] + dz;
+  disps[(size_t)f * d.hw + px] = nv;
+  if (peers)                                     // write-through into every other replica (P2P stores)
+    for (int r = 0; r < peers->n; ++r)
+      if (peers->p[r] != disps) peers->p[r][(size_t)f * d.hw + px] = nv;
   if (dz_out) dz_out[(size_t)f * d.hw + px] = dz;
 }
 
 __global__ void __launch_bounds__(kTP)
-ba_backsub_kernel(float* disps, BaDims d, BaWs ws, int owner_lo, int owner_hi, float* dz_out) {
+ba_backsub_kernel(float* disps, BaDims d, BaWs ws, int owner_lo, int owner_hi, float* dz_out, const PeerRows peers) {
   if ((int)blockIdx.y >= ws.counts[0] || ws.counts[4]) return;
-  backsub_tile(disps, d, ws, owner_lo, owner_hi, dz_out, blockIdx.y, blockIdx.x * (kTP / 32) + (threadIdx.x >> 5));
+  backsub_tile(disps, d, ws, owner_lo, owner_hi, dz_out, blockIdx.y, blockIdx.x * (kTP / 32) + (threadIdx.x >> 5),
+               peers.n > 1 ? &peers : nullptr);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1367,7 +1436,9 @@ ba_persistent_kernel(float* poses, float* disps, BaIn in, BaDims d, BaWs ws, int
     grid_barrier(barrier, epoch);
     BA_PROBE(4);
     if (blockIdx.x == 0) {
-      solve_small(poses, d, ws, ws.sys, lm, ep, dx_out, status_out ? status_out + it : nullptr, smd,
+      SysSrc local{};
+      local.p[0] = ws.sys; local.n = 1;
+      solve_small(poses, d, ws, local, lm, ep, dx_out, status_out ? status_out + it : nullptr, smd,
                   solve_sm);
       __syncthreads();
       for (size_t i = threadIdx.x; i < nsys; i += kTP) ws.sys[i] = 0.0;   // for the next iteration
@@ -1482,10 +1553,10 @@ int launch_phase1(const float* poses, const float* disps, const float* intr,
   return GOSLAM_OK;
 }
 
-int launch_phase2(float* poses, float* disps, const double* sys_in,
+int launch_phase2(float* poses, float* disps, const SysSrc& sys_in,
                   const BaDims& d, const BaWs& ws, float lm, float ep, int motion_only,
                   int owner_lo, int owner_hi, float* dx_out, float* dz_out, int* status_out,
-                  cudaStream_t st) {
+                  cudaStream_t st, const PeerRows& peer_rows = PeerRows{}) {
   const BaDevice& dv = ba_device();    // per-device function attributes are set on first use
   (void)dv;
   if (d.n <= kWarpSolveMaxN) {
@@ -1517,7 +1588,7 @@ int launch_phase2(float* poses, float* disps, const double* sys_in,
   GS_CHECK_LAUNCH();
   if (!motion_only) {
     dim3 grid(ws.ntiles, d.num);
-    ba_backsub_kernel<<<grid, kTP, 0, st>>>(disps, d, ws, owner_lo, owner_hi, dz_out);
+    ba_backsub_kernel<<<grid, kTP, 0, st>>>(disps, d, ws, owner_lo, owner_hi, dz_out, peer_rows);
     GS_CHECK_LAUNCH();
   }
   return GOSLAM_OK;
@@ -1583,7 +1654,9 @@ int goslam_ba(float* poses, float* disps, const float* intrinsics, const float* 
     int rc = launch_phase1(poses, disps, intrinsics, disps_sens, targets, weights, eta, eta_rows,
                            ii, jj, d, ws, motion_only, it == 0, st);
     if (rc) return rc;
-    rc = launch_phase2(poses, disps, ws.sys, d, ws, lm, ep, motion_only, 0, num, dx_out,
+    SysSrc local{};
+    local.p[0] = ws.sys; local.n = 1;
+    rc = launch_phase2(poses, disps, local, d, ws, lm, ep, motion_only, 0, num, dx_out,
                        dz_out, status_out ? status_out + it : nullptr, st);
     if (rc) return rc;
   }
@@ -1621,8 +1694,128 @@ int goslam_ba_phase2(float* poses, float* disps, const double* system, int N, in
   BaWs ws;
   const size_t need = ba_layout(d, workspace, workspace_bytes, &ws);
   if (workspace == nullptr || need > workspace_bytes) return GOSLAM_EWORKSPACE;
-  return launch_phase2(poses, disps, system, d, ws, lm, ep, motion_only, owner_lo, owner_hi, dx_out,
+  SysSrc local{};
+  local.p[0] = system; local.n = 1;
+  return launch_phase2(poses, disps, local, d, ws, lm, ep, motion_only, owner_lo, owner_hi, dx_out,
                        dz_out, status_out, (cudaStream_t)stream);
+}
+
+static bool peers_ok(const goslam_ba_peers* p) {
+  if (!p || p->world < 1 || p->world > kMaxPeers || p->rank < 0 || p->rank >= p->world || p->epoch == 0) return false;
+  for (int r = 0; r < p->world; ++r)
+    if (!p->system[r] || !p->flags[r] || !p->disps[r]) return false;
+  return true;
+}
+
+int goslam_ba_phase1_peers(const float* poses, const float* intrinsics, const float* disps_sens, const float* targets,
+                           const float* weights, const float* eta, int eta_rows, const int64_t* ii, const int64_t* jj,
+                           int N, int num, int ht, int wd, int t0, int t1, int motion_only,
+                           const goslam_ba_peers* peers, void* workspace, size_t workspace_bytes, void* stream) {
+  BaDims d;
+  if (!make_dims(N, num, ht, wd, t0, t1, &d) || !peers_ok(peers)) return GOSLAM_EINVAL;
+  if (d.P == 0) return GOSLAM_OK;
+  BaWs ws;
+  const size_t need = ba_layout(d, workspace, workspace_bytes, &ws);
+  if (workspace == nullptr || need > workspace_bytes) return GOSLAM_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int W = peers->world, me = peers->rank;
+  // (1) every rank has written the inverse-depth rows of the previous iteration into my replica, and has finished
+  //     reading my previous partial system (it signals slot [W + r] after its solve + back-substitution)
+  if (W > 1) {
+    ba_peer_wait_kernel<<<1, 32, 0, st>>>(peers->flags[me] + W, W, peers->epoch - 1, peers->timeout);
+    GS_CHECK_LAUNCH();
+  }
+  int rc = launch_phase1(poses, peers->disps[me], intrinsics, disps_sens, targets, weights, eta, eta_rows, ii, jj, d, ws,
+                         motion_only, true, st);
+  if (rc) return rc;
+  if (peers->system[me] != ws.sys)
+    cudaMemcpyAsync(peers->system[me], ws.sys, ((size_t)d.n * d.n + d.n) * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  // (2) publish: my partial system of iteration `epoch` is complete
+  if (W > 1) {
+    PeerRows rows{};
+    rows.n = W;
+    for (int r = 0; r < W; ++r) rows.p[r] = reinterpret_cast<float*>(peers->flags[r]);
+    ba_peer_signal_kernel<<<1, 32, 0, st>>>(rows, me, peers->epoch);
+    GS_CHECK_LAUNCH();
+  }
+  return GOSLAM_OK;
+}
+
+int goslam_ba_phase2_peers(float* poses, int N, int num, int ht, int wd, int t0, int t1, float lm, float ep,
+                           int motion_only, int owner_lo, int owner_hi, const goslam_ba_peers* peers, float* dx_out,
+                           float* dz_out, int* status_out, void* workspace, size_t workspace_bytes, void* stream) {
+  BaDims d;
+  if (!make_dims(N, num, ht, wd, t0, t1, &d) || !peers_ok(peers)) return GOSLAM_EINVAL;
+  if (d.P == 0) return GOSLAM_OK;
+  BaWs ws;
+  const size_t need = ba_layout(d, workspace, workspace_bytes, &ws);
+  if (workspace == nullptr || need > workspace_bytes) return GOSLAM_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int W = peers->world, me = peers->rank;
+  SysSrc src{};
+  src.n = W;
+  for (int r = 0; r < W; ++r) src.p[r] = peers->system[r];
+  src.flags = peers->flags[me]; src.epoch = peers->epoch; src.timeout = peers->timeout;
+  PeerRows rows{};
+  rows.n = W;
+  for (int r = 0; r < W; ++r) rows.p[r] = peers->disps[r];
+  const int rc = launch_phase2(poses, peers->disps[me], src, d, ws, lm, ep, motion_only, owner_lo, owner_hi, dx_out, dz_out,
+                               status_out, st, rows);
+  if (rc) return rc;
+  if (W > 1) {
+    PeerRows frows{};
+    frows.n = W;
+    for (int r = 0; r < W; ++r) frows.p[r] = reinterpret_cast<float*>(peers->flags[r]);
+    ba_peer_signal_kernel<<<1, 32, 0, st>>>(frows, W + me, peers->epoch);
+    GS_CHECK_LAUNCH();
+  }
+  return GOSLAM_OK;
+}
+
+int goslam_ba_peers_wait(const goslam_ba_peers* peers, void* stream) {
+  if (!peers_ok(peers)) return GOSLAM_EINVAL;
+  if (peers->world > 1) {
+    ba_peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(peers->flags[peers->rank] + peers->world, peers->world,
+                                                            peers->epoch, peers->timeout);
+    GS_CHECK_LAUNCH();
+  }
+  return GOSLAM_OK;
+}
+
+int goslam_peer_alloc(size_t bytes, void** ptr, void* handle_out) {
+  if (!ptr || !handle_out || bytes == 0) return GOSLAM_EINVAL;
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e == cudaSuccess) e = cudaMemset(q, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, q);
+  if (e != cudaSuccess) { gs_note_cuda_error(e); if (q) cudaFree(q); return GOSLAM_ELAUNCH; }
+  memcpy(handle_out, &h, sizeof(h));
+  *ptr = q;
+  return GOSLAM_OK;
+}
+
+int goslam_peer_free(void* ptr) {
+  if (!ptr) return GOSLAM_EINVAL;
+  const cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) { gs_note_cuda_error(e); return GOSLAM_ELAUNCH; }
+  return GOSLAM_OK;
+}
+
+int goslam_ipc_open(const void* handle, void** ptr) {
+  if (!handle || !ptr) return GOSLAM_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  const cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { gs_note_cuda_error(e); return GOSLAM_ELAUNCH; }
+  return GOSLAM_OK;
+}
+
+int goslam_ipc_close(void* ptr) {
+  if (!ptr) return GOSLAM_EINVAL;
+  const cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) { gs_note_cuda_error(e); return GOSLAM_ELAUNCH; }
+  return GOSLAM_OK;
 }
 
 }  // extern "C"

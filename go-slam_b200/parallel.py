@@ -100,6 +100,129 @@ class CudaBackend:
         return (dx, status) if return_status else dx
 
 
+class _PeerBuffer:
+    """a device allocation the other ranks can map (goslam_peer_alloc), viewed as a torch tensor through the CUDA array
+    interface (zero copy); freed when the object dies"""
+
+    def __init__(self, lib_mod, shape, dtype, device):
+        self._lib = lib_mod
+        self.shape, self.dtype = tuple(int(x) for x in shape), dtype
+        nbytes = max(1, int(torch.empty((), dtype=dtype).element_size() * int(torch.Size(self.shape).numel())))
+        ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            lib_mod.check(lib_mod.load().goslam_peer_alloc(ctypes.c_size_t(nbytes), ctypes.byref(ptr), handle), "peer_alloc")
+        self.ptr, self.handle, self.nbytes = int(ptr.value), bytes(handle), nbytes
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": typestr, "data": (self.ptr, False), "version": 2}
+        self.tensor = torch.as_tensor(self, device=device)
+
+    def __del__(self):
+        try:
+            self._lib.load().goslam_peer_free(ctypes.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+class PeerLink:
+    """Peer-memory plumbing of one sharded graph (one node, NVLink / NVSwitch), set up ONCE (collective call):
+    every rank allocates its partial-system buffer, its replica of disps and its flag words in IPC-shareable memory,
+    the 64-byte handles travel through one all_gather_object, and every rank maps the others' (goslam_ipc_open).
+    After that an iteration needs no collective and no host synchronisation (include/goslam_b200.h, goslam_ba_peers)."""
+
+    def __init__(self, disps_like, n_system, group=None):
+        from . import _lib
+        self._lib = _lib
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("peer-memory BA: at most 8 ranks (one NVSwitch node)")
+        dev = disps_like.device
+        self.system = _PeerBuffer(_lib, (int(n_system),), torch.float64, dev)
+        self.disps = _PeerBuffer(_lib, disps_like.shape, torch.float32, dev)
+        self.flags = _PeerBuffer(_lib, (2 * self.world,), torch.int32, dev)
+        self.timeout = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.disps.tensor.copy_(disps_like)
+        mine = {k: getattr(self, k).handle for k in ("system", "disps", "flags")}
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=group)
+        self._mapped = []
+        self.ptrs = {k: [0] * self.world for k in mine}
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            for r in range(self.world):
+                for k in mine:
+                    if r == self.rank:
+                        self.ptrs[k][r] = getattr(self, k).ptr
+                    else:
+                        q = ctypes.c_void_p()
+                        _lib.check(lib.goslam_ipc_open(handles[r][k], ctypes.byref(q)), "ipc_open")
+                        self.ptrs[k][r] = int(q.value)
+                        self._mapped.append(int(q.value))
+        self.epoch = 0
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)                 # every rank's buffers are zeroed and mapped before the first signal
+
+    def struct(self):
+        p = self._lib.BaPeers()
+        p.world, p.rank = self.world, self.rank
+        for r in range(self.world):
+            p.system[r] = self.ptrs["system"][r]
+            p.disps[r] = self.ptrs["disps"][r]
+            p.flags[r] = self.ptrs["flags"][r]
+        p.epoch = self.epoch
+        p.timeout = self.timeout.data_ptr()
+        return p
+
+    def wait_idle(self):
+        """stream-ordered: every rank has finished the last iteration (call before touching `disps.tensor` by hand)"""
+        if self.epoch > 0 and self.world > 1:
+            peers = self.struct()
+            with torch.cuda.device(self.timeout.device):
+                self._lib.check(self._lib.load().goslam_ba_peers_wait(ctypes.byref(peers), self._lib.stream_ptr()), "ba_peers_wait")
+
+    def close(self):
+        lib = self._lib.load()
+        torch.cuda.synchronize(self.timeout.device)
+        dist.barrier(group=self.group)            # nobody still reads my buffers
+        for q in self._mapped:
+            lib.goslam_ipc_close(ctypes.c_void_p(q))
+        self._mapped = []
+
+
+class PeerBackend(CudaBackend):
+    """goslam_ba_phase1_peers / goslam_ba_phase2_peers: the exchange steps of the split form are done by the kernels over
+    peer memory.  `link.disps.tensor` IS the replica of disps this backend reads and updates."""
+
+    def __init__(self, poses, link, intrinsics, disps_sens, t0, t1):
+        super().__init__(poses, link.disps.tensor, intrinsics, disps_sens, t0, t1)
+        self.link = link
+
+    def iteration(self, targets, weights, eta_by_frame, ii, jj, lm, ep, motion_only, owner_lo, owner_hi):
+        lib = self._lib.load()
+        self.N = int(ii.shape[0])
+        ws = self._workspace(self.N)
+        eta = eta_by_frame.reshape(self.num, -1)
+        if not eta.is_contiguous() or eta.dtype != torch.float32:
+            eta = eta.float().contiguous()
+        self.link.epoch += 1
+        peers = self.link.struct()
+        dev = self.poses.device
+        dx = torch.empty((self.t1 - self.t0, 6), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.goslam_ba_phase1_peers(
+                self._lib.ptr(self.poses), self._lib.ptr(self.intr), self._lib.ptr(self.sens), self._lib.ptr(targets),
+                self._lib.ptr(weights), self._lib.ptr(eta), -int(eta.shape[0]), self._lib.ptr(ii), self._lib.ptr(jj), self.N,
+                self.num, self.ht, self.wd, self.t0, self.t1, int(bool(motion_only)), ctypes.byref(peers), self._lib.ptr(ws),
+                ctypes.c_size_t(ws.numel()), self._lib.stream_ptr())
+            self._lib.check(rc, "ba_phase1_peers")
+            rc = lib.goslam_ba_phase2_peers(
+                self._lib.ptr(self.poses), self.N, self.num, self.ht, self.wd, self.t0, self.t1, float(lm), float(ep),
+                int(bool(motion_only)), int(owner_lo), int(owner_hi), ctypes.byref(peers), self._lib.ptr(dx), None, None,
+                self._lib.ptr(ws), ctypes.c_size_t(ws.numel()), self._lib.stream_ptr())
+            self._lib.check(rc, "ba_phase2_peers")
+        return dx
+
+
 class RowExchange:
     """Re-replication of the disparity rows each rank owns after the back-substitution: ONE
     all-gather of [max_rows, hw] per rank (frame ranges are balanced by edge count, so they are padded
@@ -170,23 +293,35 @@ class ShardedGraph:
     Edges are assigned by source frame (`shard_frames_by_edges`), state (poses, disps, intrinsics, sensor
     depth, feature maps) is replicated; every rank ends each update with identical poses and disps."""
 
-    def __init__(self, poses, disps, intrinsics_all, disps_sens, fmaps, ii, jj, t0, t1, group=None):
+    def __init__(self, poses, disps, intrinsics_all, disps_sens, fmaps, ii, jj, t0, t1, group=None, exchange="nccl"):
+        """exchange = "nccl": all-reduce + all-gather per iteration (any backend torch.distributed has);
+        exchange = "peer": the BA kernels exchange over peer memory themselves (one node; PeerLink) — then `self.disps` is
+        the peer-mapped replica (a copy of the `disps` passed in), not the caller's tensor."""
         from .modules.corr import AltCorrBlock
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.link = None
+        if exchange == "peer" and self.world > 1:
+            from . import _lib
+            n_sys = _lib.load().goslam_ba_system_doubles(int(t0), int(t1))
+            self.link = PeerLink(disps, n_sys, group)
+            disps = self.link.disps.tensor
         self.poses, self.disps, self.intr_all = poses, disps, intrinsics_all
         num = disps.shape[0]
         self.bounds = shard_frames_by_edges(ii, num, self.world)
         self.lo, self.hi = self.bounds[self.rank]
         self.sel = local_edges(ii, self.lo, self.hi)
         self.ii, self.jj = ii[self.sel].contiguous(), jj[self.sel].contiguous()
-        self.backend = CudaBackend(poses, disps, intrinsics_all[0].contiguous(), disps_sens, t0, t1)
+        if self.link is not None:
+            self.backend = PeerBackend(poses, self.link, intrinsics_all[0].contiguous(), disps_sens, t0, t1)
+        else:
+            self.backend = CudaBackend(poses, disps, intrinsics_all[0].contiguous(), disps_sens, t0, t1)
         f, rig, ch, ht, wd = fmaps.shape
         self.rig = rig
         self.corr_op = AltCorrBlock(fmaps.view(1, f * rig, ch, ht, wd))
         self.f1 = (rig * self.ii).contiguous()
         self.f2 = (rig * self.jj + (self.ii == self.jj).long()).contiguous()
-        self.exchange = RowExchange(disps, self.bounds, self.rank) if self.world > 1 else None
+        self.exchange = RowExchange(disps, self.bounds, self.rank) if self.world > 1 and self.link is None else None
 
     def local(self, per_edge):
         """this rank's slice of a replicated per-edge tensor [N, ...]"""
@@ -201,6 +336,11 @@ class ShardedGraph:
 
     def bundle_adjust(self, target_planar_local, weight_planar_local, eta_by_frame, iters, lm, ep, motion_only=False):
         dx = None
+        if self.link is not None:
+            for _ in range(iters):
+                dx = self.backend.iteration(target_planar_local, weight_planar_local, eta_by_frame, self.ii, self.jj, lm, ep,
+                                            motion_only, self.lo, self.hi)
+            return dx
         for _ in range(iters):
             system = self.backend.phase1(target_planar_local, weight_planar_local, eta_by_frame, self.ii, self.jj,
                                          motion_only)

@@ -216,6 +216,48 @@ int goslam_ba_phase2(float* poses, float* disps, const double* system,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * The split form over PEER MEMORY (one node, NVLink / NVSwitch): what SURVEY 8e asks NCCL for — one all-reduce of the
+ * reduced camera system and one all-gather of the owned inverse-depth rows per Gauss-Newton iteration — done by the
+ * BA kernels themselves.  Every rank keeps its partial system, its replica of disps and a row of flag words in buffers
+ * the other ranks have mapped (goslam_ipc_open on a CUDA IPC handle; the host side exchanges the handles once).
+ *   phase1_peers: waits (on the device) until every rank has finished iteration epoch-1, linearises the local edges,
+ *                 leaves the partial system in system[rank] and raises flag [rank] on every rank.
+ *   phase2_peers: the solve kernel waits for all flags and sums the partial systems IN RANK ORDER while it loads the
+ *                 matrix into shared memory (every rank factors bit-identical numbers), retracts the poses, and the
+ *                 back-substitution writes the rows of frames [owner_lo, owner_hi) into every replica of disps; then
+ *                 raises flag [world + rank] on every rank.
+ * No host synchronisation, no collective library call.  A wait that sees no progress for ~2 s sets *timeout = 1 and
+ * continues (a dead peer must not hang the GPU); the caller checks it.
+ *   flags[r]: u32 [2 * world] in rank r's memory, zero before the first call; epoch: >= 1, +1 per iteration, the same
+ *   on all ranks, never reused.  disps[rank] is the local replica the kernels read and update. */
+typedef struct goslam_ba_peers {
+  int world, rank;
+  double* system[8];
+  float* disps[8];
+  unsigned* flags[8];
+  unsigned epoch;
+  int* timeout;            /* local device int (may be NULL) */
+} goslam_ba_peers;
+int goslam_ba_phase1_peers(const float* poses, const float* intrinsics, const float* disps_sens,
+                           const float* targets, const float* weights, const float* eta, int eta_rows,
+                           const int64_t* ii, const int64_t* jj, int N, int num, int ht, int wd, int t0, int t1,
+                           int motion_only, const goslam_ba_peers* peers, void* workspace, size_t workspace_bytes,
+                           void* stream);
+int goslam_ba_phase2_peers(float* poses, int N, int num, int ht, int wd, int t0, int t1, float lm, float ep,
+                           int motion_only, int owner_lo, int owner_hi, const goslam_ba_peers* peers, float* dx_out,
+                           float* dz_out, int* status_out, void* workspace, size_t workspace_bytes, void* stream);
+/* stream-ordered wait until every rank has finished iteration peers->epoch (its rows are in my replica, it no longer
+ * reads my partial system): what a caller puts before it touches its replica of disps outside the BA calls */
+int goslam_ba_peers_wait(const goslam_ba_peers* peers, void* stream);
+/* a zero-filled device allocation other processes can map (cudaMalloc + cudaIpcGetMemHandle): handle_out gets the 64-byte
+ * CUDA IPC handle to send to the peers */
+int goslam_peer_alloc(size_t bytes, void** ptr, void* handle_out);
+int goslam_peer_free(void* ptr);
+/* map / unmap a peer process's device allocation from its 64-byte CUDA IPC handle (cudaIpcOpenMemHandle) */
+int goslam_ipc_open(const void* handle, void** ptr);
+int goslam_ipc_close(void* ptr);
+
+/* ------------------------------------------------------------------------------------
  * Hash-grid neural-surface ray marcher.  Replaces InstantNeuS.forward
  * (src/InstantNeuS.py:295-370) incl. tiny-cuda-nn HashGrid + FullyFusedMLP
  * (src/InstantNeuS.py:44-66,184-205), SDFNetwork.sdf + autograd normal (:97-160),
