@@ -596,14 +596,16 @@ struct PeerRows {
   int n;
 };
 
+// Plain loads: the peers' buffers were last written before the flags this kernel acquired in peer_wait (whose asm
+// "memory" clobbers + barrier keep these loads behind it), L1 holds nothing of them at kernel start, and plain loads let
+// the compiler issue all ranks' (and the unrolled neighbours') loads before the first add — a peer load is ~1 us.
 __device__ __forceinline__ double sys_at(const SysSrc& s, size_t i) {
-  if (s.n <= 1) return s.p[0][i];
-  double v = 0.0;
-  for (int r = 0; r < s.n; ++r) {
-    double x;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(s.p[r] + i) : "memory");
-    v += x;
-  }
+  double x[kMaxPeers];
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r) x[r] = r < s.n ? __ldcg(s.p[r] + i) : 0.0;
+  double v = x[0];
+#pragma unroll
+  for (int r = 1; r < kMaxPeers; ++r) v += x[r];          // rank order; + 0.0 for absent ranks does not change the sum
   return v;
 }
 
@@ -1022,6 +1024,7 @@ ba_solve_cluster_kernel(float* poses, BaDims d, BaWs ws, const SysSrc sys_in, fl
     const int r = q + l * kCl;
     double* dst = rows + cl_row_off(q, l);
     const int width = 6 * (r + 1);
+#pragma unroll 4
     for (int idx = tid; idx < 6 * width; idx += kClT) {
       const int a = idx / width, col = idx - a * width;
       double val = sys_at(sys_in, (size_t)(6 * r + a) * n + col);
