@@ -844,45 +844,69 @@ __global__ void __launch_bounds__(256) neus_grid_bwd_kernel(const GridBwdArgs a)
   }
   const __half2* table = reinterpret_cast<const __half2*>(a.p.grid);
   float2* gg = reinterpret_cast<float2*>(a.grid_grad);
+  // Two levels per trip: the 16 table gathers and the two dL/d(enc) pairs of both levels are in flight before the first
+  // dependent instruction (ncu on the one-level-per-trip version: long_scoreboard 78 stalled warps per issue, no unit
+  // above 35 % — latency bound).  All gathers are read-only (ld.global.nc), the scatters are fire-and-forget RED.
 #pragma unroll 1
-  for (int l = 0; l < kLevels; ++l) {
-    float t0 = 0.f, t1 = 0.f;
+  for (int l0 = 0; l0 < kLevels; l0 += 2) {
+    float fr[2][3], sc2[2];
+    unsigned idx[2][8], off2[2];
+    __half2 v[2][8];
+    float2 de[2];
     if (act) {
-      const LevelConst L = c_lvl[l];
-      float fr[3]; unsigned pg[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float pos = fmaf(L.scale, x01[c], 0.5f);
-        const float fl = floorf(pos);
-        pg[c] = (unsigned)fl; fr[c] = pos - fl;
-      }
-      // what the forward multiplies this level's input gradient with: dL/dy of the sdf output, rounded to half (tcnn)
-      const float gy0 = __half2float(__float2half_rn(a.p.sdf_w[3 + 2 * l]));
-      const float gy1 = __half2float(__float2half_rn(a.p.sdf_w[3 + 2 * l + 1]));
-      const float de0 = a.d_enc[i * 32 + 2 * l], de1 = a.d_enc[i * 32 + 2 * l + 1];
-      const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
+      for (int u = 0; u < 2; ++u) {
+        const int l = l0 + u;
+        const LevelConst L = c_lvl[l];
+        unsigned pg[3];
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        const int bx = c8 & 1, by = (c8 >> 1) & 1, bz = (c8 >> 2) & 1;
-        unsigned idx;
-        if (l >= kDenseLevels) {
-          idx = ((pg[0] + bx) ^ ((pg[1] + by) * 2654435761u) ^ ((pg[2] + bz) * 805459861u)) & 0x7FFFFu;
-        } else {
-          idx = (pg[0] + bx) + (pg[1] + by) * L.res + (pg[2] + bz) * L.res2;
-          idx = idx >= L.size ? idx - L.size : idx;
+        for (int c = 0; c < 3; ++c) {
+          const float pos = fmaf(L.scale, x01[c], 0.5f);
+          const float fl = floorf(pos);
+          pg[c] = (unsigned)fl; fr[u][c] = pos - fl;
         }
-        const float w = (wx[bx] * wy[by]) * wz[bz];
-        // q . grad_u(w_c): +/- the product of the other two axes' weights
-        const float sdot = L.scale * ((bx ? q[0] : -q[0]) * (wy[by] * wz[bz]) + (by ? q[1] : -q[1]) * (wx[bx] * wz[bz]) +
-                                      (bz ? q[2] : -q[2]) * (wx[bx] * wy[by]));
-        const float2 v = __half22float2(__ldg(table + L.offset + idx));
-        t0 = fmaf(v.x, sdot, t0); t1 = fmaf(v.y, sdot, t1);
-        const float c0 = fmaf(de0, w, gy0 * sdot), c1 = fmaf(de1, w, gy1 * sdot);
-        if (c0 != 0.f || c1 != 0.f) atomicAdd(gg + L.offset + idx, make_float2(c0, c1));
+        sc2[u] = L.scale; off2[u] = L.offset;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const int bx = c8 & 1, by = (c8 >> 1) & 1, bz = (c8 >> 2) & 1;
+          unsigned ix;
+          if (l >= kDenseLevels) {
+            ix = ((pg[0] + bx) ^ ((pg[1] + by) * 2654435761u) ^ ((pg[2] + bz) * 805459861u)) & 0x7FFFFu;
+          } else {
+            ix = (pg[0] + bx) + (pg[1] + by) * L.res + (pg[2] + bz) * L.res2;
+            ix = ix >= L.size ? ix - L.size : ix;
+          }
+          idx[u][c8] = ix;
+          v[u][c8] = __ldg(table + L.offset + ix);
+        }
+        de[u] = __ldg(reinterpret_cast<const float2*>(a.d_enc + i * 32 + 2 * l));
       }
     }
-    t0 = gs_warp_sum(t0); t1 = gs_warp_sum(t1);
-    if (lane == 0 && (t0 != 0.f || t1 != 0.f)) { atomicAdd(a.d_w0 + 3 + 2 * l, t0); atomicAdd(a.d_w0 + 3 + 2 * l + 1, t1); }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int l = l0 + u;
+      float t0 = 0.f, t1 = 0.f;
+      if (act) {
+        // what the forward multiplies this level's input gradient with: dL/dy of the sdf output, rounded to half (tcnn)
+        const float gy0 = __half2float(__float2half_rn(a.p.sdf_w[3 + 2 * l]));
+        const float gy1 = __half2float(__float2half_rn(a.p.sdf_w[3 + 2 * l + 1]));
+        const float wx[2] = {1.f - fr[u][0], fr[u][0]}, wy[2] = {1.f - fr[u][1], fr[u][1]}, wz[2] = {1.f - fr[u][2], fr[u][2]};
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const int bx = c8 & 1, by = (c8 >> 1) & 1, bz = (c8 >> 2) & 1;
+          const float w = (wx[bx] * wy[by]) * wz[bz];
+          // q . grad_u(w_c): +/- the product of the other two axes' weights
+          const float sdot = sc2[u] * ((bx ? q[0] : -q[0]) * (wy[by] * wz[bz]) + (by ? q[1] : -q[1]) * (wx[bx] * wz[bz]) +
+                                       (bz ? q[2] : -q[2]) * (wx[bx] * wy[by]));
+          const float2 vf = __half22float2(v[u][c8]);
+          t0 = fmaf(vf.x, sdot, t0); t1 = fmaf(vf.y, sdot, t1);
+          const float c0 = fmaf(de[u].x, w, gy0 * sdot), c1 = fmaf(de[u].y, w, gy1 * sdot);
+          if (c0 != 0.f || c1 != 0.f) atomicAdd(gg + off2[u] + idx[u][c8], make_float2(c0, c1));
+        }
+      }
+      t0 = gs_warp_sum(t0); t1 = gs_warp_sum(t1);
+      if (lane == 0 && (t0 != 0.f || t1 != 0.f)) { atomicAdd(a.d_w0 + 3 + 2 * l, t0); atomicAdd(a.d_w0 + 3 + 2 * l + 1, t1); }
+    }
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {

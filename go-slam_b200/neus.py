@@ -366,16 +366,22 @@ class _NeusFunction(torch.autograd.Function):
                 dY = torch.zeros(n, 8, **f16)
                 dY[:, :3] = d_y * sc
                 g_W3[:8] += torch.mm(dY.t(), H2, out_dtype=torch.float32) / sc
-                dH2 = (dY @ W3[:8]) * (H2 > 0)
+                relu_bwd = torch.ops.aten.threshold_backward                         # grad where activation > 0, one kernel
+                dH2 = relu_bwd(dY @ W3[:8], H2, 0)
                 g_W2 += torch.mm(dH2.t(), H1, out_dtype=torch.float32) / sc
-                dH1 = (dH2 @ W2) * (H1 > 0)
+                dH1 = relu_bwd(dH2 @ W2, H1, 0)
                 del dH2, H2
                 g_W1 += torch.mm(dH1.t(), X, out_dtype=torch.float32) / sc
                 dX = dH1 @ W1                                                          # [n, 80] half, scaled
                 del dH1, H1
                 # ---- colour embedding sin(pts @ B) ----
                 pts = (ro[:, None, :] + rd[:, None, :] * z_mid[sl][:, :, None]).reshape(n, 3)
-                g_B += (pts.t() @ (dX[:, :33].float() * torch.cos(pts @ colB))) / sc
+                dE = torch.zeros(n, 40, **f16)                                        # 33 columns padded to a multiple of 8
+                dE[:, :33] = dX[:, :33] * torch.cos(pts @ colB).half()
+                pt8 = torch.zeros(2, n, 8, **f16)                                     # pts as fp16 hi + lo parts (exact to 2^-22)
+                pt8[0, :, :3] = pts
+                pt8[1, :, :3] = pts - pt8[0, :, :3].float()
+                g_B += (torch.mm(pt8[0].t(), dE, out_dtype=torch.float32) + torch.mm(pt8[1].t(), dE, out_dtype=torch.float32))[:3, :33] / sc
                 # ---- sdf_layer: out = W h + b, h = [xn | enc]; sdf = out[0], feat = out[1:] ----
                 d_out = torch.empty(n, 32, **f16)
                 d_out[:, 0] = d_s * sc

@@ -53,6 +53,22 @@ def main():
             p4, d4 = D4["poses"].clone(), D4["disps"].clone()
             droid_backends.ba(p4, d4, D4["intrinsics"][0].contiguous(), D4["disps_sens"], tg, wg, eta, D4["ii"], D4["jj"], 1, num_kf,
                               2, 1e-5, 1e-2, False)
+    if what == "mapping":                          # renderer backward: forward under grad + loss + backward
+        from goslam_b200 import synthetic
+        net, _, _ = bench.make_renderer(dev, 43)
+        R = 1 << 14
+        ro, rd_, zv, ds = [t.to(dev) for t in synthetic.make_rays(R, S=bench.SAMPLES, seed=47)]
+        gg = torch.Generator().manual_seed(5)
+        rc = torch.rand(R, 3, generator=gg).to(dev)
+        depth = (0.5 + 2.5 * torch.rand(R, 1, generator=gg)).to(dev)
+        for _ in range(reps):
+            for prm in net.parameters():
+                prm.grad = None
+            with torch.enable_grad():
+                o = net(ro, rd_, zv, ds)
+                sl, spl = net.compute_sdf_error(sdf=o["sdf"], z_vals=o["z_vals"], gt_depth=depth)
+                total = 2.0 * torch.abs(o["color"] - rc).mean() + torch.abs(o["depth"] - depth).mean() + 2.0 * (sl + spl) + 0.1 * o["gradient_error"].mean()
+            total.backward()
     if what in ("neus", "all"):
         bench.RAYS = 1 << 16
         net, rays, _ = bench.make_renderer(dev, 43)
