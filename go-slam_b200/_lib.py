@@ -34,6 +34,10 @@ class NeusOut(ctypes.Structure):
     ]
 
 
+class NeusMlpBwdOut(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("H1", "H2", "dH1", "dH2", "dY8", "dE", "d_out", "h", "pts_hl", "d_grad_total")]
+
+
 class BaPeers(ctypes.Structure):
     _fields_ = [("world", c_int), ("rank", c_int), ("system", c_void_p * 8), ("disps", c_void_p * 8), ("flags", c_void_p * 8),
                 ("epoch", ctypes.c_uint), ("timeout", c_void_p)]
@@ -104,7 +108,9 @@ SIGNATURES = {
                             [ctypes.POINTER(NeusOut), c_void_p, c_size_t, c_void_p]),
     "goslam_neus_composite_backward": (c_int, [ctypes.POINTER(NeusParams)] + [c_void_p] * 12 + [c_int64, c_int, c_int] +
                                        [c_void_p] * 5),
-    "goslam_neus_grid_backward": (c_int, [ctypes.POINTER(NeusParams)] + [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 5),
+    "goslam_neus_grid_backward": (c_int, [ctypes.POINTER(NeusParams)] + [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 6),
+    "goslam_neus_mlp_backward": (c_int, [ctypes.POINTER(NeusParams)] + [c_void_p] * 10 + [c_int, c_int] +
+                                 [ctypes.POINTER(NeusMlpBwdOut), c_void_p]),
     "goslam_hashgrid_layout": (c_int64, [c_void_p, c_void_p, c_void_p]),
     "goslam_sample_z": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "goslam_cvx_upsample": (c_int, [c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_void_p]),

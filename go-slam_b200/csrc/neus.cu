@@ -803,10 +803,12 @@ __global__ void __launch_bounds__(256) neus_composite_bwd_kernel(const CompBwdAr
   if (lane == 0 && dinv != 0.f) atomicAdd(a.d_inv_s, dinv);
 }
 
+constexpr int kAggLevels = 8;      // levels whose scatter is reduced over runs of lanes in the same cell first
 struct GridBwdArgs {
   goslam_neus_params p;
   const float* rays_o; const float* rays_d; const float* z_vals; const float* dists;
-  const float* d_enc;                // [n,32]
+  const float* d_enc;                // [n,32]  (times *d_enc_scale when that pointer is set)
+  const float* d_enc_scale;          // device scalar or null
   const float* d_grad;               // [n,3]   dL/d normal (all paths)
   float* grid_grad;                  // [entries*2], accumulated
   float* d_w0;                       // [35] dL/dW_sdf[0,:] through the normal, accumulated
@@ -844,13 +846,14 @@ __global__ void __launch_bounds__(256) neus_grid_bwd_kernel(const GridBwdArgs a)
   }
   const __half2* table = reinterpret_cast<const __half2*>(a.p.grid);
   float2* gg = reinterpret_cast<float2*>(a.grid_grad);
+  const float esc = a.d_enc_scale ? 1.0f / __ldg(a.d_enc_scale) : 1.0f;
   // Two levels per trip: the 16 table gathers and the two dL/d(enc) pairs of both levels are in flight before the first
   // dependent instruction (ncu on the one-level-per-trip version: long_scoreboard 78 stalled warps per issue, no unit
   // above 35 % — latency bound).  All gathers are read-only (ld.global.nc), the scatters are fire-and-forget RED.
 #pragma unroll 1
   for (int l0 = 0; l0 < kLevels; l0 += 2) {
     float fr[2][3], sc2[2];
-    unsigned idx[2][8], off2[2];
+    unsigned idx[2][8], off2[2], cell[2] = {0xffffffffu, 0xffffffffu};
     __half2 v[2][8];
     float2 de[2];
     if (act) {
@@ -866,6 +869,7 @@ __global__ void __launch_bounds__(256) neus_grid_bwd_kernel(const GridBwdArgs a)
           pg[c] = (unsigned)fl; fr[u][c] = pos - fl;
         }
         sc2[u] = L.scale; off2[u] = L.offset;
+        cell[u] = pg[0] + 4099u * pg[1] + 16785407u * pg[2];          // injective for pg < 4099 (res <= 4096)
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8) {
           const int bx = c8 & 1, by = (c8 >> 1) & 1, bz = (c8 >> 2) & 1;
@@ -880,12 +884,29 @@ __global__ void __launch_bounds__(256) neus_grid_bwd_kernel(const GridBwdArgs a)
           v[u][c8] = __ldg(table + L.offset + ix);
         }
         de[u] = __ldg(reinterpret_cast<const float2*>(a.d_enc + i * 32 + 2 * l));
+        de[u].x *= esc; de[u].y *= esc;
       }
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int l = l0 + u;
       float t0 = 0.f, t1 = 0.f;
+      // Consecutive samples of a ray sit in the same cell of the coarser levels (the 48 surface samples of a ray are ~1 cm
+      // apart, a level-5 cell is 4 cm): runs of lanes with the same cell reduce their contributions with a segmented warp
+      // scan and only the last lane of a run issues the 8 reductions.  Levels >= kAggLevels scatter directly.
+      const bool agg = l < kAggLevels;
+      unsigned run_id = 0;
+      bool tail = true;
+      if (agg) {                                             // warp-uniform
+        const unsigned key = act ? cell[u] : 0xfffffffeu - (unsigned)lane;      // inactive lanes: runs of their own
+        const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+        run_id = __popc(heads & (0xffffffffu >> (31 - lane)));
+        tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+      }
+      float cc0[8], cc1[8];
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) { cc0[c8] = 0.f; cc1[c8] = 0.f; }
       if (act) {
         // what the forward multiplies this level's input gradient with: dL/dy of the sdf output, rounded to half (tcnn)
         const float gy0 = __half2float(__float2half_rn(a.p.sdf_w[3 + 2 * l]));
@@ -900,9 +921,25 @@ __global__ void __launch_bounds__(256) neus_grid_bwd_kernel(const GridBwdArgs a)
                                        (bz ? q[2] : -q[2]) * (wx[bx] * wy[by]));
           const float2 vf = __half22float2(v[u][c8]);
           t0 = fmaf(vf.x, sdot, t0); t1 = fmaf(vf.y, sdot, t1);
-          const float c0 = fmaf(de[u].x, w, gy0 * sdot), c1 = fmaf(de[u].y, w, gy1 * sdot);
-          if (c0 != 0.f || c1 != 0.f) atomicAdd(gg + off2[u] + idx[u][c8], make_float2(c0, c1));
+          cc0[c8] = fmaf(de[u].x, w, gy0 * sdot); cc1[c8] = fmaf(de[u].y, w, gy1 * sdot);
         }
+      }
+      if (agg) {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const unsigned rid = __shfl_up_sync(0xffffffffu, run_id, off);
+          const bool take = lane >= off && rid == run_id;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const float x0 = __shfl_up_sync(0xffffffffu, cc0[c8], off), x1 = __shfl_up_sync(0xffffffffu, cc1[c8], off);
+            if (take) { cc0[c8] += x0; cc1[c8] += x1; }
+          }
+        }
+      }
+      if (act && tail) {
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8)
+          if (cc0[c8] != 0.f || cc1[c8] != 0.f) atomicAdd(gg + off2[u] + idx[u][c8], make_float2(cc0[c8], cc1[c8]));
       }
       t0 = gs_warp_sum(t0); t1 = gs_warp_sum(t1);
       if (lane == 0 && (t0 != 0.f || t1 != 0.f)) { atomicAdd(a.d_w0 + 3 + 2 * l, t0); atomicAdd(a.d_w0 + 3 + 2 * l + 1, t1); }
@@ -912,6 +949,228 @@ __global__ void __launch_bounds__(256) neus_grid_bwd_kernel(const GridBwdArgs a)
   for (int c = 0; c < 3; ++c) {
     const float v = gs_warp_sum(dw_xyz[c]);
     if (lane == 0 && v != 0.f) atomicAdd(a.d_w0 + c, v);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// neus_mlp_bwd_kernel — the row-wise half of the colour network's backward in ONE pass per 32-sample warp tile:
+// recompute H1 = relu(X W1^T), H2 = relu(H1 W2^T) from the input rows the forward kept, then
+//   dH2 = (dY W3) . [H2 > 0],  dH1 = (dH2 W2) . [H1 > 0],  dX = dH1 W1
+// on mma.sync (fp16 operands scaled by the loss scale, fp32 accumulation), and everything that hangs off dX per sample:
+// the embedding gradient dE = dX[:33] cos(p B), dL/d normal (+ the alpha / eikonal part), dL/d(sdf_layer output), the
+// sdf_layer input row h = [x | enc | 1] and the fp16 hi/lo split of the positions.  What is left for cuBLAS are the five
+// weight-gradient GEMMs over the sample dimension (A^T B with K = n) and dL/d enc = d_out W_sdf.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kMbWarps = 8;
+constexpr int kW3TPad = 24;          // W3^T row: 16 outputs + padding (48 B rows keep ldmatrix conflict-free)
+struct MlpBwdSlab {
+  alignas(16) __half a[32 * kInPad];       // X -> dH2 -> dX
+  alignas(16) __half b[32 * kHidPad];      // H1
+  alignas(16) __half c[32 * kHidPad];      // H2 -> dH1
+  alignas(16) __half dy[32 * kW3TPad];     // dY (16 columns, 3 used)
+};
+struct MlpBwdSmem {
+  alignas(16) __half W1[kHid * kInPad];        // [64][80]
+  alignas(16) __half W2[kHid * kHidPad];       // [64][64]
+  alignas(16) __half W3T[kHid * kW3TPad];      // [64][16]  = W3^T
+  alignas(16) __half W2T[kHid * kHidPad];      // [64][64]  = W2^T
+  alignas(16) __half W1T[kIn * kHidPad];       // [80][64]  = W1^T
+  float colB[3 * 33];
+  MlpBwdSlab slab[kMbWarps];
+};
+struct MlpBwdArgs {
+  const __half* mlp_w; const float* color_B;
+  const __half* X;                 // [n,80]
+  const __half* enc;               // [n,32]
+  const float* pos;                // [n,3] normalised position
+  const float* d_y;                // [n,3]
+  const float* d_s;                // [n]
+  const float* d_g;                // [n,3]
+  const float* rays_o; const float* rays_d; const float* z_mid;
+  const float* scale;              // device scalar (power of two)
+  __half* H1; __half* H2; __half* dH1; __half* dH2;    // [n,64]
+  __half* dY8;                     // [n,8]
+  __half* dE;                      // [n,40]
+  __half* d_out;                   // [n,32]
+  __half* h;                       // [n,40]: x(3) | enc(32) | 1 | 0...
+  __half* pts_hl;                  // [n,8]: hi(3) | lo(3) | 0 0
+  float* d_gt;                     // [n,3]
+  long long n; int S;
+};
+
+template <int NT, int LD>
+__device__ __forceinline__ void store_masked_half(const float (&acc)[2][NT][4], const __half* act, __half* out, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = nt * 8 + 2 * t;
+      const float2 m0 = __half22float2(*reinterpret_cast<const __half2*>(act + (mt * 16 + g) * LD + col));
+      const float2 m1 = __half22float2(*reinterpret_cast<const __half2*>(act + (mt * 16 + g + 8) * LD + col));
+      const __half2 lo = __floats2half2_rn(m0.x > 0.f ? acc[mt][nt][0] : 0.f, m0.y > 0.f ? acc[mt][nt][1] : 0.f);
+      const __half2 hi = __floats2half2_rn(m1.x > 0.f ? acc[mt][nt][2] : 0.f, m1.y > 0.f ? acc[mt][nt][3] : 0.f);
+      *reinterpret_cast<__half2*>(out + (mt * 16 + g) * LD + col) = lo;
+      *reinterpret_cast<__half2*>(out + (mt * 16 + g + 8) * LD + col) = hi;
+    }
+}
+
+template <int NT, int LD>
+__device__ __forceinline__ void store_half(const float (&acc)[2][NT][4], __half* out, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = nt * 8 + 2 * t;
+      *reinterpret_cast<__half2*>(out + (mt * 16 + g) * LD + col) = __floats2half2_rn(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<__half2*>(out + (mt * 16 + g + 8) * LD + col) = __floats2half2_rn(acc[mt][nt][2], acc[mt][nt][3]);
+    }
+}
+
+// copy `bytes` (a multiple of 16) of this lane's row between shared and global memory
+__device__ __forceinline__ void copy_row16(void* dst, const void* src, int bytes) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  for (int v = 0; v < bytes / 16; ++v) d[v] = s[v];
+}
+
+__global__ void __launch_bounds__(kMbWarps * 32, 1) neus_mlp_bwd_kernel(const MlpBwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MlpBwdSmem& sm = *reinterpret_cast<MlpBwdSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const __half* w = a.mlp_w;
+    for (int i = tid; i < kHid * kIn; i += kMbWarps * 32) {
+      const int o = i / kIn, k = i % kIn;
+      sm.W1[o * kInPad + k] = w[i];
+      sm.W1T[k * kHidPad + o] = w[i];
+    }
+    for (int i = tid; i < kHid * kHid; i += kMbWarps * 32) {
+      const int o = i / kHid, k = i % kHid;
+      sm.W2[o * kHidPad + k] = w[kHid * kIn + i];
+      sm.W2T[k * kHidPad + o] = w[kHid * kIn + i];
+    }
+    for (int i = tid; i < kOutW * kHid; i += kMbWarps * 32) {
+      const int o = i / kHid, k = i % kHid;
+      sm.W3T[k * kW3TPad + o] = w[kHid * kIn + kHid * kHid + i];
+    }
+    for (int i = tid; i < kHid * (kW3TPad - kOutW); i += kMbWarps * 32)
+      sm.W3T[(i / (kW3TPad - kOutW)) * kW3TPad + kOutW + i % (kW3TPad - kOutW)] = __float2half_rn(0.f);
+    for (int i = tid; i < 99; i += kMbWarps * 32) sm.colB[i] = a.color_B[i];
+  }
+  __syncthreads();
+  MlpBwdSlab& sl = sm.slab[warp];
+  const float sc = __ldg(a.scale), inv_sc = 1.0f / sc;
+  const long long ntiles = (a.n + 31) / 32;
+  for (long long tile = (long long)blockIdx.x * kMbWarps + warp; tile < ntiles; tile += (long long)gridDim.x * kMbWarps) {
+    const long long i = tile * 32 + lane;
+    const bool valid = i < a.n;
+    // ---- stage X and dY ----
+    __half* xrow = sl.a + lane * kInPad;
+    if (valid) {
+      copy_row16(xrow, a.X + i * kIn, kIn * 2);
+    } else {
+      for (int k = 0; k < kIn; k += 8) *reinterpret_cast<uint4*>(xrow + k) = make_uint4(0, 0, 0, 0);
+    }
+    {
+      __half* dyr = sl.dy + lane * kW3TPad;
+      float y0 = 0.f, y1 = 0.f, y2 = 0.f;
+      if (valid) { y0 = a.d_y[i * 3] * sc; y1 = a.d_y[i * 3 + 1] * sc; y2 = a.d_y[i * 3 + 2] * sc; }
+      *reinterpret_cast<__half2*>(dyr) = __floats2half2_rn(y0, y1);
+      *reinterpret_cast<__half2*>(dyr + 2) = __floats2half2_rn(y2, 0.f);
+#pragma unroll
+      for (int k = 4; k < kW3TPad; k += 2) *reinterpret_cast<__half2*>(dyr + k) = __float2half2_rn(0.f);
+      if (valid) *reinterpret_cast<uint4*>(a.dY8 + i * 8) = *reinterpret_cast<const uint4*>(dyr);
+    }
+    __syncwarp();
+    // ---- forward recompute ----
+    {
+      float acc[2][8][4];
+      warp_layer<8, kIn / 16, kInPad, kInPad>(sl.a, sm.W1, acc, lane);
+      store_relu_half<8, kHidPad>(acc, sl.b, lane);
+      __syncwarp();
+      warp_layer<8, kHid / 16, kHidPad, kHidPad>(sl.b, sm.W2, acc, lane);
+      store_relu_half<8, kHidPad>(acc, sl.c, lane);
+      __syncwarp();
+      if (valid) { copy_row16(a.H1 + i * kHid, sl.b + lane * kHidPad, kHid * 2); copy_row16(a.H2 + i * kHid, sl.c + lane * kHidPad, kHid * 2); }
+      // ---- dH2 = (dY W3) . [H2 > 0]  -> sl.a (X is not needed any more) ----
+      warp_layer<8, 1, kW3TPad, kW3TPad>(sl.dy, sm.W3T, acc, lane);
+      __syncwarp();
+      store_masked_half<8, kHidPad>(acc, sl.c, sl.a, lane);       // rows of sl.a re-strided to kHidPad
+      __syncwarp();
+      if (valid) copy_row16(a.dH2 + i * kHid, sl.a + lane * kHidPad, kHid * 2);
+      // ---- dH1 = (dH2 W2) . [H1 > 0]  -> sl.c ----
+      warp_layer<8, kHid / 16, kHidPad, kHidPad>(sl.a, sm.W2T, acc, lane);
+      __syncwarp();
+      store_masked_half<8, kHidPad>(acc, sl.b, sl.c, lane);
+      __syncwarp();
+      if (valid) copy_row16(a.dH1 + i * kHid, sl.c + lane * kHidPad, kHid * 2);
+    }
+    // ---- dX = dH1 W1 -> sl.a (stride kInPad) ----
+    {
+      float accx[2][kIn / 8][4];
+      warp_layer<kIn / 8, kHid / 16, kHidPad, kHidPad>(sl.c, sm.W1T, accx, lane);
+      __syncwarp();
+      store_half<kIn / 8, kInPad>(accx, sl.a, lane);
+    }
+    __syncwarp();
+    // ---- per sample: everything that hangs off this row of dX ----
+    if (valid) {
+      const __half* dx = sl.a + lane * kInPad;
+      const long long ray = i / a.S;
+      const float zm = a.z_mid[i];
+      float pt[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(a.rays_o[ray * 3 + c], __fmul_rn(a.rays_d[ray * 3 + c], zm));
+      // embedding: d/d(arg) sin(arg) = cos(arg) = sin(arg + pi/2)
+      alignas(16) __half e[40];
+#pragma unroll
+      for (int j = 0; j < 33; ++j) {
+        const float arg = pt[0] * sm.colB[j] + pt[1] * sm.colB[33 + j] + pt[2] * sm.colB[66 + j];
+        e[j] = __float2half_rn(__half2float(dx[j]) * fast_sin(arg + 1.57079632679489662f));
+      }
+#pragma unroll
+      for (int j = 33; j < 40; ++j) e[j] = __float2half_rn(0.f);
+      copy_row16(a.dE + i * 40, e, 80);
+      // normal
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a.d_gt[i * 3 + c] = a.d_g[i * 3 + c] + __half2float(dx[33 + c]) * inv_sc;
+      // sdf_layer output gradient [d sdf | d feat(31)]
+      alignas(16) __half o[32];
+      o[0] = __float2half_rn(a.d_s[i] * sc);
+#pragma unroll
+      for (int j = 1; j < 32; ++j) o[j] = dx[35 + j];
+      copy_row16(a.d_out + i * 32, o, 64);
+      // sdf_layer input row [x | enc | 1 | 0 0 0 0]  (the 1 makes the bias gradient a column of the same GEMM)
+      alignas(16) __half hrow[40];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) hrow[c] = __float2half_rn(a.pos[i * 3 + c]);
+      {
+        const uint4* es = reinterpret_cast<const uint4*>(a.enc + i * 32);
+        uint4 ev[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) ev[v] = es[v];
+        const __half* eh = reinterpret_cast<const __half*>(ev);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) hrow[3 + j] = eh[j];
+      }
+      hrow[35] = __float2half_rn(1.f);
+#pragma unroll
+      for (int j = 36; j < 40; ++j) hrow[j] = __float2half_rn(0.f);
+      copy_row16(a.h + i * 40, hrow, 80);
+      // positions as fp16 hi + lo (exact to 2^-22): the embedding matrix gradient is a GEMM over them
+      alignas(16) __half pl[8];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        pl[c] = __float2half_rn(pt[c]);
+        pl[3 + c] = __float2half_rn(pt[c] - __half2float(pl[c]));
+      }
+      pl[6] = pl[7] = __float2half_rn(0.f);
+      copy_row16(a.pts_hl + i * 8, pl, 16);
+    }
+    __syncwarp();
   }
 }
 
@@ -939,6 +1198,8 @@ int neus_device_init() {
   if (cudaMemcpyToSymbol(c_lvl, lc, sizeof(lc)) != cudaSuccess) return GOSLAM_ELAUNCH;
   if (cudaFuncSetAttribute(neus_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(Smem)) != cudaSuccess) return GOSLAM_ELAUNCH;
+  if (cudaFuncSetAttribute(neus_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(MlpBwdSmem)) != cudaSuccess) return GOSLAM_ELAUNCH;
   ready[dev] = true;
   return GOSLAM_OK;
 }
@@ -1022,16 +1283,43 @@ int goslam_neus_composite_backward(const goslam_neus_params* params, const float
   return GOSLAM_OK;
 }
 
+int goslam_neus_mlp_backward(const goslam_neus_params* params, const void* mlp_in, const void* enc, const float* pos,
+                             const float* d_mlp_out, const float* d_sdf, const float* d_grad, const float* rays_o,
+                             const float* rays_d, const float* z_mid, const float* scale, int R, int S,
+                             const goslam_neus_mlp_bwd_out* out, void* stream) {
+  if (!params || !mlp_in || !enc || !pos || !d_mlp_out || !d_sdf || !d_grad || !rays_o || !rays_d || !z_mid || !scale || !out ||
+      !out->H1 || !out->H2 || !out->dH1 || !out->dH2 || !out->dY8 || !out->dE || !out->d_out || !out->h || !out->pts_hl ||
+      !out->d_grad_total || R < 0 || S <= 0)
+    return GOSLAM_EINVAL;
+  if (R == 0) return GOSLAM_OK;
+  { const int rc = neus_device_init(); if (rc != GOSLAM_OK) return rc; }
+  MlpBwdArgs a{};
+  a.mlp_w = reinterpret_cast<const __half*>(params->mlp_w); a.color_B = params->color_B;
+  a.X = reinterpret_cast<const __half*>(mlp_in); a.enc = reinterpret_cast<const __half*>(enc); a.pos = pos;
+  a.d_y = d_mlp_out; a.d_s = d_sdf; a.d_g = d_grad; a.rays_o = rays_o; a.rays_d = rays_d; a.z_mid = z_mid; a.scale = scale;
+  a.H1 = reinterpret_cast<__half*>(out->H1); a.H2 = reinterpret_cast<__half*>(out->H2);
+  a.dH1 = reinterpret_cast<__half*>(out->dH1); a.dH2 = reinterpret_cast<__half*>(out->dH2);
+  a.dY8 = reinterpret_cast<__half*>(out->dY8); a.dE = reinterpret_cast<__half*>(out->dE);
+  a.d_out = reinterpret_cast<__half*>(out->d_out); a.h = reinterpret_cast<__half*>(out->h);
+  a.pts_hl = reinterpret_cast<__half*>(out->pts_hl); a.d_gt = out->d_grad_total;
+  a.n = (long long)R * S; a.S = S;
+  const long long tiles = (a.n + 31) / 32;
+  const long long blocks = (tiles + kMbWarps - 1) / kMbWarps;
+  neus_mlp_bwd_kernel<<<(unsigned)(blocks < 148 ? blocks : 148), kMbWarps * 32, sizeof(MlpBwdSmem), (cudaStream_t)stream>>>(a);
+  GS_CHECK_LAUNCH();
+  return GOSLAM_OK;
+}
+
 int goslam_neus_grid_backward(const goslam_neus_params* params, const float* rays_o, const float* rays_d,
                               const float* z_vals, const float* dists, int R, int S, const float* d_enc,
-                              const float* d_grad, float* grid_grad, float* d_w0, void* stream) {
+                              const float* d_enc_scale, const float* d_grad, float* grid_grad, float* d_w0, void* stream) {
   if (!params || !rays_o || !rays_d || !z_vals || !dists || !d_enc || !d_grad || !grid_grad || !d_w0 || R < 0 || S <= 0)
     return GOSLAM_EINVAL;
   if (R == 0) return GOSLAM_OK;
   { const int rc = neus_device_init(); if (rc != GOSLAM_OK) return rc; }
   GridBwdArgs a{};
   a.p = *params; a.rays_o = rays_o; a.rays_d = rays_d; a.z_vals = z_vals; a.dists = dists;
-  a.d_enc = d_enc; a.d_grad = d_grad; a.grid_grad = grid_grad; a.d_w0 = d_w0;
+  a.d_enc = d_enc; a.d_enc_scale = d_enc_scale; a.d_grad = d_grad; a.grid_grad = grid_grad; a.d_w0 = d_w0;
   a.n = (long long)R * S; a.S = S;
   const long long blocks = (a.n + 255) / 256;
   if (blocks > 0x7fffffffLL) return GOSLAM_EINVAL;

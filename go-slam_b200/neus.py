@@ -15,8 +15,8 @@ reference checkpoint (go.ckpt 'mapping_net') holds:
     variance_network.variance
 Under `torch.no_grad()` the forward pass is the inference path.  With grad enabled (what
 Mapper.optimize_map does, src/mapping.py:89-91) the same fused kernel keeps its per-sample intermediates and the
-returned tensors carry a grad_fn: `loss.backward()` runs goslam_neus_composite_backward, the colour network's GEMMs
-(cuBLAS, fp32) and goslam_neus_grid_backward, and fills `.grad` of the hash grid, sdf_layer, colour `_B`, colour
+returned tensors carry a grad_fn: `loss.backward()` runs goslam_neus_composite_backward, goslam_neus_mlp_backward, the
+weight-gradient GEMMs (cuBLAS) and goslam_neus_grid_backward, and fills `.grad` of the hash grid, sdf_layer, colour `_B`, colour
 network and variance parameters.  Differentiable outputs: color, depth, sdf, gradient_error; the other
 keys are returned detached (the reference's losses use depth_variance detached and never read normal / weight_sum).
 """
@@ -285,9 +285,10 @@ class _NeusFunction(torch.autograd.Function):
     """InstantNeuS.forward as one autograd node (what autograd + tiny-cuda-nn do for the reference,
     src/InstantNeuS.py:295-370 under torch.enable_grad() in src/mapping.py:89-91).
     forward : the fused marcher with its per-sample intermediates kept.
-    backward: goslam_neus_composite_backward -> colour-network GEMMs (cuBLAS, fp32 on the fp16 activations the
-              forward used) -> sdf_layer / colour-embedding GEMMs -> goslam_neus_grid_backward (hash-grid scatter +
-              the second-order path through the analytic normal).  Chunked over rays to bound the activations."""
+    backward: goslam_neus_composite_backward -> goslam_neus_mlp_backward (row-wise colour-network backward on mma.sync)
+              -> weight-gradient GEMMs over the sample dimension (cuBLAS, fp16 in / fp32 out, loss scale)
+              -> goslam_neus_grid_backward (hash-grid scatter + the second-order path through the analytic normal).
+              Chunked over rays to bound the activations."""
     CHUNK_RAYS = 1 << 16
     KEYS = ('color', 'depth', 'sdf', 'gradient_error', 'depth_variance', 'normal', 'weight_sum', 'z_vals', 'sdf_variance')
 
@@ -325,12 +326,7 @@ class _NeusFunction(torch.autograd.Function):
         # the cast to half (mean-reduced losses give ~1e-6 entries, fp16's smallest normal is 6e-5), weight gradients
         # accumulate in fp32 (mm out_dtype) and are divided by the scale at the end.  No host synchronisation.
         f16 = dict(dtype=torch.float16, device=dev)
-        Wh = mlp.half()
-        W1 = Wh[:MLP_HID * MLP_IN_PAD].view(MLP_HID, MLP_IN_PAD)
-        W2 = Wh[MLP_HID * MLP_IN_PAD:MLP_HID * MLP_IN_PAD + MLP_HID * MLP_HID].view(MLP_HID, MLP_HID)
-        W3 = Wh[MLP_HID * MLP_IN_PAD + MLP_HID * MLP_HID:].view(MLP_OUT_PAD, MLP_HID)
         Wsdf_enc = sdf_w.float()[:, 3:].half().contiguous()                      # [32, 32]
-        colB = color_B.float()
         g_grid = torch.zeros(net.sdf_network.encoding.encoding.params.numel(), **f32)
         g_W1 = torch.zeros(MLP_HID, MLP_IN_PAD, **f32)
         g_W2 = torch.zeros(MLP_HID, MLP_HID, **f32)
@@ -358,44 +354,34 @@ class _NeusFunction(torch.autograd.Function):
                     _lib.ptr(d_y), _lib.ptr(d_s), _lib.ptr(d_g), _lib.ptr(g_inv_s), _lib.stream_ptr())
                 _lib.check(rc, "neus_composite_backward")
                 amax = torch.maximum(d_y.abs().max(), d_s.abs().max()).clamp_min(1e-30)
-                sc = torch.exp2(torch.floor(torch.log2(1024.0 / amax))).clamp(max=2.0 ** 40)     # device scalar
-                # ---- colour network (tcnn FullyFusedMLP: no biases, ReLU, half activations) ----
+                sc = torch.exp2(torch.floor(torch.log2(1024.0 / amax))).clamp(max=2.0 ** 40).reshape(1).contiguous()   # device scalar
+                # ---- colour network, row-wise half (one kernel): H1, H2, dH2, dH1, dX and what hangs off dX per sample ----
                 X = mlp_in[sl].reshape(n, MLP_IN_PAD)                                 # half, as the forward built it
-                H1 = torch.relu(X @ W1.t())
-                H2 = torch.relu(H1 @ W2.t())
-                dY = torch.zeros(n, 8, **f16)
-                dY[:, :3] = d_y * sc
-                g_W3[:8] += torch.mm(dY.t(), H2, out_dtype=torch.float32) / sc
-                relu_bwd = torch.ops.aten.threshold_backward                         # grad where activation > 0, one kernel
-                dH2 = relu_bwd(dY @ W3[:8], H2, 0)
-                g_W2 += torch.mm(dH2.t(), H1, out_dtype=torch.float32) / sc
-                dH1 = relu_bwd(dH2 @ W2, H1, 0)
-                del dH2, H2
-                g_W1 += torch.mm(dH1.t(), X, out_dtype=torch.float32) / sc
-                dX = dH1 @ W1                                                          # [n, 80] half, scaled
-                del dH1, H1
-                # ---- colour embedding sin(pts @ B) ----
-                pts = (ro[:, None, :] + rd[:, None, :] * z_mid[sl][:, :, None]).reshape(n, 3)
-                dE = torch.zeros(n, 40, **f16)                                        # 33 columns padded to a multiple of 8
-                dE[:, :33] = dX[:, :33] * torch.cos(pts @ colB).half()
-                pt8 = torch.zeros(2, n, 8, **f16)                                     # pts as fp16 hi + lo parts (exact to 2^-22)
-                pt8[0, :, :3] = pts
-                pt8[1, :, :3] = pts - pt8[0, :, :3].float()
-                g_B += (torch.mm(pt8[0].t(), dE, out_dtype=torch.float32) + torch.mm(pt8[1].t(), dE, out_dtype=torch.float32))[:3, :33] / sc
-                # ---- sdf_layer: out = W h + b, h = [xn | enc]; sdf = out[0], feat = out[1:] ----
+                H1, H2, dH1, dH2 = (torch.empty(n, MLP_HID, **f16) for _ in range(4))
+                dY8, pts_hl = torch.empty(n, 8, **f16), torch.empty(n, 8, **f16)
+                dE, h = torch.empty(n, 40, **f16), torch.empty(n, 40, **f16)
                 d_out = torch.empty(n, 32, **f16)
-                d_out[:, 0] = d_s * sc
-                d_out[:, 1:] = dX[:, 36:67]
-                h = torch.zeros(n, 40, **f16)                                          # K padded to a multiple of 8
-                h[:, :3] = pos[sl].reshape(n, 3)
-                h[:, 3:35] = enc[sl].reshape(n, 32)
-                g_sdf_w += torch.mm(d_out.t(), h, out_dtype=torch.float32)[:, :35] / sc
-                g_sdf_b += d_out.float().sum(0) / sc
-                d_enc = torch.mm(d_out, Wsdf_enc, out_dtype=torch.float32) / sc       # [n, 32] f32
-                d_gt = d_g + dX[:, 33:36].float() / sc                                # normal: alpha + eikonal + colour input
-                del dX, d_out, h
+                d_gt = torch.empty(n, 3, **f32)
+                mo = _lib.NeusMlpBwdOut()
+                mo.H1, mo.H2, mo.dH1, mo.dH2 = H1.data_ptr(), H2.data_ptr(), dH1.data_ptr(), dH2.data_ptr()
+                mo.dY8, mo.dE, mo.d_out, mo.h = dY8.data_ptr(), dE.data_ptr(), d_out.data_ptr(), h.data_ptr()
+                mo.pts_hl, mo.d_grad_total = pts_hl.data_ptr(), d_gt.data_ptr()
+                rc = lib.goslam_neus_mlp_backward(ctypes.byref(p), _lib.ptr(X), _lib.ptr(enc[sl]), _lib.ptr(pos[sl]), _lib.ptr(d_y),
+                                                  _lib.ptr(d_s), _lib.ptr(d_g), _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(z_mid[sl]),
+                                                  _lib.ptr(sc), r1 - r0, S, ctypes.byref(mo), _lib.stream_ptr())
+                _lib.check(rc, "neus_mlp_backward")
+                # ---- weight gradients: GEMMs over the sample dimension (cuBLAS, fp16 in, fp32 out) ----
+                g_W3[:8] += torch.mm(dY8.t(), H2, out_dtype=torch.float32) / sc
+                g_W2 += torch.mm(dH2.t(), H1, out_dtype=torch.float32) / sc
+                g_W1 += torch.mm(dH1.t(), X, out_dtype=torch.float32) / sc
+                gb = torch.mm(pts_hl.t(), dE, out_dtype=torch.float32)                 # colour embedding sin(pts @ B)
+                g_B += (gb[:3, :33] + gb[3:6, :33]) / sc
+                gs = torch.mm(d_out.t(), h, out_dtype=torch.float32) / sc               # sdf_layer: out = W h + b
+                g_sdf_w += gs[:, :35]
+                g_sdf_b += gs[:, 35]
+                d_enc = torch.mm(d_out, Wsdf_enc, out_dtype=torch.float32)             # [n, 32] f32, still scaled
                 rc = lib.goslam_neus_grid_backward(ctypes.byref(p), _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(zv), _lib.ptr(ds),
-                                                   r1 - r0, S, _lib.ptr(d_enc), _lib.ptr(d_gt), _lib.ptr(g_grid),
+                                                   r1 - r0, S, _lib.ptr(d_enc), _lib.ptr(sc), _lib.ptr(d_gt), _lib.ptr(g_grid),
                                                    _lib.ptr(g_w0), _lib.stream_ptr())
                 _lib.check(rc, "neus_grid_backward")
         g_sdf_w[0] += g_w0

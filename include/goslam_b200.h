@@ -315,7 +315,7 @@ int goslam_neus_forward(const goslam_neus_params* params, const float* rays_o,
  *        d_grad [R,S,3] (w.r.t. the SDF normal: alpha path + eikonal), d_inv_s [1] (ACCUMULATED: zero it first).
  *   Samples outside the real-time bound get zeros (the forward gives them constants).  S <= 128.
  *
- * goslam_neus_grid_backward — per sample: scatters dL/d(encoding) [R*S,32] and the part of dL/d(normal) [R*S,3] that
+ * goslam_neus_grid_backward — per sample: scatters dL/d(encoding) [R*S,32] (divided by *d_enc_scale when given) and the part of dL/d(normal) [R*S,3] that
  *   flows through the hash grid into grid_grad [n_params] f32 (ACCUMULATED), and accumulates into d_w0 [35] the gradient
  *   of row 0 of sdf_layer.weight THROUGH THE NORMAL (normal = (W0[:3] + 0.5 * d enc/d u . W0[3:]) * 2/(b1-b0)), i.e. the
  *   second-order path autograd takes with create_graph=True (src/InstantNeuS.py:139-146).  The direct path
@@ -328,7 +328,28 @@ int goslam_neus_composite_backward(const goslam_neus_params* params, const float
                                    float* d_inv_s, void* stream);
 int goslam_neus_grid_backward(const goslam_neus_params* params, const float* rays_o, const float* rays_d,
                               const float* z_vals, const float* dists, int R, int S, const float* d_enc,
-                              const float* d_grad, float* grid_grad, float* d_w0, void* stream);
+                              const float* d_enc_scale, const float* d_grad, float* grid_grad, float* d_w0, void* stream);
+/* goslam_neus_mlp_backward — the row-wise half of the colour network's backward (tcnn FullyFusedMLP 80->64->64->16, no
+ * biases, ReLU, fp16) in one pass per 32-sample warp tile on mma.sync: recomputes H1, H2 from the kept input rows,
+ * dH2 = (dY W3).[H2>0], dH1 = (dH2 W2).[H1>0], dX = dH1 W1, and from dX per sample: dE = dX[:33] cos(p B) (embedding),
+ * d_grad_total = d_grad + dX[33:36] (normal), d_out = [d_sdf | dX[36:67]] (sdf_layer output), h = [x | enc | 1] (sdf_layer
+ * input, the 1 carries the bias gradient) and the fp16 hi/lo split of the sample positions.  Gradient operands are
+ * multiplied by *scale (a power of two chosen by the caller so that fp16 does not underflow) before the cast to half;
+ * every fp16 output is in scaled units, d_grad_total is unscaled f32.  Left to the caller: the weight-gradient GEMMs over
+ * the sample dimension (dY8^T H2, dH2^T H1, dH1^T X, pts_hl^T dE, d_out^T h) and d_enc = d_out W_sdf[:,3:]. */
+typedef struct goslam_neus_mlp_bwd_out {
+  void* H1; void* H2; void* dH1; void* dH2;   /* f16 [R*S,64] */
+  void* dY8;                                  /* f16 [R*S,8]  scaled dL/d(MLP output), 3 columns used */
+  void* dE;                                   /* f16 [R*S,40] 33 columns used */
+  void* d_out;                                /* f16 [R*S,32] */
+  void* h;                                    /* f16 [R*S,40] 36 columns used */
+  void* pts_hl;                               /* f16 [R*S,8]  hi(3) | lo(3) */
+  float* d_grad_total;                        /* f32 [R*S,3] */
+} goslam_neus_mlp_bwd_out;
+int goslam_neus_mlp_backward(const goslam_neus_params* params, const void* mlp_in, const void* enc, const float* pos,
+                             const float* d_mlp_out, const float* d_sdf, const float* d_grad, const float* rays_o,
+                             const float* rays_d, const float* z_mid, const float* scale, int R, int S,
+                             const goslam_neus_mlp_bwd_out* out, void* stream);
 /* hash-grid geometry helper (host side, no GPU): fills offsets[17] (in PARAMS, i.e.
  * entries*2), resolutions[16], scales[16]; returns total number of f16 params. */
 int64_t goslam_hashgrid_layout(int64_t* offsets, int* resolutions, float* scales);
