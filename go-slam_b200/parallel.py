@@ -382,3 +382,65 @@ def sharded_distance(poses, disps, intrinsics, ii, jj, beta=0.3, bidirectional=T
         return sharded_pairs(one_way, ii, jj, group)
     return sharded_pairs(lambda a, b: droid_backends.frame_distance_bidirectional(poses, disps, intrinsics, a, b, beta),
                          ii, jj, group)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Data-parallel mapping step ("multi-GPU adds an all-reduce of grid grads").  Rays are independent: every rank
+# renders and back-propagates its slice of the ray batch; the losses are written in SUM form over the GLOBAL counts so that the
+# SUM of the ranks' gradients is exactly the gradient of the reference's single-process loss on the whole batch
+# (src/mapping.py:97-128), whatever the split and however many rays of a slice have no sensor depth.
+# ---------------------------------------------------------------------------------------------------------------
+def ray_slice(n_rays, group=None):
+    """contiguous, balanced slice [lo, hi) of a ray batch for this rank"""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per, rem = divmod(int(n_rays), world)
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+def mapping_loss_local(net, out, rays_color, rays_depth, n_rays_global, w_color, w_sdf, w_eikonal, uncertainty_based=True,
+                       group=None):
+    """this rank's share of Mapper.optimize_map's total loss (src/mapping.py:97-128) on its ray slice: color / depth / sdf
+    terms are sums over the slice's valid rays divided by the GLOBAL number of valid rays (one tiny all-reduce of the
+    count), the eikonal term is the slice's gradient_error weighted by its share of the samples.  Summed over the ranks
+    this IS the reference's loss on the whole batch; so are the gradients after `allreduce_gradients`."""
+    depth = rays_depth.reshape(-1, 1)
+    valid = (depth > 0).reshape(-1)
+    n_valid = valid.sum().to(torch.float32).reshape(1)
+    if dist.get_world_size(group) > 1:
+        dist.all_reduce(n_valid, op=dist.ReduceOp.SUM, group=group)
+    n_valid = n_valid.clamp_min(1.0)
+    unc = 1.0 / torch.sqrt(out["depth_variance"][valid].detach() + 1e-10)
+    if not uncertainty_based:
+        unc = torch.ones_like(unc)
+    total = torch.abs(out["color"][valid] - rays_color[valid]).sum() / (3.0 * n_valid) * w_color
+    total = total + (torch.abs(out["depth"][valid] - depth[valid]) * unc).sum() / n_valid
+    if w_sdf > 0 and bool(valid.any()):
+        n_local = valid.sum().to(torch.float32)
+        sdf_loss, sparse_loss = net.compute_sdf_error(sdf=out["sdf"][valid], z_vals=out["z_vals"][valid], gt_depth=depth[valid])
+        total = total + (sdf_loss + sparse_loss) * (n_local / n_valid) * w_sdf          # its means are over the local valid rays
+    if w_eikonal > 0:
+        total = total + w_eikonal * out["gradient_error"].mean() * (float(rays_depth.numel()) / float(n_rays_global))
+    return total.reshape(())
+
+
+def allreduce_gradients(params, group=None):
+    """SUM the .grad of `params` over the ranks: the small tensors travel as one flat buffer, every tensor above 1 M elements
+    (the 12.6 M-entry hash grid) on its own.  Parameters without a gradient on some rank count as zero."""
+    if dist.get_world_size(group) == 1:
+        return
+    params = [p for p in params]
+    small = [p for p in params if p.numel() <= (1 << 20)]
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    if small:
+        flat = torch.cat([p.grad.reshape(-1) for p in small])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        o = 0
+        for p in small:
+            p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad))
+            o += p.numel()
+    for p in params:
+        if p.numel() > (1 << 20):
+            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
