@@ -672,7 +672,8 @@ def mapping_leg(dev, rank, world, steps, barrier):
     on 2^16 rays x 72 samples PER RANK (the reference samples ~4.4 k pixels per iteration; the batch here is sized to fill the
     GPU).  Also the reference-sized batch.  N > 1: data parallel (parallel.mapping_loss_local / allreduce_gradients)."""
     from goslam_b200 import parallel, synthetic
-    net, _, _ = make_renderer(dev, 43)               # the same initial weights on every rank (data parallel)
+    net, _, _ = make_renderer(dev, 43)
+    parallel.broadcast_parameters(list(net.parameters()))          # data parallel: every replica starts from rank 0's weights
     out = {}
     for tag, R in (("rays_65536", 1 << 16), ("rays_4096", 1 << 12)):
         ro, rd, zv, ds = [t.to(dev) for t in synthetic.make_rays(R, S=SAMPLES, seed=47 + rank)]

@@ -424,6 +424,15 @@ def mapping_loss_local(net, out, rays_color, rays_depth, n_rays_global, w_color,
     return total.reshape(())
 
 
+def broadcast_parameters(params, src=0, group=None):
+    """every replica starts from rank `src`'s parameters (also the ones no loss term touches: weight decay moves them)"""
+    if dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for p in params:
+            dist.broadcast(p.data, src=src, group=group)
+
+
 def allreduce_gradients(params, group=None):
     """SUM the .grad of `params` over the ranks: the small tensors travel as one flat buffer, every tensor above 1 M elements
     (the 12.6 M-entry hash grid) on its own.  Parameters without a gradient on some rank count as zero."""
