@@ -390,9 +390,16 @@ def sharded_distance(poses, disps, intrinsics, ii, jj, beta=0.3, bidirectional=T
 # SUM of the ranks' gradients is exactly the gradient of the reference's single-process loss on the whole batch
 # (src/mapping.py:97-128), whatever the split and however many rays of a slice have no sensor depth.
 # ---------------------------------------------------------------------------------------------------------------
+def _world_rank(group=None):
+    """(world, rank); a process that never initialised torch.distributed is one rank"""
+    if not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
 def ray_slice(n_rays, group=None):
     """contiguous, balanced slice [lo, hi) of a ray batch for this rank"""
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world, rank = _world_rank(group)
     per, rem = divmod(int(n_rays), world)
     lo = rank * per + min(rank, rem)
     return lo, lo + per + (1 if rank < rem else 0)
@@ -407,7 +414,7 @@ def mapping_loss_local(net, out, rays_color, rays_depth, n_rays_global, w_color,
     depth = rays_depth.reshape(-1, 1)
     valid = (depth > 0).reshape(-1)
     n_valid = valid.sum().to(torch.float32).reshape(1)
-    if dist.get_world_size(group) > 1:
+    if _world_rank(group)[0] > 1:
         dist.all_reduce(n_valid, op=dist.ReduceOp.SUM, group=group)
     n_valid = n_valid.clamp_min(1.0)
     unc = 1.0 / torch.sqrt(out["depth_variance"][valid].detach() + 1e-10)
@@ -426,7 +433,7 @@ def mapping_loss_local(net, out, rays_color, rays_depth, n_rays_global, w_color,
 
 def broadcast_parameters(params, src=0, group=None):
     """every replica starts from rank `src`'s parameters (also the ones no loss term touches: weight decay moves them)"""
-    if dist.get_world_size(group) == 1:
+    if _world_rank(group)[0] == 1:
         return
     with torch.no_grad():
         for p in params:
@@ -436,7 +443,7 @@ def broadcast_parameters(params, src=0, group=None):
 def allreduce_gradients(params, group=None):
     """SUM the .grad of `params` over the ranks: the small tensors travel as one flat buffer, every tensor above 1 M elements
     (the 12.6 M-entry hash grid) on its own.  Parameters without a gradient on some rank count as zero."""
-    if dist.get_world_size(group) == 1:
+    if _world_rank(group)[0] == 1:
         return
     params = [p for p in params]
     small = [p for p in params if p.numel() <= (1 << 20)]

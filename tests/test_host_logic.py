@@ -220,3 +220,15 @@ def test_synthetic_true_reprojection_matches_oracle():
         ref, _ = geom_oracle.reproject(sc["poses"].numpy(), sc["disps"].numpy(), sc["intrinsics"].numpy(),
                                        sc["ii"].numpy(), sc["jj"].numpy())
         np.testing.assert_allclose(synthetic.true_reprojection(sc).numpy(), ref, rtol=1e-6, atol=1e-5)
+
+
+def test_data_parallel_helpers_are_no_ops_without_a_process_group():
+    """bench.py's mapping leg calls them at N = 1 without torch.distributed initialised"""
+    import torch
+    from goslam_b200 import parallel
+    assert parallel.ray_slice(10) == (0, 10)
+    p = torch.nn.Parameter(torch.ones(3))
+    p.grad = torch.full((3,), 2.0)
+    parallel.broadcast_parameters([p])
+    parallel.allreduce_gradients([p])
+    assert torch.equal(p.grad, torch.full((3,), 2.0))
