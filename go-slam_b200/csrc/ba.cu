@@ -102,84 +102,141 @@ size_t ba_layout(const BaDims& d, void* base, size_t cap, BaWs* ws) {
 // ------------------------------------------------------------------------------------
 // Graph tables.  One block; everything is indexed by frame id so "sorted unique" is a
 // prefix sum over a presence bitmap (frame order == sorted order, as torch::_unique gives).
+// All prefix sums are block-wide scans (warp shuffles + one shared-memory hop), the per-frame
+// degree is counted with shared-memory atomics, the CSR keeps the edges of a frame in edge-index
+// order (stable: the linearisation's summation order does not depend on thread scheduling).
+// Round 1 did the scans and the Schur tables in thread 0 (chains of dependent global loads).
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+constexpr int kPrepThreads = 1024;
+constexpr int kPrepMaxFrames = 4 * kPrepThreads;       // == the 4096 of make_dims
+
+// in-place exclusive scan of a[0..n) in shared memory, n <= 4 * blockDim.x; returns the total.  All threads call.
+__device__ int prep_excl_scan(int* a, int n, int* wsum /* [33] */) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int base = tid * per;
+  int loc[4], s = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    loc[q] = s;
+    if (q < per && base + q < n) s += a[base + q];
+  }
+  int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = lane < ((int)blockDim.x >> 5) ? wsum[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    wsum[lane] = winc - w;
+    if (lane == 31) wsum[32] = winc;
+  }
+  __syncthreads();
+  const int off = wsum[warp] + inc - s;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (q < per && base + q < n) a[base + q] = off + loc[q];
+  const int total = wsum[32];
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(kPrepThreads)
 ba_prep_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, BaDims d, BaWs ws, int zero,
                int eta_rows) {
-  extern __shared__ int sm[];          // [num] scratch
+  extern __shared__ int sm[];          // a[num] | b[num + 1] | c[num] | wsum[33]
   const int tid = threadIdx.x, nt = blockDim.x;
   if (zero) {                          // single-kernel driver: reduced system and grid-barrier counter start at 0
     const size_t nsys = (size_t)d.n * d.n + d.n;
     for (size_t i = tid; i < nsys; i += nt) ws.sys[i] = 0.0;
     if (tid == 0) ws.counts[3] = 0;
   }
-  int* present = sm;
-  for (int f = tid; f < d.num; f += nt) present[f] = (f >= d.t0 && f < d.t1) ? 1 : 0;
+  int* a = sm;                         // presence -> entries per slot -> entry_ptr
+  int* b = sm + d.num;                 // degree -> row_ptr (kept)
+  int* c = b + d.num + 1;              // slot scan -> pairs per slot -> pair_ptr
+  int* wsum = c + d.num;
+  for (int f = tid; f < d.num; f += nt) { a[f] = (f >= d.t0 && f < d.t1) ? 1 : 0; b[f] = 0; }
   __syncthreads();
   for (int e = tid; e < d.N; e += nt) {
     const int f = (int)ii[e];
-    if (f >= 0 && f < d.num) present[f] = 1;     // benign race, all write 1
+    if (f >= 0 && f < d.num) { a[f] = 1; atomicAdd(&b[f], 1); }     // presence: benign race, all write 1
     ws.edge_j[e] = (int)jj[e];
   }
   __syncthreads();
-  // serial scans by thread 0 are fine: num <= 4096, once per BA call.
+  // ---- depth slots: frames of [t0,t1) U ii in sorted order ----
+  for (int f = tid; f < d.num; f += nt) c[f] = a[f];
+  __syncthreads();
+  const int M = prep_excl_scan(c, d.num, wsum);
+  for (int f = tid; f < d.num; f += nt) {
+    if (a[f]) { ws.slot_of_frame[f] = c[f]; ws.kx[c[f]] = f; }
+    else ws.slot_of_frame[f] = -1;
+  }
   if (tid == 0) {
-    int m = 0;
-    for (int f = 0; f < d.num; ++f) {
-      if (present[f]) { ws.slot_of_frame[f] = m; ws.kx[m] = f; ++m; }
-      else ws.slot_of_frame[f] = -1;
-    }
-    ws.counts[0] = m;
+    ws.counts[0] = M;
     // eta must have one row (broadcast), one row per depth slot (the reference's
     // `damping[unique(cat(arange(t0,t1), ii))]`, src/factor_graph.py:236-238) or — negative
     // eta_rows — one row per FRAME.  Anything else is a caller bug that the reference reports as a
     // broadcast error (src/lib/droid_kernels.cu:1397); here the call becomes a no-op with status 2.
-    ws.counts[4] = (eta_rows == 0 || eta_rows == 1 || eta_rows == m || eta_rows == -d.num) ? 0 : 1;
+    ws.counts[4] = (eta_rows == 0 || eta_rows == 1 || eta_rows == M || eta_rows == -d.num) ? 0 : 1;
   }
+  // ---- CSR over source frames, edges of a frame in edge-index order ----
+  const int n_listed = prep_excl_scan(b, d.num, wsum);
+  if (tid == 0) b[d.num] = n_listed;
   __syncthreads();
-  // CSR: one thread per frame scans the edge list => stable (edge-index) order
-  for (int f = tid; f < d.num; f += nt) {
-    int c = 0;
-    for (int e = 0; e < d.N; ++e) c += ((int)ii[e] == f);
-    present[f] = c;                     // reuse as per-frame degree
+  for (int f = tid; f <= d.num; f += nt) ws.row_ptr[f] = b[f];
+  for (int e = tid; e < d.N; e += nt) {
+    const int f = (int)ii[e];
+    if (f < 0 || f >= d.num) continue;
+    int rank = 0;
+    for (int q = 0; q < e; ++q) rank += ((int)ii[q] == f);          // stable position inside the frame's run
+    ws.edge_idx[b[f] + rank] = e;
   }
-  __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int f = 0; f < d.num; ++f) { ws.row_ptr[f] = acc; acc += present[f]; }
-    ws.row_ptr[d.num] = acc;
-  }
-  __syncthreads();
-  for (int f = tid; f < d.num; f += nt) {
-    int o = ws.row_ptr[f];
-    if (present[f] > 0)
-      for (int e = 0; e < d.N; ++e)
-        if ((int)ii[e] == f) ws.edge_idx[o++] = e;
-  }
-  __syncthreads();
-  // Schur entries per slot: [E_i of the frame's own pose if optimised] + [E_ij of each
-  // outgoing edge whose target pose is optimised]  (schur_block graph, :1244-1253)
-  if (tid == 0) {
-    const int M = ws.counts[0];
-    int eo = 0, po = 0;
-    for (int k = 0; k < M; ++k) {
-      const int f = ws.kx[k];
-      ws.entry_ptr[k] = eo;
-      ws.pair_ptr[k] = po;
-      const int e0 = eo;
-      if (f >= d.t0 && f < d.t1) ws.entry_code[eo++] = -(f - d.t0 + 1);
-      for (int r = ws.row_ptr[f]; r < ws.row_ptr[f + 1]; ++r) {
-        const int e = ws.edge_idx[r];
-        const int j = (int)jj[e];
-        if (j >= d.t0 && j < d.t1) ws.entry_code[eo++] = e;
+  __syncthreads();                     // edge_idx (global) is read below by other threads of this block
+  // ---- Schur entries per slot: [E_i of the frame's own pose if optimised] + [E_ij of each outgoing edge whose
+  // target pose is optimised]  (schur_block graph, :1244-1253); pairs = ne (ne + 1) / 2 ----
+  for (int k = tid; k < d.num; k += nt) {
+    int ne = 0;
+    if (k < M) {
+      const int f = ws.kx[k];            // written by another thread of this block, visible after the barriers above
+      ne = (f >= d.t0 && f < d.t1) ? 1 : 0;
+      for (int r = b[f]; r < b[f + 1]; ++r) {
+        const int j = (int)jj[ws.edge_idx[r]];
+        ne += (j >= d.t0 && j < d.t1) ? 1 : 0;
       }
-      const int ne = eo - e0;
-      po += ne * (ne + 1) / 2;
     }
-    ws.entry_ptr[M] = eo;
-    ws.pair_ptr[M] = po;
-    ws.counts[1] = eo;
-    ws.counts[2] = po;
+    // (a and c are dead as presence / slot index from here on: their last readers are behind a barrier)
+    a[k] = ne;
+    c[k] = ne * (ne + 1) / 2;
+  }
+  __syncthreads();
+  const int n_entries = prep_excl_scan(a, d.num, wsum);
+  const int n_pairs = prep_excl_scan(c, d.num, wsum);
+  for (int k = tid; k < M; k += nt) {
+    const int f = ws.kx[k];
+    int eo = a[k];
+    ws.entry_ptr[k] = eo;
+    ws.pair_ptr[k] = c[k];
+    if (f >= d.t0 && f < d.t1) ws.entry_code[eo++] = -(f - d.t0 + 1);
+    for (int r = b[f]; r < b[f + 1]; ++r) {
+      const int e = ws.edge_idx[r];
+      const int j = (int)jj[e];
+      if (j >= d.t0 && j < d.t1) ws.entry_code[eo++] = e;
+    }
+  }
+  if (tid == 0) {
+    ws.entry_ptr[M] = n_entries;
+    ws.pair_ptr[M] = n_pairs;
+    ws.counts[1] = n_entries;
+    ws.counts[2] = n_pairs;
   }
 }
 
@@ -1510,6 +1567,8 @@ void ba_persistent_kernel_attrs(BaDevice* dv, int dev) {
   dv->blocks_per_sm = (!coop || occ < 1) ? 0 : (occ > kWant ? kWant : occ);
 }
 
+inline size_t prep_smem_bytes(int num) { return ((size_t)3 * num + 1 + 33) * sizeof(int); }
+
 const BaDevice& ba_device() {
   static BaDevice table[kMaxDevices];
   static std::mutex mu;
@@ -1519,6 +1578,7 @@ const BaDevice& ba_device() {
   std::lock_guard<std::mutex> lock(mu);
   BaDevice& dv = table[dev];
   if (!dv.ready) {
+    cudaFuncSetAttribute(ba_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem_bytes(kPrepMaxFrames));
     cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(((size_t)kSmemSolveMaxN * kSmemSolveMaxN + kSmemSolveMaxN) * 8));
     cudaFuncSetAttribute(ba_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1538,7 +1598,7 @@ int launch_phase1(const float* poses, const float* disps, const float* intr,
                   const BaDims& d, const BaWs& ws, int motion_only, bool prep, cudaStream_t st) {
   const BaIn in{poses, disps, intr, disps_sens, targets, weights, eta, eta_rows, ii, jj};
   if (prep) {
-    ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws, 0, motion_only ? 0 : eta_rows);
+    ba_prep_kernel<<<1, kPrepThreads, prep_smem_bytes(d.num), st>>>(ii, jj, d, ws, 0, motion_only ? 0 : eta_rows);
     GS_CHECK_LAUNCH();
   }
   cudaMemsetAsync(ws.sys, 0, ((size_t)d.n * d.n + d.n) * sizeof(double), st);
@@ -1638,7 +1698,7 @@ int goslam_ba(float* poses, float* disps, const float* intrinsics, const float* 
     if (blocks_per_sm > 0) {
       // two launches per call: the table kernel (which also zeroes the reduced system and the barrier
       // counter) and the cooperative kernel (which zeroes dz_out itself)
-      ba_prep_kernel<<<1, 1024, d.num * sizeof(int), st>>>(ii, jj, d, ws, 1, motion_only ? 0 : eta_rows);
+      ba_prep_kernel<<<1, kPrepThreads, prep_smem_bytes(d.num), st>>>(ii, jj, d, ws, 1, motion_only ? 0 : eta_rows);
       GS_CHECK_LAUNCH();
       unsigned* barrier = reinterpret_cast<unsigned*>(ws.counts + 3);
       BaIn in{poses, disps, intrinsics, disps_sens, targets, weights, eta, eta_rows, ii, jj};
