@@ -198,6 +198,6 @@ def test_backward_is_independent_of_ray_chunking(monkeypatch):
     for a, b in zip(*grads):
         scale = float(a.abs().max())
         assert scale > 0
-        # different loss scales per chunk and a different summation order: fp16-level agreement on the colour network,
-        # fp32-level elsewhere
-        assert float((a - b).abs().max()) <= 2e-3 * scale, (a.shape, float((a - b).abs().max()), scale)
+        # different loss scales per chunk and a different summation order (fp16 operands on the colour network, fp32
+        # reductions in scheduling order): a chunking bug (a wrong 1/(R*S), a dropped chunk) is an O(1) error, 1e-2 is ample
+        assert float((a - b).abs().max()) <= 1e-2 * scale, (a.shape, float((a - b).abs().max()), scale)
